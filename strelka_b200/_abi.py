@@ -1,0 +1,198 @@
+"""ctypes view of include/sb/sb_api.h (the C ABI) and numpy dtypes of its POD arrays.
+
+The layouts here are checked against sizeof() values exported by the library
+(tests/test_abi.py) so that a drift between the header and this file fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_NAME = "libstrelka_b200.so"
+
+
+class SbError(RuntimeError):
+    """Raised for every non-SB_OK result of the C ABI (the reference assert(0)s instead)."""
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, _LIB_NAME)
+
+
+# ---- numpy dtypes of the scene arrays (byte-identical to the structs in sb_api.h) -------------
+VERTEX_DTYPE = np.dtype(
+    [("pos", "<f4", (3,)), ("tangent", "<u4"), ("normal", "<u4"), ("uv", "<u4"), ("pad0", "<f4"), ("pad1", "<f4")]
+)
+MESH_DTYPE = np.dtype([("index", "<u4"), ("count", "<u4"), ("vb_offset", "<u4"), ("vertex_count", "<u4")])
+CURVE_DTYPE = np.dtype(
+    [
+        ("vertex_counts_start", "<u4"),
+        ("vertex_counts_count", "<u4"),
+        ("points_start", "<u4"),
+        ("points_count", "<u4"),
+        ("widths_start", "<u4"),
+        ("widths_count", "<u4"),
+    ]
+)
+INSTANCE_DTYPE = np.dtype(
+    [("transform", "<f4", (16,)), ("type", "<u4"), ("geom_id", "<u4"), ("material_id", "<u4"), ("light_id", "<u4")]
+)
+LIGHT_DTYPE = np.dtype(
+    [
+        ("points", "<f4", (4, 4)),
+        ("color", "<f4", (4,)),
+        ("normal", "<f4", (4,)),
+        ("type", "<i4"),
+        ("half_angle", "<f4"),
+        ("pad0", "<f4"),
+        ("pad1", "<f4"),
+    ]
+)
+MATERIAL_DTYPE = np.dtype(
+    [
+        ("model", "<u4"),
+        ("base_color", "<f4", (3,)),
+        ("roughness", "<f4"),
+        ("metallic", "<f4"),
+        ("ior", "<f4"),
+        ("opacity", "<f4"),
+        ("clearcoat", "<f4"),
+        ("clearcoat_roughness", "<f4"),
+        ("specular_color", "<f4", (3,)),
+        ("use_specular_workflow", "<u4"),
+        ("hair_absorption", "<f4", (3,)),
+        ("hair_roughness_lon", "<f4"),
+        ("hair_roughness_azi", "<f4"),
+        ("hair_cuticle_angle", "<f4"),
+        ("pad", "<f4", (4,)),
+    ]
+)
+HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4"), ("instance", "<u4"), ("kind", "<u4")])
+
+assert VERTEX_DTYPE.itemsize == 32 and MESH_DTYPE.itemsize == 16 and CURVE_DTYPE.itemsize == 24
+assert INSTANCE_DTYPE.itemsize == 80 and LIGHT_DTYPE.itemsize == 112 and MATERIAL_DTYPE.itemsize == 96
+assert HIT_DTYPE.itemsize == 24
+
+SB_INSTANCE_MESH, SB_INSTANCE_LIGHT, SB_INSTANCE_CURVE = 0, 1, 2
+SB_MATERIAL_DIFFUSE, SB_MATERIAL_USD_PREVIEW_SURFACE, SB_MATERIAL_HAIR = 0, 1, 2
+SB_FORMAT_UNSIGNED_BYTE4, SB_FORMAT_FLOAT4, SB_FORMAT_FLOAT3 = 0, 1, 2
+SB_CFG_TRAVERSAL_STATS = 1
+
+
+class sb_scene_view(C.Structure):
+    _fields_ = [
+        ("vertices", C.c_void_p), ("num_vertices", C.c_uint64),
+        ("indices", C.c_void_p), ("num_indices", C.c_uint64),
+        ("meshes", C.c_void_p), ("num_meshes", C.c_uint32),
+        ("curves", C.c_void_p), ("num_curves", C.c_uint32),
+        ("curve_points", C.c_void_p), ("num_curve_points", C.c_uint64),
+        ("curve_widths", C.c_void_p), ("num_curve_widths", C.c_uint64),
+        ("curve_vertex_counts", C.c_void_p), ("num_curve_vertex_counts", C.c_uint64),
+        ("instances", C.c_void_p), ("num_instances", C.c_uint32),
+        ("lights", C.c_void_p), ("num_lights", C.c_uint32),
+        ("materials", C.c_void_p), ("num_materials", C.c_uint32),
+    ]
+
+
+class sb_settings(C.Structure):
+    _fields_ = [
+        ("spp", C.c_uint32), ("spp_total", C.c_uint32), ("depth", C.c_uint32), ("enable_acc", C.c_uint32),
+        ("rect_light_sampling_method", C.c_uint32), ("debug", C.c_uint32),
+        ("shadow_ray_tmin", C.c_float), ("material_ray_tmin", C.c_float),
+        ("tonemapper_type", C.c_uint32), ("gamma", C.c_float),
+        ("film_iso", C.c_float), ("cm2_factor", C.c_float), ("f_stop", C.c_float), ("shutter_speed", C.c_float),
+        ("sample_offset", C.c_uint32), ("sample_stride", C.c_uint32),
+        ("reserved", C.c_uint32 * 4),
+    ]
+
+
+class sb_device_cfg(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_batch_paths", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class sb_counters(C.Structure):
+    _fields_ = [
+        ("paths", C.c_uint64), ("radiance_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
+        ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("segs_tested", C.c_uint64),
+        ("stack_overflows", C.c_uint64),
+        ("num_triangles", C.c_uint64), ("num_segments", C.c_uint64),
+        ("bvh_nodes_tri", C.c_uint64), ("bvh_nodes_curve", C.c_uint64),
+        ("build_ms", C.c_double), ("render_ms", C.c_double),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+# Every symbol include/sb/sb_api.h declares (tests/test_abi.py checks they are all exported).
+ABI_SYMBOLS = [
+    "sb_settings_default", "sb_create", "sb_destroy", "sb_last_error", "sb_set_scene", "sb_set_camera",
+    "sb_set_camera_matrices", "sb_set_settings", "sb_reset_accumulation", "sb_subframe_index",
+    "sb_buffer_create", "sb_buffer_destroy", "sb_buffer_resize", "sb_buffer_map", "sb_buffer_unmap",
+    "sb_buffer_host_ptr", "sb_buffer_host_size", "sb_buffer_device_ptr", "sb_buffer_width", "sb_buffer_height",
+    "sb_render", "sb_render_iterations", "sb_synchronize", "sb_accum_device_ptr", "sb_resolve",
+    "sb_get_counters", "sb_reset_counters", "sb_test_sampler", "sb_test_light_sample", "sb_test_trace",
+]
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load the CUDA backend.  Fails loudly when it has not been built (no fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise SbError(
+            f"{path} is missing: build the CUDA backend first (python -c 'import __graft_entry__ as g; g.build()' "
+            "or make -C strelka_b200/csrc). There is no CPU fallback."
+        )
+    lib = C.CDLL(path)
+    vp, u32, u64, f32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_float
+    P = C.POINTER
+    sig = {
+        "sb_settings_default": (None, [P(sb_settings)]),
+        "sb_create": (C.c_int, [P(sb_device_cfg), P(vp)]),
+        "sb_destroy": (None, [vp]),
+        "sb_last_error": (C.c_char_p, [vp]),
+        "sb_set_scene": (C.c_int, [vp, P(sb_scene_view)]),
+        "sb_set_camera": (C.c_int, [vp, P(f32), f32]),
+        "sb_set_camera_matrices": (C.c_int, [vp, P(f32), P(f32)]),
+        "sb_set_settings": (C.c_int, [vp, P(sb_settings)]),
+        "sb_reset_accumulation": (C.c_int, [vp]),
+        "sb_subframe_index": (u32, [vp]),
+        "sb_buffer_create": (C.c_int, [vp, u32, u32, u32, P(vp)]),
+        "sb_buffer_destroy": (None, [vp]),
+        "sb_buffer_resize": (C.c_int, [vp, u32, u32]),
+        "sb_buffer_map": (C.c_int, [vp, P(vp)]),
+        "sb_buffer_unmap": (C.c_int, [vp]),
+        "sb_buffer_host_ptr": (vp, [vp]),
+        "sb_buffer_host_size": (C.c_size_t, [vp]),
+        "sb_buffer_device_ptr": (vp, [vp]),
+        "sb_buffer_width": (u32, [vp]),
+        "sb_buffer_height": (u32, [vp]),
+        "sb_render": (C.c_int, [vp, vp]),
+        "sb_render_iterations": (C.c_int, [vp, vp, u32]),
+        "sb_synchronize": (C.c_int, [vp]),
+        "sb_accum_device_ptr": (vp, [vp, P(u64)]),
+        "sb_resolve": (C.c_int, [vp, vp, u32]),
+        "sb_get_counters": (C.c_int, [vp, P(sb_counters)]),
+        "sb_reset_counters": (C.c_int, [vp]),
+        "sb_test_sampler": (C.c_int, [vp, u32, vp, vp, vp, vp, vp, vp, vp]),
+        "sb_test_light_sample": (C.c_int, [vp, u32, vp, vp, vp, u32, vp]),
+        "sb_test_trace": (C.c_int, [vp, u32, vp, u32, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def np_ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data) if a is not None and a.size else C.c_void_p(0)

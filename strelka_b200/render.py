@@ -1,0 +1,271 @@
+"""Host-side mirror of the reference's render interface on top of the C ABI.
+
+Reference: include/render/render.h:9-63 (Render, RenderFactory, RenderType), include/render/buffer.h:
+9-88 (Buffer, BufferDesc, BufferFormat), include/render/common.h:22-28 (SharedContext).  Names,
+argument meaning and call order follow the reference so tests read like a Strelka client:
+
+    render = RenderFactory.createRender(RenderType.eCompute)
+    render.setScene(scene); render.setSharedContext(ctx); render.init()
+    buf = render.createBuffer(BufferDesc(w, h, BufferFormat.FLOAT4))
+    render.render(buf); buf.map(); pixels = buf.getHostPointer()
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _abi
+from ._abi import SbError, sb_counters, sb_device_cfg
+from .scene import Scene
+from .settings import SettingsManager
+
+
+class RenderType(enum.IntEnum):  # render.h:9-14
+    eOptiX = 0
+    eMetal = 1
+    eCompute = 2
+
+
+class BufferFormat(enum.IntEnum):  # buffer.h:9-14
+    UNSIGNED_BYTE4 = 0
+    FLOAT4 = 1
+    FLOAT3 = 2
+
+
+@dataclass
+class BufferDesc:  # buffer.h:16-21
+    width: int
+    height: int
+    format: BufferFormat = BufferFormat.FLOAT4
+
+
+@dataclass
+class SharedContext:  # common.h:22-28
+    mFrameNumber: int = 0  # noqa: N815
+    mSubframeIndex: int = 0  # noqa: N815
+    mSettingsManager: SettingsManager | None = None  # noqa: N815
+    mRender: "Render | None" = None  # noqa: N815
+
+
+def _check(lib, ctx, rc, what):
+    if rc != 0:
+        msg = lib.sb_last_error(ctx)
+        raise SbError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+class Buffer:
+    """oka::Buffer (buffer.h:23-88) over sb_buffer."""
+
+    _ELEM = {BufferFormat.FLOAT4: 16, BufferFormat.FLOAT3: 12, BufferFormat.UNSIGNED_BYTE4: 4}
+
+    def __init__(self, render: "Render", desc: BufferDesc):
+        self._render = render
+        self._lib = render._lib
+        self._format = BufferFormat(desc.format)
+        h = C.c_void_p()
+        _check(self._lib, render._ctx, self._lib.sb_buffer_create(render._ctx, desc.width, desc.height, int(desc.format), C.byref(h)),
+               "sb_buffer_create")
+        self._h = h
+
+    def resize(self, width: int, height: int) -> None:
+        _check(self._lib, self._render._ctx, self._lib.sb_buffer_resize(self._h, width, height), "sb_buffer_resize")
+
+    def map(self):
+        """Blocking device->host copy (OptixBuffer.cpp:37-43).  Returns the host array."""
+        p = C.c_void_p()
+        _check(self._lib, self._render._ctx, self._lib.sb_buffer_map(self._h, C.byref(p)), "sb_buffer_map")
+        return self.getHostPointer()
+
+    def unmap(self) -> None:
+        _check(self._lib, self._render._ctx, self._lib.sb_buffer_unmap(self._h), "sb_buffer_unmap")
+
+    def width(self) -> int:
+        return self._lib.sb_buffer_width(self._h)
+
+    def height(self) -> int:
+        return self._lib.sb_buffer_height(self._h)
+
+    def getFormat(self) -> BufferFormat:  # noqa: N802
+        return self._format
+
+    def getElementSize(self) -> int:  # noqa: N802
+        return self._ELEM[self._format]
+
+    def getHostDataSize(self) -> int:  # noqa: N802
+        return self._lib.sb_buffer_host_size(self._h)
+
+    def getHostPointer(self) -> np.ndarray:  # noqa: N802
+        """Host mirror as a numpy view (h, w, channels)."""
+        ptr = self._lib.sb_buffer_host_ptr(self._h)
+        n = self.getHostDataSize()
+        w, h = self.width(), self.height()
+        if self._format == BufferFormat.UNSIGNED_BYTE4:
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n,)).reshape(h, w, 4)
+        ch = 4 if self._format == BufferFormat.FLOAT4 else 3
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(n // 4,)).reshape(h, w, ch)
+
+    def getNativePtr(self) -> int:  # noqa: N802
+        return self._lib.sb_buffer_device_ptr(self._h)
+
+    def destroy(self) -> None:
+        if self._h:
+            self._lib.sb_buffer_destroy(self._h)
+            self._h = None
+
+
+class Render:
+    """oka::Render (render.h:19-56) implemented by the B200 backend (RenderType::eCompute)."""
+
+    def __init__(self, device: int = 0, traversal_stats: bool = False, max_batch_paths: int = 0):
+        self._lib = _abi.load_library()
+        self._ctx = None
+        self._device = device
+        self._flags = _abi.SB_CFG_TRAVERSAL_STATS if traversal_stats else 0
+        self._max_batch = max_batch_paths
+        self.mSharedCtx: SharedContext | None = None  # noqa: N815
+        self.mScene: Scene | None = None  # noqa: N815
+        self._scene_uploaded = False
+        self._last_view = None
+        self._last_fov = None
+        self._last_settings = None
+
+    # -- non-virtual setters of oka::Render (render.h:33-51)
+    def setSharedContext(self, ctx: SharedContext) -> None:  # noqa: N802
+        self.mSharedCtx = ctx
+
+    def getSharedContext(self) -> SharedContext:  # noqa: N802
+        return self.mSharedCtx
+
+    def setScene(self, scene: Scene) -> None:  # noqa: N802
+        self.mScene = scene
+        self._scene_uploaded = False
+
+    def getScene(self) -> Scene:  # noqa: N802
+        return self.mScene
+
+    # -- virtuals
+    def init(self) -> None:
+        cfg = sb_device_cfg(self._device, self._max_batch, self._flags, 0)
+        h = C.c_void_p()
+        rc = self._lib.sb_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            msg = self._lib.sb_last_error(None)
+            raise SbError(f"sb_create failed ({rc}): {msg.decode() if msg else ''}")
+        self._ctx = h
+
+    def createBuffer(self, desc: BufferDesc) -> Buffer:  # noqa: N802
+        return Buffer(self, desc)
+
+    def getNativeDevicePtr(self):  # noqa: N802
+        return None
+
+    def _sync_inputs(self) -> None:
+        lib, ctx = self._lib, self._ctx
+        if not self._scene_uploaded:
+            # frame 0 of OptiXRender::render (OptixRender.cpp:876-888)
+            v = self.mScene.view()
+            _check(lib, ctx, lib.sb_set_scene(ctx, C.byref(v)), "sb_set_scene")
+            self._scene_uploaded = True
+            self._last_view = None
+        cam = self.mScene.getCamera(0)
+        cam.updateViewMatrix()
+        view = cam.view_glm()
+        if self._last_view is None or not np.array_equal(view, self._last_view) or cam.fov != self._last_fov:
+            _check(lib, ctx, lib.sb_set_camera(ctx, view.ctypes.data_as(C.POINTER(C.c_float)), float(cam.fov)), "sb_set_camera")
+            self._last_view, self._last_fov = view.copy(), cam.fov
+        st = self.mSharedCtx.mSettingsManager.to_sb_settings()
+        raw = bytes(st)
+        if raw != self._last_settings:
+            _check(lib, ctx, lib.sb_set_settings(ctx, C.byref(st)), "sb_set_settings")
+            self._last_settings = raw
+
+    def render(self, output: Buffer) -> None:
+        """OptiXRender::render(Buffer*) (OptixRender.cpp:874-1057): one launch of `spp` samples."""
+        self._sync_inputs()
+        _check(self._lib, self._ctx, self._lib.sb_render(self._ctx, output._h), "sb_render")
+        self.mSharedCtx.mSubframeIndex = self._lib.sb_subframe_index(self._ctx)
+        self.mSharedCtx.mFrameNumber += 1
+
+    def render_iterations(self, output: Buffer, iterations: int) -> None:
+        """`iterations` consecutive render() calls of the reference app loop, pipelined."""
+        self._sync_inputs()
+        _check(self._lib, self._ctx, self._lib.sb_render_iterations(self._ctx, output._h, iterations), "sb_render_iterations")
+        self.mSharedCtx.mSubframeIndex = self._lib.sb_subframe_index(self._ctx)
+        self.mSharedCtx.mFrameNumber += iterations
+
+    def synchronize(self) -> None:
+        _check(self._lib, self._ctx, self._lib.sb_synchronize(self._ctx), "sb_synchronize")
+
+    def reset_accumulation(self) -> None:
+        _check(self._lib, self._ctx, self._lib.sb_reset_accumulation(self._ctx), "sb_reset_accumulation")
+        self.mSharedCtx.mSubframeIndex = 0
+
+    def counters(self) -> dict:
+        c = sb_counters()
+        _check(self._lib, self._ctx, self._lib.sb_get_counters(self._ctx, C.byref(c)), "sb_get_counters")
+        return c.as_dict()
+
+    def reset_counters(self) -> None:
+        _check(self._lib, self._ctx, self._lib.sb_reset_counters(self._ctx), "sb_reset_counters")
+
+    # -- multi-GPU plumbing
+    def accum_device_ptr(self):
+        n = C.c_uint64()
+        p = self._lib.sb_accum_device_ptr(self._ctx, C.byref(n))
+        return p, n.value
+
+    def resolve(self, output: Buffer, total_samples: int) -> None:
+        _check(self._lib, self._ctx, self._lib.sb_resolve(self._ctx, output._h, total_samples), "sb_resolve")
+
+    # -- test hooks
+    def test_sampler(self, x, y, sample, max_samples, depth, dim) -> np.ndarray:
+        arrs = [np.ascontiguousarray(a, dtype=np.uint32) for a in (x, y, sample, max_samples, depth, dim)]
+        n = len(arrs[0])
+        out = np.zeros(n, dtype=np.float32)
+        _check(self._lib, self._ctx, self._lib.sb_test_sampler(self._ctx, n, *[a.ctypes.data for a in arrs], out.ctypes.data),
+               "sb_test_sampler")
+        return out
+
+    def test_light_sample(self, lights, hit_points, u, method) -> np.ndarray:
+        lights = np.ascontiguousarray(lights, dtype=_abi.LIGHT_DTYPE)
+        hp = np.ascontiguousarray(hit_points, dtype=np.float32)
+        uu = np.ascontiguousarray(u, dtype=np.float32)
+        n = len(lights)
+        out = np.zeros((n, 12), dtype=np.float32)
+        _check(self._lib, self._ctx,
+               self._lib.sb_test_light_sample(self._ctx, n, lights.ctypes.data, hp.ctypes.data, uu.ctypes.data, method, out.ctypes.data),
+               "sb_test_light_sample")
+        return out
+
+    def test_trace(self, rays, mode: int = 0) -> np.ndarray:
+        if not self._scene_uploaded:
+            v = self.mScene.view()
+            _check(self._lib, self._ctx, self._lib.sb_set_scene(self._ctx, C.byref(v)), "sb_set_scene")
+            self._scene_uploaded = True
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+        hits = np.zeros(len(rays), dtype=_abi.HIT_DTYPE)
+        _check(self._lib, self._ctx, self._lib.sb_test_trace(self._ctx, len(rays), rays.ctypes.data, mode, hits.ctypes.data),
+               "sb_test_trace")
+        return hits
+
+    def destroy(self) -> None:
+        if self._ctx:
+            self._lib.sb_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class RenderFactory:  # render.h:58-63, render.cpp:10-35
+    @staticmethod
+    def createRender(type_: RenderType = RenderType.eCompute, **kw) -> Render | None:  # noqa: N802
+        if type_ == RenderType.eCompute:
+            return Render(**kw)
+        return None  # "unsupported" -> nullptr, like render.cpp:17-18,25

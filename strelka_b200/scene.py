@@ -1,0 +1,342 @@
+"""oka::Scene mirror (reference: include/scene/scene.h, src/scene/scene.cpp) -- the flat CPU
+arrays a render backend consumes, plus the packing helpers of the Hydra delegate
+(src/HdStrelka/RenderPass.cpp:53-67) and the light bookkeeping of Scene::createLight/updateLight
+(scene.cpp:306-408), restated glm-free with numpy.
+
+Transforms are 4x4 numpy arrays in math convention (p_world = M @ p_object); they are stored in
+glm's column-major order when handed to the C ABI (sb_instance.transform).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _abi
+from ._abi import (
+    CURVE_DTYPE,
+    INSTANCE_DTYPE,
+    LIGHT_DTYPE,
+    MATERIAL_DTYPE,
+    MESH_DTYPE,
+    VERTEX_DTYPE,
+    SB_INSTANCE_CURVE,
+    SB_INSTANCE_LIGHT,
+    SB_INSTANCE_MESH,
+)
+from .camera import Camera
+
+_F = np.float32
+
+
+def pack_normal(n) -> np.ndarray:
+    """packNormal, RenderPass.cpp:53-59 / scene.cpp:111-117 (10-10-10 bits), float32 arithmetic."""
+    n = np.asarray(n, dtype=_F)
+    q = ((n + _F(1.0)) / _F(2.0) * _F(511.99999)).astype(np.uint32)
+    return (q[..., 0] + (q[..., 1] << np.uint32(10)) + (q[..., 2] << np.uint32(20))).astype(np.uint32)
+
+
+def unpack_normal(v) -> np.ndarray:
+    """unpackNormal, closest_hit.cu:236-244."""
+    v = np.asarray(v, dtype=np.uint32)
+    z = ((v & np.uint32(0xFFF00000)) >> np.uint32(20)).astype(_F) / _F(511.99999) * _F(2.0) - _F(1.0)
+    y = ((v & np.uint32(0x000FFC00)) >> np.uint32(10)).astype(_F) / _F(511.99999) * _F(2.0) - _F(1.0)
+    x = (v & np.uint32(0x000003FF)).astype(_F) / _F(511.99999) * _F(2.0) - _F(1.0)
+    return np.stack([x, y, z], axis=-1)
+
+
+def pack_uv(uv) -> np.ndarray:
+    """packUV, RenderPass.cpp:61-67 (16-16 bits over [-10, 10])."""
+    uv = np.asarray(uv, dtype=_F)
+    q = ((uv + _F(10.0)) / _F(20.0) * _F(16383.99999)).astype(np.uint32)
+    return (q[..., 0] + (q[..., 1] << np.uint32(16))).astype(np.uint32)
+
+
+def make_vertices(pos, normals=None, tangents=None, uvs=None) -> np.ndarray:
+    pos = np.asarray(pos, dtype=_F).reshape(-1, 3)
+    vb = np.zeros(len(pos), dtype=VERTEX_DTYPE)
+    vb["pos"] = pos
+    if normals is not None:
+        vb["normal"] = pack_normal(np.asarray(normals, dtype=_F).reshape(-1, 3))
+    if tangents is not None:
+        vb["tangent"] = pack_normal(np.asarray(tangents, dtype=_F).reshape(-1, 3))
+    if uvs is not None:
+        vb["uv"] = pack_uv(np.asarray(uvs, dtype=_F).reshape(-1, 2))
+    else:
+        vb["uv"] = pack_uv(np.zeros((len(pos), 2), dtype=_F))
+    return vb
+
+
+def scale_matrix(sx, sy, sz) -> np.ndarray:
+    m = np.eye(4)
+    m[0, 0], m[1, 1], m[2, 2] = sx, sy, sz
+    return m
+
+
+def translate_matrix(t) -> np.ndarray:
+    m = np.eye(4)
+    m[:3, 3] = t
+    return m
+
+
+def rotate_matrix(axis, degrees) -> np.ndarray:
+    axis = np.asarray(axis, dtype=np.float64)
+    axis = axis / np.linalg.norm(axis)
+    a = np.radians(degrees)
+    c, s = np.cos(a), np.sin(a)
+    x, y, z = axis
+    m = np.eye(4)
+    m[:3, :3] = [
+        [c + x * x * (1 - c), x * y * (1 - c) - z * s, x * z * (1 - c) + y * s],
+        [y * x * (1 - c) + z * s, c + y * y * (1 - c), y * z * (1 - c) - x * s],
+        [z * x * (1 - c) - y * s, z * y * (1 - c) + x * s, c + z * z * (1 - c)],
+    ]
+    return m
+
+
+@dataclass
+class UniformLightDesc:
+    """Scene::UniformLightDesc, scene.h:158-179 (only the useXform path the Hydra delegate uses)."""
+
+    type: int = 0  # 0 rect, 1 disc, 2 sphere, 3 distant
+    xform: np.ndarray = field(default_factory=lambda: np.eye(4))
+    color: tuple = (1.0, 1.0, 1.0)
+    intensity: float = 1.0
+    width: float = 1.0
+    height: float = 1.0
+    radius: float = 1.0
+    halfAngle: float = 0.0  # noqa: N815
+
+
+class Scene:
+    """Flat scene arrays, same getters as oka::Scene."""
+
+    def __init__(self):
+        self._vb: list[np.ndarray] = []
+        self._ib: list[np.ndarray] = []
+        self._nverts = 0
+        self._nidx = 0
+        self.meshes: list[tuple] = []
+        self.curves: list[tuple] = []
+        self._cpoints: list[np.ndarray] = []
+        self._cwidths: list[np.ndarray] = []
+        self._ccounts: list[np.ndarray] = []
+        self._ncpoints = 0
+        self._ncwidths = 0
+        self._nccounts = 0
+        self.instances: list[tuple] = []
+        self.lights: list[np.ndarray] = []
+        self.light_descs: list[UniformLightDesc] = []
+        self.materials: list[np.ndarray] = []
+        self.cameras: list[Camera] = [Camera()]
+        self._rect_mesh = self._disc_mesh = self._sphere_mesh = -1
+        self._keep = None
+
+    # ---- meshes / instances (scene.cpp:15-88) --------------------------------------------------
+    def createMesh(self, vb: np.ndarray, ib) -> int:  # noqa: N802
+        vb = np.ascontiguousarray(vb, dtype=VERTEX_DTYPE)
+        ib = np.ascontiguousarray(ib, dtype=np.uint32).reshape(-1)
+        mesh_id = len(self.meshes)
+        self.meshes.append((self._nidx, len(ib), self._nverts, len(vb)))
+        self._vb.append(vb)
+        self._ib.append(ib)
+        self._nverts += len(vb)
+        self._nidx += len(ib)
+        return mesh_id
+
+    def createInstance(self, type_: int, geom_id: int, material_id: int, transform, light_id: int = 0xFFFFFFFF) -> int:  # noqa: N802
+        t = np.asarray(transform, dtype=np.float64).reshape(4, 4)
+        self.instances.append((t.T.astype(_F).reshape(16), type_, geom_id, material_id & 0xFFFFFFFF, light_id & 0xFFFFFFFF))
+        return len(self.instances) - 1
+
+    def addMaterial(self, **kw) -> int:  # noqa: N802
+        """Scene::addMaterial (scene.cpp:90-96) with the description pre-resolved to sb_material."""
+        m = np.zeros((), dtype=MATERIAL_DTYPE)
+        m["model"] = kw.get("model", _abi.SB_MATERIAL_DIFFUSE)
+        m["base_color"] = kw.get("base_color", (1.0, 1.0, 1.0))
+        m["roughness"] = kw.get("roughness", 0.5)
+        m["metallic"] = kw.get("metallic", 0.0)
+        m["ior"] = kw.get("ior", 1.5)
+        m["opacity"] = kw.get("opacity", 1.0)
+        m["clearcoat"] = kw.get("clearcoat", 0.0)
+        m["clearcoat_roughness"] = kw.get("clearcoat_roughness", 0.01)
+        m["specular_color"] = kw.get("specular_color", (0.0, 0.0, 0.0))
+        m["use_specular_workflow"] = kw.get("use_specular_workflow", 0)
+        m["hair_absorption"] = kw.get("hair_absorption", (0.0, 0.0, 0.0))
+        m["hair_roughness_lon"] = kw.get("hair_roughness_lon", 0.3)
+        m["hair_roughness_azi"] = kw.get("hair_roughness_azi", 0.3)
+        m["hair_cuticle_angle"] = kw.get("hair_cuticle_angle", 0.035)
+        self.materials.append(m)
+        return len(self.materials) - 1
+
+    # ---- curves (scene.cpp:463-489) -------------------------------------------------------------
+    def createCurve(self, vertex_counts, points, widths) -> int:  # noqa: N802
+        points = np.ascontiguousarray(points, dtype=_F).reshape(-1, 3)
+        counts = np.ascontiguousarray(vertex_counts, dtype=np.uint32).reshape(-1)
+        widths = np.ascontiguousarray(widths, dtype=_F).reshape(-1)
+        if len(widths):
+            wstart, wcount = self._ncwidths, len(widths)
+        else:
+            wstart, wcount = 0xFFFFFFFF, 0xFFFFFFFF
+        self.curves.append((self._nccounts, len(counts), self._ncpoints, len(points), wstart, wcount))
+        self._cpoints.append(points)
+        self._ccounts.append(counts)
+        self._cwidths.append(widths)
+        self._ncpoints += len(points)
+        self._nccounts += len(counts)
+        self._ncwidths += len(widths)
+        return len(self.curves) - 1
+
+    # ---- light meshes (scene.cpp:119-250) ---------------------------------------------------------
+    def _create_rect_light_mesh(self) -> int:
+        if self._rect_mesh < 0:
+            pos = [(0.5, 0.5, 0.0), (-0.5, 0.5, 0.0), (-0.5, -0.5, 0.0), (0.5, -0.5, 0.0)]
+            vb = make_vertices(pos, normals=[(0.0, 0.0, 1.0)] * 4)
+            vb["uv"] = 0  # the reference leaves tangent/uv uninitialised/zero here
+            self._rect_mesh = self.createMesh(vb, [0, 1, 2, 2, 3, 0])
+        return self._rect_mesh
+
+    def _create_sphere_light_mesh(self) -> int:
+        if self._sphere_mesh < 0:
+            seg = rings = 16
+            pos, nrm, idx = [], [], []
+            for i in range(rings + 1):
+                theta = _F(i) * _F(np.pi) / _F(rings)
+                st, ct = np.sin(theta, dtype=_F), np.cos(theta, dtype=_F)
+                for j in range(seg + 1):
+                    phi = _F(j) * _F(2.0) * _F(np.pi) / _F(seg)
+                    sp, cp = np.sin(phi, dtype=_F), np.cos(phi, dtype=_F)
+                    p = (cp * st, ct, sp * st)
+                    pos.append(p)
+                    nrm.append(p)
+            for i in range(rings):
+                for j in range(seg):
+                    p0 = i * (seg + 1) + j
+                    p1, p2 = p0 + 1, (i + 1) * (seg + 1) + j
+                    p3 = p2 + 1
+                    idx += [p0, p1, p2, p2, p1, p3]
+            vb = make_vertices(pos, normals=nrm)
+            vb["uv"] = 0
+            self._sphere_mesh = self.createMesh(vb, idx)
+        return self._sphere_mesh
+
+    def _create_disc_light_mesh(self) -> int:
+        if self._disc_mesh < 0:
+            pos = [(0.0, 0.0, 0.0), (1.0, 0.0, 0.0)]
+            idx = []
+            step = 2.0 * np.pi / 16
+            angle = 0.0
+            for _ in range(16):
+                idx += [0, len(pos) - 1]
+                angle += step
+                pos.append((np.cos(angle), np.sin(angle), 0.0))
+                idx.append(len(pos) - 1)
+            vb = make_vertices(pos, normals=[(0.0, 0.0, 1.0)] * len(pos))
+            vb["uv"] = 0
+            self._disc_mesh = self.createMesh(vb, idx)
+        return self._disc_mesh
+
+    # ---- lights (scene.cpp:306-408) ---------------------------------------------------------------
+    def createLight(self, desc: UniformLightDesc) -> int:  # noqa: N802
+        light_id = len(self.lights)
+        self.lights.append(np.zeros((), dtype=LIGHT_DTYPE))
+        self.light_descs.append(desc)
+        self.updateLight(light_id, desc)
+        if desc.type == 0:
+            mesh_id = self._create_rect_light_mesh()
+            s = scale_matrix(desc.width, desc.height, 1.0)
+        elif desc.type == 1:
+            mesh_id = self._create_disc_light_mesh()
+            s = scale_matrix(desc.radius, desc.radius, desc.radius)
+        elif desc.type == 2:
+            mesh_id = self._create_sphere_light_mesh()
+            s = scale_matrix(desc.radius, desc.radius, desc.radius)
+        else:
+            mesh_id = 0  # quirk Q8: the distant light instances mesh 0, whatever it is
+            s = scale_matrix(desc.radius, desc.radius, desc.radius)
+        transform = np.asarray(desc.xform, dtype=np.float64) @ s
+        self.createInstance(SB_INSTANCE_LIGHT, mesh_id, 0xFFFFFFFF, transform, light_id)
+        return light_id
+
+    def updateLight(self, light_id: int, desc: UniformLightDesc) -> None:  # noqa: N802
+        l = self.lights[light_id]  # noqa: E741
+        xf = np.asarray(desc.xform, dtype=np.float64)
+        if desc.type == 0:
+            m = (xf @ scale_matrix(desc.width, desc.height, 1.0)).astype(_F)
+            corners = np.array(
+                [(0.5, 0.5, 0.0, 1.0), (-0.5, 0.5, 0.0, 1.0), (-0.5, -0.5, 0.0, 1.0), (0.5, -0.5, 0.0, 1.0)], dtype=_F
+            )
+            l["points"] = (m @ corners.T).T
+            l["type"] = 0
+        elif desc.type == 1:
+            m = (xf @ scale_matrix(desc.radius, desc.radius, desc.radius)).astype(_F)
+            l["points"][0] = (desc.radius, 0.0, 0.0, 0.0)
+            l["points"][1] = m @ np.array([0.0, 0.0, 0.0, 1.0], dtype=_F)
+            l["points"][2] = m @ np.array([1.0, 0.0, 0.0, 0.0], dtype=_F)
+            l["points"][3] = m @ np.array([0.0, 1.0, 0.0, 0.0], dtype=_F)
+            l["normal"] = m @ np.array([0.0, 0.0, 1.0, 0.0], dtype=_F)
+            l["type"] = 1
+        elif desc.type == 2:
+            m = xf.astype(_F)
+            l["points"][0] = (desc.radius, 0.0, 0.0, 0.0)
+            l["points"][1] = m @ np.array([0.0, 0.0, 0.0, 1.0], dtype=_F)
+            l["type"] = 2
+        else:
+            m = xf.astype(_F)
+            n = m @ np.array([0.0, 0.0, -1.0, 0.0], dtype=_F)
+            l["normal"] = n / np.linalg.norm(n)
+            l["half_angle"] = desc.halfAngle
+            l["type"] = 3
+        l["color"] = np.array([*desc.color, 1.0], dtype=_F) * _F(desc.intensity)
+
+    # ---- getters ---------------------------------------------------------------------------------
+    def getCamera(self, i: int = 0) -> Camera:  # noqa: N802
+        return self.cameras[i]
+
+    def arrays(self) -> dict:
+        def cat(lst, dtype, shape=None):
+            if not lst:
+                return np.zeros((0,) + (shape or ()), dtype=dtype)
+            return np.ascontiguousarray(np.concatenate(lst))
+
+        a = {
+            "vertices": cat(self._vb, VERTEX_DTYPE),
+            "indices": cat(self._ib, np.uint32),
+            "meshes": np.array(self.meshes, dtype=np.uint32).reshape(-1, 4).view(MESH_DTYPE).reshape(-1)
+            if self.meshes else np.zeros(0, dtype=MESH_DTYPE),
+            "curves": np.array(self.curves, dtype=np.uint32).reshape(-1, 6).view(CURVE_DTYPE).reshape(-1)
+            if self.curves else np.zeros(0, dtype=CURVE_DTYPE),
+            "curve_points": cat(self._cpoints, _F, (3,)),
+            "curve_widths": cat(self._cwidths, _F),
+            "curve_vertex_counts": cat(self._ccounts, np.uint32),
+            "lights": np.array(self.lights, dtype=LIGHT_DTYPE) if self.lights else np.zeros(0, dtype=LIGHT_DTYPE),
+            "materials": np.array(self.materials, dtype=MATERIAL_DTYPE) if self.materials else np.zeros(0, dtype=MATERIAL_DTYPE),
+        }
+        inst = np.zeros(len(self.instances), dtype=INSTANCE_DTYPE)
+        for i, (t, ty, g, m, l) in enumerate(self.instances):  # noqa: E741
+            inst[i] = (t, ty, g, m, l)
+        a["instances"] = inst
+        return a
+
+    def view(self) -> _abi.sb_scene_view:
+        """Borrowed sb_scene_view over freshly flattened arrays (kept alive on self)."""
+        a = self.arrays()
+        self._keep = a
+        v = _abi.sb_scene_view()
+        p = _abi.np_ptr
+        v.vertices, v.num_vertices = p(a["vertices"]), len(a["vertices"])
+        v.indices, v.num_indices = p(a["indices"]), len(a["indices"])
+        v.meshes, v.num_meshes = p(a["meshes"]), len(a["meshes"])
+        v.curves, v.num_curves = p(a["curves"]), len(a["curves"])
+        v.curve_points, v.num_curve_points = p(a["curve_points"]), len(a["curve_points"])
+        v.curve_widths, v.num_curve_widths = p(a["curve_widths"]), len(a["curve_widths"])
+        v.curve_vertex_counts, v.num_curve_vertex_counts = p(a["curve_vertex_counts"]), len(a["curve_vertex_counts"])
+        v.instances, v.num_instances = p(a["instances"]), len(a["instances"])
+        v.lights, v.num_lights = p(a["lights"]), len(a["lights"])
+        v.materials, v.num_materials = p(a["materials"]), len(a["materials"])
+        return v
+
+    def stats(self) -> dict:
+        tri = sum(self.meshes[g][1] // 3 for (_, ty, g, _, _) in self.instances if ty in (SB_INSTANCE_MESH, SB_INSTANCE_LIGHT))
+        return {"instances": len(self.instances), "triangles": tri, "lights": len(self.lights), "materials": len(self.materials)}
