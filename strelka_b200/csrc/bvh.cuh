@@ -1,0 +1,371 @@
+// Compressed 8-wide BVH (CWBVH, after Ylitie, Karras, Laine 2017) -- data layout, the per-element
+// steps of the on-device builder, and the traversal core.
+//
+// This replaces what the reference delegates to NVIDIA's closed OptiX driver: optixAccelBuild of one
+// GAS per mesh/curve + one IAS (OptixRender.cpp:218-316,318-386,388-496) and optixTrace
+// (OptixRender.cu:120-129, closest_hit.cu:185-197).  Design choice for 180 GB of HBM3e: instances are
+// flattened to world space once (the reference's Hydra path already duplicates geometry per instance,
+// RenderPass.cpp:252-257) and ONE wide BVH per primitive kind is built over all of it, so traversal
+// never transforms rays and never chases an instance indirection.
+//
+// Node (80 B = 5 x 16 B, fetched with 128-bit loads):
+//   n0 = { p.x, p.y, p.z, ex | ey<<8 | ez<<16 | imask<<24 }      quantisation frame + inner-node mask
+//   n1 = { childBase, primBase, meta[0..3], meta[4..7] }
+//   n2 = { qlo.x[0..3], qlo.x[4..7], qlo.y[0..3], qlo.y[4..7] }
+//   n3 = { qlo.z[0..3], qlo.z[4..7], qhi.x[0..3], qhi.x[4..7] }
+//   n4 = { qhi.y[0..3], qhi.y[4..7], qhi.z[0..3], qhi.z[4..7] }
+// child box = p + q * 2^(e-127); meta: 0 empty | inner: 0x20 | (24 + slot) | leaf: unary(count)<<5 | first
+// primitive offset (relative to primBase, < 24).  Slot s prefers children lying towards
+// ((s&1?+:-), (s&2?+:-), (s&4?+:-)) of the node centre, which makes (slot ^ octant) a front-to-back order.
+#pragma once
+#include "hd.cuh"
+
+namespace sb
+{
+
+struct Aabb
+{
+    float3 lo, hi;
+};
+SB_HD Aabb aabb_empty()
+{
+    Aabb b;
+    b.lo = mk3(3.0e38f);
+    b.hi = mk3(-3.0e38f);
+    return b;
+}
+SB_HD Aabb aabb_union(const Aabb& a, const Aabb& b)
+{
+    Aabb r;
+    r.lo = mk3(fminf(a.lo.x, b.lo.x), fminf(a.lo.y, b.lo.y), fminf(a.lo.z, b.lo.z));
+    r.hi = mk3(fmaxf(a.hi.x, b.hi.x), fmaxf(a.hi.y, b.hi.y), fmaxf(a.hi.z, b.hi.z));
+    return r;
+}
+SB_HD void aabb_grow(Aabb& a, const float3& p)
+{
+    a.lo = mk3(fminf(a.lo.x, p.x), fminf(a.lo.y, p.y), fminf(a.lo.z, p.z));
+    a.hi = mk3(fmaxf(a.hi.x, p.x), fmaxf(a.hi.y, p.y), fmaxf(a.hi.z, p.z));
+}
+SB_HD float aabb_half_area(const Aabb& a)
+{
+    const float dx = a.hi.x - a.lo.x, dy = a.hi.y - a.lo.y, dz = a.hi.z - a.lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+// Binary BVH node used during construction.  Nodes [0, N) are the leaves (leaf i = i-th primitive in
+// Morton order), nodes [N, 2N-1) are internal.
+struct Bvh2Node
+{
+    float lo[3];
+    uint32_t left;
+    float hi[3];
+    uint32_t right;
+};
+SB_HD Aabb node_box(const Bvh2Node& n)
+{
+    Aabb b;
+    b.lo = mk3(n.lo[0], n.lo[1], n.lo[2]);
+    b.hi = mk3(n.hi[0], n.hi[1], n.hi[2]);
+    return b;
+}
+SB_HD void node_set_box(Bvh2Node& n, const Aabb& b)
+{
+    n.lo[0] = b.lo.x;
+    n.lo[1] = b.lo.y;
+    n.lo[2] = b.lo.z;
+    n.hi[0] = b.hi.x;
+    n.hi[1] = b.hi.y;
+    n.hi[2] = b.hi.z;
+}
+
+struct WideNode
+{
+    uint4 n0, n1, n2, n3, n4;
+};
+static_assert(sizeof(WideNode) == 80, "CWBVH node must be 80 bytes");
+
+// ---- 63-bit Morton code of a point in the unit cube ------------------------------------------------
+SB_HD uint64_t spread21(uint64_t x)
+{
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+SB_HD uint64_t morton63(const float3& p, const float3& lo, const float3& invExtent)
+{
+    const float fx = fminf(fmaxf((p.x - lo.x) * invExtent.x, 0.0f), 1.0f);
+    const float fy = fminf(fmaxf((p.y - lo.y) * invExtent.y, 0.0f), 1.0f);
+    const float fz = fminf(fmaxf((p.z - lo.z) * invExtent.z, 0.0f), 1.0f);
+    const uint64_t x = uint64_t(fx * 2097151.0f), y = uint64_t(fy * 2097151.0f), z = uint64_t(fz * 2097151.0f);
+    return (spread21(x) << 2) | (spread21(y) << 1) | spread21(z);
+}
+
+// ---- PLOC (Meister & Bittner 2018): nearest neighbour inside a window of the Morton-ordered clusters
+constexpr int kPlocRadius = 16;
+
+SB_HD uint32_t ploc_nearest(const Bvh2Node* nodes, const uint32_t* cluster, uint32_t n, uint32_t i)
+{
+    const Aabb bi = node_box(nodes[cluster[i]]);
+    const uint32_t j0 = i > uint32_t(kPlocRadius) ? i - kPlocRadius : 0u;
+    const uint32_t j1 = (i + kPlocRadius + 1 < n) ? i + kPlocRadius + 1 : n;
+    float best = 3.0e38f;
+    uint32_t bestJ = 0xffffffffu;
+    for (uint32_t j = j0; j < j1; ++j)
+    {
+        if (j == i)
+            continue;
+        const float a = aabb_half_area(aabb_union(bi, node_box(nodes[cluster[j]])));
+        if (a < best) // ties keep the lowest j: deterministic
+        {
+            best = a;
+            bestJ = j;
+        }
+    }
+    return bestJ;
+}
+
+// ---- BVH2 -> BVH8 collapse -----------------------------------------------------------------------
+constexpr uint32_t kInvalid = 0xffffffffu;
+
+struct CollapseItem
+{
+    uint32_t bvh2Node; // subtree root to turn into one wide node
+    uint32_t wideIndex; // where the wide node goes
+};
+
+// Greedy surface-area collapse of the subtree under `root` into at most 8 slots, followed by the
+// octant-aware slot assignment.  `count[]` = primitives under each BVH2 node.  Returns the number of
+// inner children; nPrims = primitives referenced directly by this node's leaf slots.
+SB_HD uint32_t collapse_select(const Bvh2Node* nodes, const uint32_t* count, uint32_t numLeaves, uint32_t root,
+                               uint32_t maxLeaf, uint32_t slots[8], uint32_t& nPrims)
+{
+    uint32_t cand[8];
+    int n = 0;
+    if (root < numLeaves)
+    {
+        cand[n++] = root; // a tree that is a single leaf
+    }
+    else
+    {
+        cand[n++] = nodes[root].left;
+        cand[n++] = nodes[root].right;
+    }
+    // pass 0: open the largest node that MUST be opened (more primitives than a leaf slot holds);
+    // pass 1: with slots to spare, also split small groups so that every primitive gets its own box
+    for (int pass = 0; pass < 2; ++pass)
+    {
+        while (n < 8)
+        {
+            int best = -1;
+            float bestArea = -1.0f;
+            for (int k = 0; k < n; ++k)
+            {
+                const uint32_t c = cand[k];
+                if (c < numLeaves)
+                    continue;
+                const bool big = count[c] > maxLeaf;
+                if ((pass == 0) != big)
+                    continue;
+                const float a = aabb_half_area(node_box(nodes[c]));
+                if (a > bestArea)
+                {
+                    bestArea = a;
+                    best = k;
+                }
+            }
+            if (best < 0)
+                break;
+            const uint32_t c = cand[best];
+            cand[best] = nodes[c].left;
+            cand[n++] = nodes[c].right;
+        }
+    }
+    // octant-aware assignment: greedily give the (child, slot) pair with the largest
+    // dot(child centre - node centre, slot direction) until every child has a slot
+    const Aabb pb = node_box(nodes[root]);
+    const float3 pc = (pb.lo + pb.hi) * 0.5f;
+    float3 off[8];
+    for (int k = 0; k < n; ++k)
+    {
+        const Aabb cb = node_box(nodes[cand[k]]);
+        off[k] = (cb.lo + cb.hi) * 0.5f - pc;
+    }
+    bool childDone[8] = { false, false, false, false, false, false, false, false };
+    for (int s = 0; s < 8; ++s)
+        slots[s] = kInvalid;
+    for (int it = 0; it < n; ++it)
+    {
+        float bestCost = -3.0e38f;
+        int bc = -1, bs = -1;
+        for (int k = 0; k < n; ++k)
+        {
+            if (childDone[k])
+                continue;
+            for (int s = 0; s < 8; ++s)
+            {
+                if (slots[s] != kInvalid)
+                    continue;
+                const float cost = ((s & 1) ? off[k].x : -off[k].x) + ((s & 2) ? off[k].y : -off[k].y) + ((s & 4) ? off[k].z : -off[k].z);
+                if (cost > bestCost)
+                {
+                    bestCost = cost;
+                    bc = k;
+                    bs = s;
+                }
+            }
+        }
+        childDone[bc] = true;
+        slots[bs] = cand[bc];
+    }
+    uint32_t nInner = 0;
+    nPrims = 0;
+    for (int s = 0; s < 8; ++s)
+    {
+        const uint32_t c = slots[s];
+        if (c == kInvalid)
+            continue;
+        if (c >= numLeaves && count[c] > maxLeaf)
+            ++nInner;
+        else
+            nPrims += (c < numLeaves) ? 1u : count[c];
+    }
+    return nInner;
+}
+
+// leaves under a small subtree (<= 3), in left-to-right order
+SB_HD uint32_t collect_leaves(const Bvh2Node* nodes, uint32_t numLeaves, uint32_t root, uint32_t out[4])
+{
+    uint32_t stack[8];
+    int sp = 0;
+    uint32_t n = 0;
+    stack[sp++] = root;
+    while (sp > 0)
+    {
+        const uint32_t c = stack[--sp];
+        if (c < numLeaves)
+        {
+            if (n < 4)
+                out[n++] = c;
+        }
+        else
+        {
+            if (sp + 2 <= 8)
+            {
+                stack[sp++] = nodes[c].right;
+                stack[sp++] = nodes[c].left;
+            }
+        }
+    }
+    return n;
+}
+
+// biased exponent e (uint8) such that extent <= 255 * 2^(e-127)
+SB_HD uint32_t quant_exponent(float extent)
+{
+    if (!(extent > 0.0f))
+        return 1u; // degenerate axis: any tiny positive cell size works
+    const float cell = extent / 255.0f;
+    uint32_t e = (f2u(cell) + 0x7fffffu) >> 23; // round the magnitude up to a power of two
+    if (e < 1u)
+        e = 1u;
+    if (e > 253u)
+        e = 253u;
+    // keep one cell of head-room so that ceil() of the far face can never reach 256
+    if (extent * (1.0f / u2f(e << 23)) > 254.0f)
+        e += 1u;
+    return e;
+}
+
+// Writes the compressed node for the slots chosen by collapse_select.  Emits the next level's work
+// items (inner children, slot order) and this node's primitives (leaf slots, slot order).
+SB_HD void collapse_emit(const Bvh2Node* nodes, const uint32_t* count, uint32_t numLeaves, uint32_t root, uint32_t maxLeaf,
+                         const uint32_t slots[8], uint32_t childBase, uint32_t primBase, WideNode& out, CollapseItem* nextItems,
+                         uint32_t nextOffset, uint32_t* primOrder)
+{
+    const Aabb pb = node_box(nodes[root]);
+    const uint32_t ex = quant_exponent(pb.hi.x - pb.lo.x), ey = quant_exponent(pb.hi.y - pb.lo.y), ez = quant_exponent(pb.hi.z - pb.lo.z);
+    const float sx = u2f(ex << 23), sy = u2f(ey << 23), sz = u2f(ez << 23); // cell sizes (powers of two)
+    const float isx = 1.0f / sx, isy = 1.0f / sy, isz = 1.0f / sz;
+    uint8_t meta[8], qlo[3][8], qhi[3][8];
+    uint32_t imask = 0, innerRank = 0, primOff = 0;
+    for (int s = 0; s < 8; ++s)
+    {
+        const uint32_t c = slots[s];
+        if (c == kInvalid)
+        {
+            meta[s] = 0;
+            for (int a = 0; a < 3; ++a)
+            {
+                qlo[a][s] = 255; // inverted box: can never be hit
+                qhi[a][s] = 0;
+            }
+            continue;
+        }
+        const Aabb cb = node_box(nodes[c]);
+        // conservative quantisation (power-of-two cells make the products exact)
+        const float lo[3] = { floorf((cb.lo.x - pb.lo.x) * isx), floorf((cb.lo.y - pb.lo.y) * isy), floorf((cb.lo.z - pb.lo.z) * isz) };
+        const float hi[3] = { ceilf((cb.hi.x - pb.lo.x) * isx), ceilf((cb.hi.y - pb.lo.y) * isy), ceilf((cb.hi.z - pb.lo.z) * isz) };
+        const float plo[3] = { pb.lo.x, pb.lo.y, pb.lo.z };
+        const float cs[3] = { sx, sy, sz };
+        const float clo[3] = { cb.lo.x, cb.lo.y, cb.lo.z };
+        const float chi[3] = { cb.hi.x, cb.hi.y, cb.hi.z };
+        for (int a = 0; a < 3; ++a)
+        {
+            float l = fminf(fmaxf(lo[a], 0.0f), 255.0f), h = fminf(fmaxf(hi[a], 0.0f), 255.0f);
+            // make sure the dequantised box really contains the child box (subtraction above rounds)
+            while (l > 0.0f && plo[a] + l * cs[a] > clo[a])
+                l -= 1.0f;
+            while (h < 255.0f && plo[a] + h * cs[a] < chi[a])
+                h += 1.0f;
+            qlo[a][s] = uint8_t(l);
+            qhi[a][s] = uint8_t(h);
+        }
+        if (c >= numLeaves && count[c] > maxLeaf)
+        {
+            meta[s] = uint8_t(0x20u | (24u + uint32_t(s)));
+            imask |= 1u << s;
+            CollapseItem it;
+            it.bvh2Node = c;
+            it.wideIndex = childBase + innerRank;
+            nextItems[nextOffset + innerRank] = it;
+            ++innerRank;
+        }
+        else
+        {
+            uint32_t leaves[4];
+            const uint32_t nl = collect_leaves(nodes, numLeaves, c, leaves);
+            for (uint32_t k = 0; k < nl; ++k)
+                primOrder[primBase + primOff + k] = leaves[k];
+            const uint32_t unary = (nl >= 3) ? 7u : ((nl == 2) ? 3u : 1u);
+            meta[s] = uint8_t((unary << 5) | primOff);
+            primOff += nl;
+        }
+    }
+    auto pack4 = [](const uint8_t* b) { return uint32_t(b[0]) | (uint32_t(b[1]) << 8) | (uint32_t(b[2]) << 16) | (uint32_t(b[3]) << 24); };
+    out.n0.x = f2u(pb.lo.x);
+    out.n0.y = f2u(pb.lo.y);
+    out.n0.z = f2u(pb.lo.z);
+    out.n0.w = ex | (ey << 8) | (ez << 16) | (imask << 24);
+    out.n1.x = childBase;
+    out.n1.y = primBase;
+    out.n1.z = pack4(meta);
+    out.n1.w = pack4(meta + 4);
+    out.n2.x = pack4(qlo[0]);
+    out.n2.y = pack4(qlo[0] + 4);
+    out.n2.z = pack4(qlo[1]);
+    out.n2.w = pack4(qlo[1] + 4);
+    out.n3.x = pack4(qlo[2]);
+    out.n3.y = pack4(qlo[2] + 4);
+    out.n3.z = pack4(qhi[0]);
+    out.n3.w = pack4(qhi[0] + 4);
+    out.n4.x = pack4(qhi[1]);
+    out.n4.y = pack4(qhi[1] + 4);
+    out.n4.z = pack4(qhi[2]);
+    out.n4.w = pack4(qhi[2] + 4);
+}
+
+} // namespace sb

@@ -1,0 +1,312 @@
+// Hand-written sm_100a kernels of the wavefront path tracer + their launchers.
+//
+// Launch geometry (B200: 148 SMs): every stage is a grid-stride kernel over a device-resident queue
+// count, launched with a fixed grid of 148 * kBlocksPerSm blocks so that (a) no host round-trip is
+// needed to size a launch, (b) the grid is always a whole number of waves.  Blocks are 128 threads:
+// traversal is latency-bound pointer chasing, so occupancy (registers) matters more than block size.
+#include <cstdint>
+namespace sb
+{
+__constant__ uint32_t c_sobol[5][32];
+uint32_t h_sobol[5][32];
+} // namespace sb
+
+#include "wavefront.cuh"
+#include "kernels.h"
+
+namespace sb
+{
+
+void upload_sobol_table(cudaStream_t stream)
+{
+    sobol_generate(h_sobol);
+    SB_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_sobol, h_sobol, sizeof(h_sobol), 0, cudaMemcpyHostToDevice, stream));
+    SB_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+constexpr int kBlock = 128;
+
+__global__ void __launch_bounds__(kBlock) k_raygen(FrameParams P, Queues Q)
+{
+    const uint32_t n = P.nPixPadded * P.chunk;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        raygen_one(P, Q, i);
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&Q.stats->paths, (unsigned long long)(P.width) * P.height * P.chunk);
+}
+
+// flush per-thread traversal statistics with one atomic per warp
+__device__ __forceinline__ void flush_stats(StatCounters* g, const TravStats& st)
+{
+    unsigned n = st.nodes, t = st.tris, s = st.segs, o = st.overflow;
+    for (int off = 16; off > 0; off >>= 1)
+    {
+        n += __shfl_xor_sync(0xffffffffu, n, off);
+        t += __shfl_xor_sync(0xffffffffu, t, off);
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+        o += __shfl_xor_sync(0xffffffffu, o, off);
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+        if (n)
+            atomicAdd(&g->nodes, (unsigned long long)n);
+        if (t)
+            atomicAdd(&g->tris, (unsigned long long)t);
+        if (s)
+            atomicAdd(&g->segs, (unsigned long long)s);
+        if (o)
+            atomicAdd(&g->overflow, (unsigned long long)o);
+    }
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(kBlock) k_extend(FrameParams P, SceneDev S, Queues Q, uint32_t depth)
+{
+    const uint32_t n = Q.counts[depth];
+    TravStats st = { 0, 0, 0, 0 };
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        extend_one<STATS>(P, S, Q, depth, i, &st);
+    if (STATS)
+        flush_stats(Q.stats, st);
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&Q.stats->radianceRays, (unsigned long long)n);
+}
+
+__global__ void __launch_bounds__(kBlock) k_shade(FrameParams P, SceneDev S, Queues Q, uint32_t depth)
+{
+    const uint32_t n = Q.counts[depth];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        shade_one(P, S, Q, depth, i);
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(kBlock) k_shadow(SceneDev S, Queues Q, uint32_t depth)
+{
+    const uint32_t n = Q.counts[kCountShadowBase + depth];
+    TravStats st = { 0, 0, 0, 0 };
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        shadow_one<STATS>(S, Q, i, &st);
+    if (STATS)
+        flush_stats(Q.stats, st);
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&Q.stats->shadowRays, (unsigned long long)n);
+}
+
+__global__ void __launch_bounds__(256) k_accumulate(FrameParams P, Queues Q, float4* S, float4* direct, uint32_t mode, uint32_t subframe)
+{
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P.nPixPadded; p += gridDim.x * blockDim.x)
+        accumulate_pixel(P, Q, S, direct, mode, subframe, p);
+}
+
+// format: SB_FORMAT_* of the output buffer
+__global__ void __launch_bounds__(256) k_resolve(const float4* S, void* out, uint32_t npix, uint32_t n, float3 e, uint32_t tonemapper, float gamma,
+                                                 uint32_t format)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x)
+    {
+        const float4 c = resolve_pixel(S[i], n, e, tonemapper, gamma);
+        if (format == SB_FORMAT_FLOAT4)
+        {
+            reinterpret_cast<float4*>(out)[i] = c;
+        }
+        else if (format == SB_FORMAT_FLOAT3)
+        {
+            float* o = reinterpret_cast<float*>(out) + 3 * size_t(i);
+            o[0] = c.x;
+            o[1] = c.y;
+            o[2] = c.z;
+        }
+        else
+        {
+            uchar4 q;
+            q.x = (unsigned char)(saturate(c.x) * 255.0f + 0.5f);
+            q.y = (unsigned char)(saturate(c.y) * 255.0f + 0.5f);
+            q.z = (unsigned char)(saturate(c.z) * 255.0f + 0.5f);
+            q.w = 255;
+            reinterpret_cast<uchar4*>(out)[i] = q;
+        }
+    }
+}
+
+// debug / no-accumulation output: copy a float4 image into the (possibly narrower) output format
+__global__ void __launch_bounds__(256) k_copy_image(const float4* src, void* out, uint32_t npix, uint32_t format)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x)
+    {
+        const float4 c = src[i];
+        if (format == SB_FORMAT_FLOAT4)
+        {
+            reinterpret_cast<float4*>(out)[i] = c;
+        }
+        else if (format == SB_FORMAT_FLOAT3)
+        {
+            float* o = reinterpret_cast<float*>(out) + 3 * size_t(i);
+            o[0] = c.x;
+            o[1] = c.y;
+            o[2] = c.z;
+        }
+        else
+        {
+            uchar4 q;
+            q.x = (unsigned char)(saturate(c.x) * 255.0f + 0.5f);
+            q.y = (unsigned char)(saturate(c.y) * 255.0f + 0.5f);
+            q.z = (unsigned char)(saturate(c.z) * 255.0f + 0.5f);
+            q.w = 255;
+            reinterpret_cast<uchar4*>(out)[i] = q;
+        }
+    }
+}
+
+// ---- launchers -------------------------------------------------------------------------------------
+
+static inline unsigned grid_for(const LaunchCfg& cfg, int blocksPerSm)
+{
+    return unsigned(cfg.numSms * blocksPerSm);
+}
+
+void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const SceneDev& S, const Queues& Q, bool stats)
+{
+    cudaStream_t st = cfg.stream;
+    SB_CUDA_CHECK(cudaMemsetAsync(Q.counts, 0, sizeof(uint32_t) * kNumCounts, st));
+    k_raygen<<<grid_for(cfg, 8), kBlock, 0, st>>>(P, Q);
+    for (uint32_t depth = 0; depth < P.maxDepth; ++depth)
+    {
+        if (stats)
+            k_extend<true><<<grid_for(cfg, 8), kBlock, 0, st>>>(P, S, Q, depth);
+        else
+            k_extend<false><<<grid_for(cfg, 8), kBlock, 0, st>>>(P, S, Q, depth);
+        k_shade<<<grid_for(cfg, 8), kBlock, 0, st>>>(P, S, Q, depth);
+        if (P.debug == 1u)
+            break; // debug normals: only the first hit is shaded (OptixRender.cu:151-152)
+        if (stats)
+            k_shadow<true><<<grid_for(cfg, 8), kBlock, 0, st>>>(S, Q, depth);
+        else
+            k_shadow<false><<<grid_for(cfg, 8), kBlock, 0, st>>>(S, Q, depth);
+    }
+    SB_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_accumulate(const LaunchCfg& cfg, const FrameParams& P, const Queues& Q, float4* S, float4* direct, uint32_t mode, uint32_t subframe)
+{
+    k_accumulate<<<grid_for(cfg, 4), 256, 0, cfg.stream>>>(P, Q, S, direct, mode, subframe);
+    SB_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_resolve(const LaunchCfg& cfg, const float4* S, void* out, uint32_t npix, uint32_t n, const float exposure[3], uint32_t tonemapper,
+                    float gamma, uint32_t format)
+{
+    k_resolve<<<grid_for(cfg, 4), 256, 0, cfg.stream>>>(S, out, npix, n, make_float3(exposure[0], exposure[1], exposure[2]), tonemapper, gamma, format);
+    SB_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_copy_image(const LaunchCfg& cfg, const float4* src, void* out, uint32_t npix, uint32_t format)
+{
+    k_copy_image<<<grid_for(cfg, 4), 256, 0, cfg.stream>>>(src, out, npix, format);
+    SB_CUDA_CHECK(cudaGetLastError());
+}
+
+// ---- test hooks ------------------------------------------------------------------------------------
+
+__global__ void k_test_sampler(uint32_t n, const uint32_t* x, const uint32_t* y, const uint32_t* sample, const uint32_t* maxs, const uint32_t* depth,
+                               const uint32_t* dim, float* out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t sidx = sampler_index(x[i], y[i], sample[i], maxs[i]);
+        const float a = sampler_rnd(sidx, depth[i], dim[i]);
+        // cross-check the fused five-value path the integrator uses against the generic one
+        const Sample5 s5 = sampler_sample5(sidx, depth[i]);
+        const float b = s5.v[(dim[i] + depth[i] * 10u) % 5u];
+        out[i] = (a == b) ? a : -1.0f;
+    }
+}
+
+__global__ void k_test_light_sample(uint32_t n, const sb_light* lights, const float* hp, const float* u, uint32_t method, float* out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const LightSample s = sample_light(lights[i], u[2 * i], u[2 * i + 1], mk3(hp[3 * i], hp[3 * i + 1], hp[3 * i + 2]), method);
+        float* o = out + 12 * size_t(i);
+        o[0] = s.pointOnLight.x;
+        o[1] = s.pointOnLight.y;
+        o[2] = s.pointOnLight.z;
+        o[3] = s.pdf;
+        o[4] = s.normal.x;
+        o[5] = s.normal.y;
+        o[6] = s.normal.z;
+        o[7] = s.area;
+        o[8] = s.L.x;
+        o[9] = s.L.y;
+        o[10] = s.L.z;
+        o[11] = s.distToLight;
+    }
+}
+
+__global__ void k_test_trace(SceneDev S, uint32_t n, const float* rays, uint32_t mode, sb_hit* hits)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const float* r = rays + 8 * size_t(i);
+        Ray ray;
+        ray.o = mk3(r[0], r[1], r[2]);
+        ray.tmin = r[3];
+        ray.d = mk3(r[4], r[5], r[6]);
+        ray.tmax = r[7];
+        const RayPrep rp = prepare_ray(ray.d);
+        HitRec hit;
+        hit.t = hit.u = hit.v = 0.0f;
+        hit.prim = hit.inst = hit.kind = 0u;
+        hit.gid = 0xffffffffu;
+        TravStats st = { 0, 0, 0, 0 };
+        sb_hit h = { 0, 0, 0, 0, 0, 0 };
+        if (mode == 0)
+        {
+            if (S.numTriNodes)
+                traverse_bvh<1, false, false>(S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, &st);
+            if (S.numSegNodes)
+            {
+                if (traverse_bvh<2, false, false>(S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, &st))
+                {
+                    const SegInfo si = S.segInfo[hit.prim];
+                    hit.inst = si.inst;
+                    hit.prim = si.prim;
+                }
+            }
+            h.t = hit.t;
+            h.u = hit.u;
+            h.v = hit.v;
+            h.prim = hit.prim;
+            h.instance = hit.inst;
+            h.kind = hit.kind;
+        }
+        else
+        {
+            bool occ = false;
+            if (S.numTriNodes)
+                occ = traverse_bvh<1, true, false>(S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, &st);
+            if (!occ && S.numSegNodes)
+                occ = traverse_bvh<2, true, false>(S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, &st);
+            h.kind = occ ? 1u : 0u;
+        }
+        hits[i] = h;
+    }
+}
+
+void launch_test_sampler(const LaunchCfg& cfg, uint32_t n, const uint32_t* x, const uint32_t* y, const uint32_t* sample, const uint32_t* maxs,
+                         const uint32_t* depth, const uint32_t* dim, float* out)
+{
+    k_test_sampler<<<grid_for(cfg, 2), 128, 0, cfg.stream>>>(n, x, y, sample, maxs, depth, dim, out);
+    SB_CUDA_CHECK(cudaGetLastError());
+}
+void launch_test_light_sample(const LaunchCfg& cfg, uint32_t n, const sb_light* lights, const float* hp, const float* u, uint32_t method, float* out)
+{
+    k_test_light_sample<<<grid_for(cfg, 2), 128, 0, cfg.stream>>>(n, lights, hp, u, method, out);
+    SB_CUDA_CHECK(cudaGetLastError());
+}
+void launch_test_trace(const LaunchCfg& cfg, const SceneDev& S, uint32_t n, const float* rays, uint32_t mode, sb_hit* hits)
+{
+    k_test_trace<<<grid_for(cfg, 2), 128, 0, cfg.stream>>>(S, n, rays, mode, hits);
+    SB_CUDA_CHECK(cudaGetLastError());
+}
+
+} // namespace sb

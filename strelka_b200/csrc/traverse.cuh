@@ -1,0 +1,271 @@
+// Software traversal of the compressed 8-wide BVH: closest-hit and any-hit queries over world-space
+// triangles (Moller-Trumbore on precomputed edges) and round cubic B-spline curve segments.
+// Replaces optixTrace (OptixRender.cu:120-129: mask 255, FLAG_NONE, no culling; closest_hit.cu:185-197:
+// mask RAY_MASK_SHADOW=3, TERMINATE_ON_FIRST_HIT) -- closed driver code in the reference.
+//
+// Determinism / parity rule shared with the CPU oracle: among hits with the same t the primitive with
+// the lower global id (instance-major, primitive-minor order of the scene arrays) wins, so the reported
+// hit does not depend on the shape of the acceleration structure; triangles beat curves on exact ties.
+#pragma once
+#include "bvh.cuh"
+#include "curve.cuh"
+
+namespace sb
+{
+
+#if defined(__CUDA_ARCH__)
+#define SB_LDG4(p) __ldg(reinterpret_cast<const uint4*>(p))
+#define SB_LDGF4(p) __ldg(reinterpret_cast<const float4*>(p))
+#else
+#define SB_LDG4(p) (*reinterpret_cast<const uint4*>(p))
+#define SB_LDGF4(p) (*reinterpret_cast<const float4*>(p))
+#endif
+
+// GEOMETRY_MASK_*, OptixRenderParams.h:9-17
+constexpr uint32_t kMaskTriangle = 1u, kMaskCurve = 2u, kMaskLight = 4u;
+constexpr uint32_t kRayMaskPrimary = 255u, kRayMaskShadow = 3u;
+
+struct TriRec // 48 B
+{
+    float4 v0; // xyz, w = bits(primitive index inside its mesh)
+    float4 e1; // v1 - v0, w = bits(instance | visibilityMask << 28)
+    float4 e2; // v2 - v0, w = bits(global triangle id)
+};
+struct SegRec // 64 B: world-space control points, w = radius
+{
+    float4 q[4];
+};
+struct SegInfo
+{
+    uint32_t prim; // optixGetPrimitiveIndex: index into the curve prim's segment list
+    uint32_t inst;
+    uint32_t firstPoint; // global index of the first control point
+    uint32_t pad;
+};
+
+struct Ray
+{
+    float3 o;
+    float tmin;
+    float3 d;
+    float tmax;
+};
+struct HitRec
+{
+    float t, u, v;
+    uint32_t prim, inst, kind; // kind 0 miss, 1 triangle, 2 curve
+    uint32_t gid;
+};
+struct TravStats
+{
+    uint32_t nodes, tris, segs, overflow;
+};
+
+constexpr int kStackSize = 32;
+
+SB_HD uint32_t byte_of(uint32_t w, int j)
+{
+    return (w >> (8 * j)) & 0xffu;
+}
+
+// Ray/child-box tests of one wide node -> 32-bit hit mask: bits 24..31 inner children in traversal
+// priority (highest first), bits 0..23 leaf primitives relative to primBase.
+SB_HD uint32_t wide_node_hits(const uint4& n0, const uint4& n1, const uint4& n2, const uint4& n3, const uint4& n4, const float3& o,
+                              const float3& idir, uint32_t octinv4, bool negx, bool negy, bool negz, float tmin, float tmax)
+{
+    const float3 p = mk3(u2f(n0.x), u2f(n0.y), u2f(n0.z));
+    const float ax = u2f((n0.w & 0xffu) << 23) * idir.x;
+    const float ay = u2f(((n0.w >> 8) & 0xffu) << 23) * idir.y;
+    const float az = u2f(((n0.w >> 16) & 0xffu) << 23) * idir.z;
+    const float bx = (p.x - o.x) * idir.x;
+    const float by = (p.y - o.y) * idir.y;
+    const float bz = (p.z - o.z) * idir.z;
+    uint32_t hitmask = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half)
+    {
+        const uint32_t meta4 = half ? n1.w : n1.z;
+        const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t innerMask4 = (isInner4 >> 4) * 0xffu;
+        const uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1f1f1f1fu;
+        const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+        const uint32_t qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z, qloz = half ? n3.y : n3.x;
+        const uint32_t qhix = half ? n3.w : n3.z, qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
+        const uint32_t nearx = negx ? qhix : qlox, farx = negx ? qlox : qhix;
+        const uint32_t neary = negy ? qhiy : qloy, fary = negy ? qloy : qhiy;
+        const uint32_t nearz = negz ? qhiz : qloz, farz = negz ? qloz : qhiz;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+            const float t0x = fmaf(float(byte_of(nearx, j)), ax, bx);
+            const float t0y = fmaf(float(byte_of(neary, j)), ay, by);
+            const float t0z = fmaf(float(byte_of(nearz, j)), az, bz);
+            const float t1x = fmaf(float(byte_of(farx, j)), ax, bx);
+            const float t1y = fmaf(float(byte_of(fary, j)), ay, by);
+            const float t1z = fmaf(float(byte_of(farz, j)), az, bz);
+            const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
+            // 1 + 2*gamma(3): conservative far plane (Ize 2013); also used by the CPU oracle's BVH
+            const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tmax)) * 1.0000004f;
+            if (cmin <= cmax)
+                hitmask |= byte_of(childBits4, j) << byte_of(bitIndex4, j);
+        }
+    }
+    return hitmask;
+}
+
+// Moller-Trumbore on (v0, e1, e2); expression tree identical to the oracle's (fma dot/cross).
+SB_HD bool intersect_tri(const float3& v0, const float3& e1, const float3& e2, const float3& o, const float3& d, float tmin, float tmax,
+                         float& t, float& u, float& v)
+{
+    const float3 p = cross_fma(d, e2);
+    const float det = dot_fma(e1, p);
+    if (det == 0.0f)
+        return false;
+    const float inv = 1.0f / det;
+    const float3 tv = o - v0;
+    u = dot_fma(tv, p) * inv;
+    if (!(u >= 0.0f && u <= 1.0f))
+        return false;
+    const float3 q = cross_fma(tv, e1);
+    v = dot_fma(d, q) * inv;
+    if (!(v >= 0.0f && u + v <= 1.0f))
+        return false;
+    t = dot_fma(e2, q) * inv;
+    return t > tmin && t <= tmax;
+}
+
+struct RayPrep
+{
+    float3 idir;
+    uint32_t octinv4;
+    uint32_t octinv;
+    bool negx, negy, negz;
+};
+SB_HD RayPrep prepare_ray(const float3& d)
+{
+    RayPrep r;
+    r.negx = d.x < 0.0f;
+    r.negy = d.y < 0.0f;
+    r.negz = d.z < 0.0f;
+    const uint32_t oct = (r.negx ? 1u : 0u) | (r.negy ? 2u : 0u) | (r.negz ? 4u : 0u);
+    r.octinv = 7u - oct;
+    r.octinv4 = r.octinv * 0x01010101u;
+    const float eps = 1e-20f;
+    r.idir.x = 1.0f / (fabsf(d.x) > eps ? d.x : copysignf(eps, d.x));
+    r.idir.y = 1.0f / (fabsf(d.y) > eps ? d.y : copysignf(eps, d.y));
+    r.idir.z = 1.0f / (fabsf(d.z) > eps ? d.z : copysignf(eps, d.z));
+    return r;
+}
+
+// KIND 1: triangles (prims = TriRec), KIND 2: curve segments (prims = SegRec).
+// ANY: stop at the first accepted hit (shadow rays).  hit/ray.tmax are updated in place.
+template <int KIND, bool ANY, bool STATS>
+SB_HD bool traverse_bvh(const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask, Ray& ray, const RayPrep& rp,
+                        HitRec& hit, TravStats* st)
+{
+    uint2 stack[kStackSize];
+    int sp = 0;
+    uint2 ngroup;
+    ngroup.x = 0u;
+    ngroup.y = 0x80000000u; // the root: one inner "child" at base 0
+    bool found = false;
+    for (;;)
+    {
+        uint2 tgroup;
+        tgroup.x = 0u;
+        tgroup.y = 0u;
+        if (ngroup.y > 0x00ffffffu)
+        {
+            const uint32_t hits = ngroup.y;
+            const uint32_t bit = bfind32(hits);
+            ngroup.y &= ~(1u << bit);
+            if (ngroup.y > 0x00ffffffu)
+            {
+                if (sp < kStackSize)
+                    stack[sp++] = ngroup;
+                else if (STATS)
+                    st->overflow++;
+            }
+            const uint32_t slot = (bit - 24u) ^ (rp.octinv & 7u);
+            const uint32_t rel = popc32(hits & ~(0xffffffffu << slot) & 0xffu);
+            const WideNode* np = nodes + (ngroup.x + rel);
+            const uint4 n0 = SB_LDG4(&np->n0), n1 = SB_LDG4(&np->n1), n2 = SB_LDG4(&np->n2), n3 = SB_LDG4(&np->n3), n4 = SB_LDG4(&np->n4);
+            if (STATS)
+                st->nodes++;
+            const uint32_t hm = wide_node_hits(n0, n1, n2, n3, n4, ray.o, rp.idir, rp.octinv4, rp.negx, rp.negy, rp.negz, ray.tmin, ray.tmax);
+            ngroup.x = n1.x;
+            ngroup.y = (hm & 0xff000000u) | (n0.w >> 24);
+            tgroup.x = n1.y;
+            tgroup.y = hm & 0x00ffffffu;
+        }
+        while (tgroup.y != 0u)
+        {
+            const uint32_t rel = bfind32(tgroup.y);
+            tgroup.y &= ~(1u << rel);
+            const uint32_t pi = tgroup.x + rel;
+            if (KIND == 1)
+            {
+                const TriRec* tr = reinterpret_cast<const TriRec*>(prims) + pi;
+                const float4 a = SB_LDGF4(&tr->v0), b = SB_LDGF4(&tr->e1), c = SB_LDGF4(&tr->e2);
+                if (STATS)
+                    st->tris++;
+                const uint32_t instMask = f2u(b.w);
+                if (!((instMask >> 28) & rayMask))
+                    continue;
+                float t, u, v;
+                if (intersect_tri(mk3(a), mk3(b), mk3(c), ray.o, ray.d, ray.tmin, ray.tmax, t, u, v))
+                {
+                    if (ANY)
+                        return true;
+                    const uint32_t gid = f2u(c.w);
+                    if (t < ray.tmax || !found || gid < hit.gid)
+                    {
+                        hit.t = t;
+                        hit.u = u;
+                        hit.v = v;
+                        hit.prim = f2u(a.w);
+                        hit.inst = instMask & 0x0fffffffu;
+                        hit.kind = 1u;
+                        hit.gid = gid;
+                        ray.tmax = t;
+                        found = true;
+                    }
+                }
+            }
+            else
+            {
+                const SegRec* sr = reinterpret_cast<const SegRec*>(prims) + pi;
+                float4 q[4];
+                q[0] = SB_LDGF4(&sr->q[0]);
+                q[1] = SB_LDGF4(&sr->q[1]);
+                q[2] = SB_LDGF4(&sr->q[2]);
+                q[3] = SB_LDGF4(&sr->q[3]);
+                if (STATS)
+                    st->segs++;
+                float t, u;
+                if (intersect_round_cubic(q, ray.o, ray.d, ray.tmin, ray.tmax, t, u))
+                {
+                    if (ANY)
+                        return true;
+                    hit.t = t;
+                    hit.u = u;
+                    hit.v = 0.0f;
+                    hit.prim = pi; // index into the SegInfo table; resolved by the caller
+                    hit.kind = 2u;
+                    hit.gid = pi;
+                    ray.tmax = t;
+                    found = true;
+                }
+            }
+        }
+        if (ngroup.y <= 0x00ffffffu)
+        {
+            if (sp == 0)
+                break;
+            ngroup = stack[--sp];
+        }
+    }
+    return found;
+}
+
+} // namespace sb

@@ -1,0 +1,493 @@
+// Per-path logic of the wavefront integrator (SB_HD: compiled by nvcc for the kernels in kernels.cu and,
+// for the CPU test-suite only, by g++ in tests/emul).
+//
+// One camera path = one iteration of the sample loop of __raygen__rg (OptixRender.cu:94-167).  The
+// reference runs it as a megakernel thread per pixel; here every bounce is three data-parallel stages
+// over SoA queues:   extend (closest hit)  ->  shade (this file)  ->  shadow (any hit + NEE add)
+// Surviving paths are compacted into the next queue with warp-aggregated atomics.
+//
+//   raygen_one : initSampler + generateCameraRay (OptixRender.cu:38-58, 96-113)
+//   shade_one  : __miss__ms (:250-257), __closesthit__light (:315-341), __closesthit__radiance
+//                (closest_hit.cu:456-606) and the tail of the bounce loop (OptixRender.cu:131-153)
+//   shadow_one : traceOcclusion (closest_hit.cu:185-197) + the NEE add (:586)
+//   accumulate : accumulate() (OptixRender.cu:60-78) in its shardable form S = sum_k T(L_k)
+#pragma once
+#include "sampler.cuh"
+#include "lights.cuh"
+#include "bsdf.cuh"
+#include "bvh_build.h"
+
+namespace sb
+{
+
+constexpr uint32_t kMaxDepth = 32;
+constexpr uint32_t kCountShadowBase = 32; // counts[0..31] path queues per depth, counts[32..63] shadow queues
+constexpr uint32_t kNumCounts = 64;
+
+// per-path flag bits (stored in thr.w)
+constexpr uint32_t kFlagInside = 1u, kFlagSpecular = 2u;
+constexpr uint32_t kFlagEventShift = 2u; // EventType of the first bounce (2 bits): 0 undef, 1 absorb, 2 diffuse, 3 specular
+
+struct FrameParams
+{
+    uint32_t width, height, tilesX, nPixPadded;
+    uint32_t maxDepth, sppTotal, rectMethod, debug;
+    float shadowTmin, materialTmin;
+    float clipToView[16], viewToWorld[16];
+    float exposure[3];
+    uint32_t sampleBase, sampleStride, chunk, numLights;
+};
+
+struct StatCounters // device-resident, persistent across launches
+{
+    unsigned long long paths, radianceRays, shadowRays, nodes, tris, segs, overflow;
+};
+
+struct Queues
+{
+    float4* rayO[2]; // origin.xyz, bits(pathId)
+    float4* rayD[2]; // dir.xyz, lastBsdfPdf
+    float4* thr[2]; // throughput.xyz, bits(flags)
+    float4* hitA; // t, u, v, bits(prim)
+    uint32_t* hitB; // instance | kind << 30
+    float4* Lacc; // per pathId: radiance accumulated along the path (w unused)
+    float4* shO; // origin.xyz, tmin
+    float4* shD; // dir.xyz, tmax
+    float4* shC; // contribution.xyz, bits(pathId)
+    uint32_t* counts; // kNumCounts
+    StatCounters* stats;
+};
+
+// Warp-aggregated slot allocation: one atomicAdd per warp instead of one per surviving lane.
+SB_HD uint32_t queue_alloc(uint32_t* counter)
+{
+#if defined(__CUDA_ARCH__)
+    const unsigned mask = __activemask();
+    const int leader = __ffs(mask) - 1;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned rank = __popc(mask & ((1u << lane) - 1u));
+    uint32_t base = 0;
+    if (int(lane) == leader)
+        base = atomicAdd(counter, uint32_t(__popc(mask)));
+    base = __shfl_sync(mask, base, leader);
+    return base + rank;
+#else
+    return (*counter)++;
+#endif
+}
+
+SB_HD void path_pixel(const FrameParams& P, uint32_t pathId, uint32_t& x, uint32_t& y, uint32_t& k)
+{
+    k = pathId / P.nPixPadded;
+    const uint32_t p = pathId - k * P.nPixPadded;
+    const uint32_t tile = p >> 5, within = p & 31u;
+    x = (tile % P.tilesX) * 8u + (within & 7u); // 8x4-pixel tiles: one warp = one tile of primary rays
+    y = (tile / P.tilesX) * 4u + (within >> 3);
+}
+
+// row-major 4x4 * float4 as sutil::Matrix4x4 does it (sutil/Matrix.h)
+SB_HD float4 mat4_mul(const float* m, const float4& v)
+{
+    return mk4(m[0] * v.x + m[1] * v.y + m[2] * v.z + m[3] * v.w, m[4] * v.x + m[5] * v.y + m[6] * v.z + m[7] * v.w,
+               m[8] * v.x + m[9] * v.y + m[10] * v.z + m[11] * v.w, m[12] * v.x + m[13] * v.y + m[14] * v.z + m[15] * v.w);
+}
+
+SB_HD void raygen_one(const FrameParams& P, const Queues& Q, uint32_t pathId)
+{
+    uint32_t x, y, k;
+    path_pixel(P, pathId, x, y, k);
+    Q.Lacc[pathId] = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (x >= P.width || y >= P.height)
+        return;
+    const uint32_t sidx = sampler_index(x, y, P.sampleBase + k * P.sampleStride, P.sppTotal);
+    const uint32_t s0 = fmix32(52u);
+    const uint32_t index = owen_scramble(sidx, s0);
+    const float jx = u32_to_unit(owen_scramble(sobol_u32(index, 0), seed_combine(s0, 0)));
+    const float jy = u32_to_unit(owen_scramble(sobol_u32(index, 1), seed_combine(s0, 1)));
+    // generateCameraRay, OptixRender.cu:38-58
+    const float posx = float(x) + jx, posy = float(y) + jy;
+    const float ndcx = (posx / float(P.width)) * 2.0f - 1.0f;
+    const float ndcy = (posy / float(P.height)) * 2.0f - 1.0f;
+    const float4 vs = mat4_mul(P.clipToView, mk4(ndcx, ndcy, 1.0f, 1.0f));
+    const float4 wdir = mat4_mul(P.viewToWorld, mk4(vs.x, vs.y, vs.z, 0.0f));
+    const float3 origin = mk3(mat4_mul(P.viewToWorld, mk4(0.0f, 0.0f, 0.0f, 1.0f)));
+    const float3 dir = normalize(mk3(wdir));
+    const uint32_t slot = queue_alloc(&Q.counts[0]);
+    Q.rayO[0][slot] = mk4(origin, u2f(pathId));
+    Q.rayD[0][slot] = mk4(dir, 0.0f);
+    Q.thr[0][slot] = mk4(1.0f, 1.0f, 1.0f, u2f(0u));
+}
+
+// unpackNormal, closest_hit.cu:236-244
+SB_HD float3 unpack_normal(uint32_t val)
+{
+    float3 n;
+    n.z = ((val & 0xfff00000u) >> 20) / 511.99999f * 2.0f - 1.0f;
+    n.y = ((val & 0x000ffc00u) >> 10) / 511.99999f * 2.0f - 1.0f;
+    n.x = (val & 0x000003ffu) / 511.99999f * 2.0f - 1.0f;
+    return n;
+}
+// offset_ray, closest_hit.cu:218-233 (Ray Tracing Gems ch. 6)
+SB_HD float3 offset_ray(const float3& p, const float3& n)
+{
+    const float origin = 1.0f / 32.0f;
+    const float float_scale = 1.0f / 65536.0f;
+    const float int_scale = 256.0f;
+    const int ix = int(int_scale * n.x), iy = int(int_scale * n.y), iz = int(int_scale * n.z);
+    const float3 pi = mk3(u2f(uint32_t(int(f2u(p.x)) + ((p.x < 0) ? -ix : ix))), u2f(uint32_t(int(f2u(p.y)) + ((p.y < 0) ? -iy : iy))),
+                          u2f(uint32_t(int(f2u(p.z)) + ((p.z < 0) ? -iz : iz))));
+    return mk3(fabsf(p.x) < origin ? p.x + float_scale * n.x : pi.x, fabsf(p.y) < origin ? p.y + float_scale * n.y : pi.y,
+               fabsf(p.z) < origin ? p.z + float_scale * n.z : pi.z);
+}
+// interpolateAttrib, closest_hit.cu:199-205
+SB_HD float3 interp3(const float3& a, const float3& b, const float3& c, float bx, float by)
+{
+    return a * (1.0f - bx - by) + b * bx + c * by;
+}
+
+struct Surface
+{
+    float3 position, normal, geomNormal, tangent;
+};
+
+// fillTriangleGeomData, closest_hit.cu:365-421 (quirks Q11, Q12)
+SB_HD Surface tri_surface(const SceneDev& S, const InstDev& I, uint32_t prim, float bu, float bv, bool inside)
+{
+    const sb_mesh m = S.meshes[I.geom];
+    const uint32_t i0 = S.indices[m.index + prim * 3 + 0], i1 = S.indices[m.index + prim * 3 + 1], i2 = S.indices[m.index + prim * 3 + 2];
+    const sb_vertex v0 = S.vertices[m.vb_offset + i0], v1 = S.vertices[m.vb_offset + i1], v2 = S.vertices[m.vb_offset + i2];
+    const float3 p0 = mk3(v0.pos[0], v0.pos[1], v0.pos[2]), p1 = mk3(v1.pos[0], v1.pos[1], v1.pos[2]), p2 = mk3(v2.pos[0], v2.pos[1], v2.pos[2]);
+    Surface s;
+    s.position = xform_point(I.o2w, interp3(p0, p1, p2, bu, bv));
+    s.normal = normalize(xform_normal(I.w2o, interp3(unpack_normal(v0.normal), unpack_normal(v1.normal), unpack_normal(v2.normal), bu, bv)));
+    s.geomNormal = normalize(xform_normal(I.w2o, cross(p1 - p0, p2 - p0)));
+    s.tangent = normalize(xform_normal(I.w2o, interp3(unpack_normal(v0.tangent), unpack_normal(v1.tangent), unpack_normal(v2.tangent), bu, bv)));
+    const float flip = inside ? -1.0f : 1.0f;
+    s.geomNormal *= flip;
+    s.normal *= flip;
+    return s;
+}
+
+// fillCurveGeomData, closest_hit.cu:423-454 (quirk Q14)
+SB_HD Surface curve_surface(const SceneDev& S, const InstDev& I, uint32_t segIndex, float u, float t, const float3& rayO, const float3& rayD,
+                            bool inside)
+{
+    const uint32_t first = S.segInfo[segIndex].firstPoint;
+    float4 q[4];
+    for (int k = 0; k < 4; ++k)
+    {
+        const uint32_t pi = first + k;
+        q[k] = mk4(S.curvePoints[3 * pi], S.curvePoints[3 * pi + 1], S.curvePoints[3 * pi + 2], pi < S.numCurveRadii ? S.curveRadii[pi] : 0.0f);
+    }
+    const CubicSeg bc = cubic_from_bspline(q);
+    float3 hitPoint = rayO + t * rayD;
+    hitPoint = xform_point(I.w2o, hitPoint);
+    Surface s;
+    s.normal = normalize(xform_normal(I.w2o, cubic_surface_normal(bc, u, hitPoint)));
+    s.tangent = normalize(xform_normal(I.w2o, cubic_tangent(bc, u)));
+    s.normal *= (inside ? -1.0f : 1.0f);
+    s.position = xform_point(I.o2w, hitPoint);
+    s.geomNormal = s.normal;
+    return s;
+}
+
+// One bounce of one path after its closest-hit query.  `depth` == prd.depth == sampler.depth.
+SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, uint32_t depth, uint32_t slot)
+{
+    const int qi = int(depth & 1u), qo = qi ^ 1;
+    const float4 ro = Q.rayO[qi][slot], rd = Q.rayD[qi][slot], th = Q.thr[qi][slot];
+    const float4 ha = Q.hitA[slot];
+    const uint32_t hb = Q.hitB[slot];
+    const uint32_t pathId = f2u(ro.w);
+    const float3 rayO = mk3(ro), rayD = mk3(rd);
+    float3 throughput = mk3(th);
+    uint32_t flags = f2u(th.w);
+    const float lastBsdfPdf = rd.w;
+    const uint32_t kind = hb >> 30;
+    if (kind == 0u)
+        return; // __miss__ms: radiance += throughput * bg_color(0); path ends
+    const InstDev I = S.instances[hb & 0x0fffffffu];
+    float3 Lpath = mk3(Q.Lacc[pathId]);
+
+    if (I.type == SB_INSTANCE_LIGHT)
+    {
+        // __closesthit__light, OptixRender.cu:315-341 (quirks Q5, Q19)
+        if (I.light < S.numLights)
+        {
+            const sb_light l = S.lights[I.light];
+            const float3 hitPoint = rayO + ha.x * rayD;
+            const float3 ln = light_normal(l, hitPoint);
+            const float3 color = mk3(l.color[0], l.color[1], l.color[2]);
+            if (-dot(rayD, ln) > 0.0f)
+            {
+                if (depth == 0u || (flags & kFlagSpecular))
+                {
+                    Lpath += throughput * color * -dot(rayD, ln);
+                }
+                else
+                {
+                    const float lightPdf = light_pdf(l, hitPoint, rayO) / float(S.numLights);
+                    const float w = mis_balance(lastBsdfPdf, lightPdf);
+                    Lpath += throughput * color * -dot(rayD, ln) * w;
+                }
+                Q.Lacc[pathId] = mk4(Lpath, 0.0f);
+            }
+        }
+        return; // throughput = 0: the path ends
+    }
+
+    // ---- __closesthit__radiance, closest_hit.cu:456-606 --------------------------------------------
+    const bool isInside = (flags & kFlagInside) != 0u;
+    const Surface sf = (kind == 1u) ? tri_surface(S, I, f2u(ha.w), ha.y, ha.z, isInside) : curve_surface(S, I, f2u(ha.w), ha.y, ha.x, rayO, rayD, isInside);
+    if (P.debug == 1u)
+    {
+        Q.Lacc[pathId] = mk4((sf.normal + mk3(1.0f)) * 0.5f, 0.0f); // closest_hit.cu:504-508
+        return;
+    }
+    const sb_material mat = S.materials[I.material];
+    uint32_t px, py, pk;
+    path_pixel(P, pathId, px, py, pk);
+    const uint32_t sidx = sampler_index(px, py, P.sampleBase + pk * P.sampleStride, P.sppTotal);
+    // the five distinct Sobol values of this bounce (quirk Q2): xi = v[0..3], lightId = v[2],
+    // lightPoint = (v[3], v[4]), russian roulette = v[4]
+    const Sample5 rn = sampler_sample5(sidx, depth);
+    const float3 k1 = -rayD;
+    const BsdfSample bs = bsdf_sample(mat, sf.normal, sf.geomNormal, k1, mk4(rn.v[0], rn.v[1], rn.v[2], rn.v[3]));
+    if (bs.event == EV_ABSORB)
+    {
+        return; // throughput = 0 (firstEventType = eAbsorb only matters for the AOVs)
+    }
+    const bool specularBounce = (bs.event & EV_SPECULAR) != 0;
+    if (depth == 0u)
+    {
+        uint32_t ev = 0u;
+        if (bs.event & EV_DIFFUSE)
+            ev = 2u;
+        if (bs.event & EV_GLOSSY)
+            ev = 3u;
+        flags = (flags & ~(3u << kFlagEventShift)) | (ev << kFlagEventShift);
+    }
+    if (bs.event & (EV_DIFFUSE | EV_GLOSSY))
+    {
+        // estimateDirectLighting + sampleLight, closest_hit.cu:260-324
+        if (S.numLights > 0u) // numLights == 0 is undefined behaviour in the reference (quirk Q18)
+        {
+            uint32_t lightId = uint32_t(float(S.numLights) * rn.v[2]);
+            if (lightId >= S.numLights)
+                lightId = S.numLights - 1u;
+            const float lightSelectionPdf = 1.0f / float(S.numLights);
+            const sb_light l = S.lights[lightId];
+            const LightSample ls = sample_light(l, rn.v[3], rn.v[4], sf.position, P.rectMethod);
+            const float3 Li = mk3(l.color[0], l.color[1], l.color[2]);
+            if (dot(sf.normal, ls.L) > 0.0f && -dot(ls.L, ls.normal) > 0.0 && all_nonzero(Li))
+            {
+                const float lightPdf = ls.pdf * lightSelectionPdf;
+                const float3 radiance = Li * saturate(dot(sf.normal, ls.L)); // visibility applied by the shadow stage
+                if (isnan3(radiance) || isnanf_(lightPdf))
+                {
+                    Q.Lacc[pathId] = mk4(10000.0f, 0.0f, 0.0f, 0.0f); // quirk Q17
+                    return;
+                }
+                const bool nextEventValid = ((dot(ls.L, sf.normal) > 0.0f) != isInside) && lightPdf != 0.0f;
+                if (nextEventValid)
+                {
+                    const BsdfEval ev = bsdf_evaluate(mat, sf.normal, sf.geomNormal, k1, ls.L);
+                    if (isnan3(ev.diffuse) || isnan3(ev.glossy))
+                    {
+                        Q.Lacc[pathId] = mk4(10000.0f, 0.0f, 0.0f, 0.0f);
+                        return;
+                    }
+                    if (ev.pdf > 0.0f)
+                    {
+                        const float3 radianceOverPdf = radiance / lightPdf;
+                        const float w = mis_balance(lightPdf, ev.pdf);
+                        const float3 contrib = throughput * radianceOverPdf * w * (ev.diffuse + ev.glossy);
+                        if (contrib.x != 0.0f || contrib.y != 0.0f || contrib.z != 0.0f)
+                        {
+                            const uint32_t sslot = queue_alloc(&Q.counts[kCountShadowBase + depth]);
+                            Q.shO[sslot] = mk4(offset_ray(sf.position, sf.geomNormal), P.shadowTmin);
+                            Q.shD[sslot] = mk4(ls.L, ls.distToLight);
+                            Q.shC[sslot] = mk4(contrib, u2f(pathId));
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // next path segment, closest_hit.cu:591-605
+    float3 newOrigin;
+    if (bs.event & EV_TRANSMISSION)
+    {
+        flags ^= kFlagInside;
+        newOrigin = offset_ray(sf.position, -sf.geomNormal);
+    }
+    else
+    {
+        newOrigin = offset_ray(sf.position, sf.geomNormal);
+    }
+    flags = specularBounce ? (flags | kFlagSpecular) : (flags & ~kFlagSpecular);
+    const float newPdf = specularBounce ? 1.0f : bs.pdf; // quirk Q19
+    throughput *= bs.bsdf_over_pdf;
+    // tail of the bounce loop, OptixRender.cu:134-153
+    if (depth > 3u)
+    {
+        const float p = maxcomp(throughput);
+        if (rn.v[4] > p)
+            return;
+        throughput *= 1.0f / (p + 1e-5f);
+    }
+    if (dot(throughput, throughput) < 1e-5f)
+        return;
+    if (depth + 1u >= P.maxDepth)
+        return;
+    const uint32_t nslot = queue_alloc(&Q.counts[depth + 1u]);
+    Q.rayO[qo][nslot] = mk4(newOrigin, u2f(pathId));
+    Q.rayD[qo][nslot] = mk4(bs.k2, newPdf);
+    Q.thr[qo][nslot] = mk4(throughput, u2f(flags));
+}
+
+// closest hit of one queued ray: triangles first, then curves (strictly closer only)
+template <bool STATS>
+SB_HD void extend_one(const FrameParams& P, const SceneDev& S, const Queues& Q, uint32_t depth, uint32_t slot, TravStats* st)
+{
+    const int qi = int(depth & 1u);
+    const float4 ro = Q.rayO[qi][slot], rd = Q.rayD[qi][slot];
+    Ray ray;
+    ray.o = mk3(ro);
+    ray.d = mk3(rd);
+    ray.tmin = P.materialTmin;
+    ray.tmax = 1e16f;
+    const RayPrep rp = prepare_ray(ray.d);
+    HitRec hit;
+    hit.t = 0.0f;
+    hit.u = hit.v = 0.0f;
+    hit.prim = hit.inst = hit.kind = 0u;
+    hit.gid = 0xffffffffu;
+    if (S.numTriNodes)
+        traverse_bvh<1, false, STATS>(S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, st);
+    if (S.numSegNodes)
+    {
+        if (traverse_bvh<2, false, STATS>(S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, st))
+            hit.inst = S.segInfo[hit.prim].inst;
+    }
+    Q.hitA[slot] = mk4(hit.t, hit.u, hit.v, u2f(hit.prim));
+    Q.hitB[slot] = hit.inst | (hit.kind << 30);
+}
+
+template <bool STATS>
+SB_HD void shadow_one(const SceneDev& S, const Queues& Q, uint32_t j, TravStats* st)
+{
+    const float4 so = Q.shO[j], sd = Q.shD[j], sc = Q.shC[j];
+    Ray ray;
+    ray.o = mk3(so);
+    ray.tmin = so.w;
+    ray.d = mk3(sd);
+    ray.tmax = sd.w;
+    const RayPrep rp = prepare_ray(ray.d);
+    HitRec hit;
+    hit.gid = 0xffffffffu;
+    hit.kind = 0u;
+    bool occluded = false;
+    if (S.numTriNodes)
+        occluded = traverse_bvh<1, true, STATS>(S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, st);
+    if (!occluded && S.numSegNodes)
+        occluded = traverse_bvh<2, true, STATS>(S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, st);
+    if (!occluded)
+    {
+        const uint32_t pathId = f2u(sc.w);
+        const float4 L = Q.Lacc[pathId];
+        Q.Lacc[pathId] = mk4(L.x + sc.x, L.y + sc.y, L.z + sc.z, 0.0f);
+    }
+}
+
+// tonemap / inverseTonemap, postprocessing/Utils.h:5-15
+SB_HD float3 tonemap3(float3 c, const float3& e)
+{
+    c = c * e;
+    return c / (c + mk3(1.0f));
+}
+SB_HD float3 inverse_tonemap3(const float3& c, const float3& e)
+{
+    return c / (e - c * e);
+}
+
+// Fold the finished samples of one (padded) pixel into the accumulation buffer.
+//  mode 0: S += sum_k T(L_k)                      (spp == 1 per launch: the reference's running mean of T)
+//  mode 1: reference lerp for a launch of `chunk` samples (quirk Q1: weight 1/(subframe+1))
+//  mode 2: no accumulation: `direct` receives the linear mean of the launch
+SB_HD void accumulate_pixel(const FrameParams& P, const Queues& Q, float4* S, float4* direct, uint32_t mode, uint32_t subframe, uint32_t p)
+{
+    const uint32_t tile = p >> 5, within = p & 31u;
+    const uint32_t x = (tile % P.tilesX) * 8u + (within & 7u), y = (tile / P.tilesX) * 4u + (within >> 3);
+    if (x >= P.width || y >= P.height)
+        return;
+    const uint32_t lin = y * P.width + x;
+    const float3 e = mk3(P.exposure[0], P.exposure[1], P.exposure[2]);
+    if (mode == 0u)
+    {
+        float3 s = mk3(S[lin]);
+        for (uint32_t k = 0; k < P.chunk; ++k)
+            s += tonemap3(mk3(Q.Lacc[k * P.nPixPadded + p]), e);
+        S[lin] = mk4(s, 0.0f);
+        return;
+    }
+    float3 result = mk3(0.0f);
+    for (uint32_t k = 0; k < P.chunk; ++k)
+        result += mk3(Q.Lacc[k * P.nPixPadded + p]);
+    result = result / float(P.chunk);
+    if (mode == 2u)
+    {
+        direct[lin] = mk4(result, 1.0f);
+        return;
+    }
+    // S holds n * A with A the tone-mapped running value; the reference lerps A towards T(result)
+    float3 A = tonemap3(result, e);
+    if (subframe > 0u)
+    {
+        const float3 prev = mk3(S[lin]) / float(subframe);
+        const float a = 1.0f / float(subframe + 1u);
+        A = lerp(prev, A, a);
+    }
+    S[lin] = mk4(A * float(subframe + P.chunk), 0.0f);
+}
+
+// image = T^-1(S / n), then the optional post-process of OptixRender.cpp:1045-1049 (Tonemappers.cu)
+SB_HD float4 resolve_pixel(const float4& s, uint32_t n, const float3& e, uint32_t tonemapper, float gamma)
+{
+    float3 c = mk3(0.0f);
+    if (n > 0u)
+        c = inverse_tonemap3(mk3(s) / float(n), e);
+    if (tonemapper == 1u)
+    {
+        const float3 r = c * e;
+        const float lum = r.x * 0.299f + r.y * 0.587f + r.z * 0.114f;
+        c = r / (lum + 1);
+    }
+    else if (tonemapper == 2u)
+    {
+        const float3 r = c * e;
+        float3 v = mk3(0.59719f * r.x + 0.35458f * r.y + 0.04823f * r.z, 0.07600f * r.x + 0.90834f * r.y + 0.01566f * r.z,
+                       0.02840f * r.x + 0.13383f * r.y + 0.83777f * r.z);
+        const float3 a = v * (v + mk3(0.0245786f)) - mk3(0.000090537f);
+        const float3 b = v * (0.983729f * v + mk3(0.4329510f)) + mk3(0.238081f);
+        v = a / b;
+        c = mk3(1.60475f * v.x + -0.53108f * v.y + -0.07367f * v.z, -0.10208f * v.x + 1.10813f * v.y + -0.00605f * v.z,
+                -0.00327f * v.x + -0.07276f * v.y + 1.07602f * v.z);
+        c = mk3(saturate(c.x), saturate(c.y), saturate(c.z));
+    }
+    else if (tonemapper == 3u)
+    {
+        const float3 x = c * e;
+        const float A = 2.51f, B = 0.03f, C = 2.43f, D = 0.59f, E = 0.14f;
+        const float3 r = (x * (A * x + mk3(B))) / (x * (C * x + mk3(D)) + mk3(E));
+        c = mk3(saturate(r.x), saturate(r.y), saturate(r.z));
+    }
+    if (gamma > 0.0f)
+    {
+        const float ig = 1.0f / gamma;
+        c = mk3(powf(c.x, ig), powf(c.y, ig), powf(c.z, ig));
+    }
+    return mk4(c, 1.0f);
+}
+
+} // namespace sb
