@@ -211,12 +211,17 @@ typedef struct sb_device_cfg
 
 enum
 {
-    SB_CFG_TRAVERSAL_STATS = 1u /* run the instrumented traversal kernels (counts nodes/prims per ray) */
+    SB_CFG_TRAVERSAL_STATS = 1u, /* run the instrumented traversal kernels (counts nodes/prims per ray) */
+    SB_CFG_STAGE_TIMERS = 2u     /* bracket every kernel launch with CUDA events (per-stage device time) */
 };
 
 /* RenderFactory::createRender(RenderType::eCompute) + Render::init()
  * (render.cpp:10-26, render.h:13, OptixRender.cpp:1059-1105). */
 sb_result sb_create(const sb_device_cfg* cfg, sb_ctx** out_ctx);
+/* Run on a caller-owned CUDA stream (cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream) instead
+ * of the context's own one, so that the caller's events and collectives are stream-ordered with the
+ * render (reference: one created stream, OptixRender.cpp:168-170).  NULL restores the private stream. */
+sb_result sb_set_stream(sb_ctx* ctx, void* cuda_stream);
 /* OptiXRender::~OptiXRender (OptixRender.cpp:159-161; the reference leaks, we free). */
 void sb_destroy(sb_ctx* ctx);
 /* Last error text of this context (or of sb_create when ctx == NULL). Never NULL. */
@@ -304,11 +309,15 @@ typedef struct sb_counters
     uint64_t paths;          /* camera paths started */
     uint64_t radiance_rays;  /* closest-hit rays traced */
     uint64_t shadow_rays;    /* any-hit rays traced */
-    /* SB_CFG_TRAVERSAL_STATS only (else 0): totals over all traced rays */
+    /* SB_CFG_TRAVERSAL_STATS only (else 0): totals over the closest-hit (radiance) rays ... */
     uint64_t nodes_visited;  /* 80 B CWBVH nodes fetched */
     uint64_t tris_tested;    /* 48 B triangle records fetched */
     uint64_t segs_tested;    /* 64 B curve-segment records fetched */
     uint64_t stack_overflows;
+    /* ... and over the any-hit (shadow) rays */
+    uint64_t nodes_visited_shadow;
+    uint64_t tris_tested_shadow;
+    uint64_t segs_tested_shadow;
     /* geometry / build info */
     uint64_t num_triangles;  /* world-space triangles in the BVH */
     uint64_t num_segments;   /* curve segments in the BVH */
@@ -316,6 +325,11 @@ typedef struct sb_counters
     uint64_t bvh_nodes_curve;
     double build_ms;         /* last sb_set_scene: upload + flatten + BVH build */
     double render_ms;        /* device time of the last render call (CUDA events) */
+    uint64_t kernel_launches; /* kernels launched by render/resolve calls since the last reset */
+    /* SB_CFG_STAGE_TIMERS only: device milliseconds and launch counts per stage since the last reset,
+     * order: raygen, extend, shade, shadow, accumulate, resolve */
+    double stage_ms[6];
+    uint64_t stage_launches[6];
 } sb_counters;
 
 sb_result sb_get_counters(sb_ctx* ctx, sb_counters* out); /* synchronizes */

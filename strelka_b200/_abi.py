@@ -80,6 +80,7 @@ SB_INSTANCE_MESH, SB_INSTANCE_LIGHT, SB_INSTANCE_CURVE = 0, 1, 2
 SB_MATERIAL_DIFFUSE, SB_MATERIAL_USD_PREVIEW_SURFACE, SB_MATERIAL_HAIR = 0, 1, 2
 SB_FORMAT_UNSIGNED_BYTE4, SB_FORMAT_FLOAT4, SB_FORMAT_FLOAT3 = 0, 1, 2
 SB_CFG_TRAVERSAL_STATS = 1
+SB_CFG_STAGE_TIMERS = 2
 
 
 class sb_scene_view(C.Structure):
@@ -118,18 +119,27 @@ class sb_counters(C.Structure):
         ("paths", C.c_uint64), ("radiance_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
         ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("segs_tested", C.c_uint64),
         ("stack_overflows", C.c_uint64),
+        ("nodes_visited_shadow", C.c_uint64), ("tris_tested_shadow", C.c_uint64), ("segs_tested_shadow", C.c_uint64),
         ("num_triangles", C.c_uint64), ("num_segments", C.c_uint64),
         ("bvh_nodes_tri", C.c_uint64), ("bvh_nodes_curve", C.c_uint64),
         ("build_ms", C.c_double), ("render_ms", C.c_double),
+        ("kernel_launches", C.c_uint64),
+        ("stage_ms", C.c_double * 6), ("stage_launches", C.c_uint64 * 6),
     ]
 
+    STAGES = ("raygen", "extend", "shade", "shadow", "accumulate", "resolve")
+
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        d = {}
+        for n, _ in self._fields_:
+            v = getattr(self, n)
+            d[n] = list(v) if hasattr(v, "__len__") else v
+        return d
 
 
 # Every symbol include/sb/sb_api.h declares (tests/test_abi.py checks they are all exported).
 ABI_SYMBOLS = [
-    "sb_settings_default", "sb_create", "sb_destroy", "sb_last_error", "sb_set_scene", "sb_set_camera",
+    "sb_settings_default", "sb_create", "sb_set_stream", "sb_destroy", "sb_last_error", "sb_set_scene", "sb_set_camera",
     "sb_set_camera_matrices", "sb_set_settings", "sb_reset_accumulation", "sb_subframe_index",
     "sb_buffer_create", "sb_buffer_destroy", "sb_buffer_resize", "sb_buffer_map", "sb_buffer_unmap",
     "sb_buffer_host_ptr", "sb_buffer_host_size", "sb_buffer_device_ptr", "sb_buffer_width", "sb_buffer_height",
@@ -157,6 +167,7 @@ def load_library() -> C.CDLL:
     sig = {
         "sb_settings_default": (None, [P(sb_settings)]),
         "sb_create": (C.c_int, [P(sb_device_cfg), P(vp)]),
+        "sb_set_stream": (C.c_int, [vp, vp]),
         "sb_destroy": (None, [vp]),
         "sb_last_error": (C.c_char_p, [vp]),
         "sb_set_scene": (C.c_int, [vp, P(sb_scene_view)]),

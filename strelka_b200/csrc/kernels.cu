@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kBlock) k_raygen(FrameParams P, Queues Q)
 }
 
 // flush per-thread traversal statistics with one atomic per warp
-__device__ __forceinline__ void flush_stats(StatCounters* g, const TravStats& st)
+__device__ __forceinline__ void flush_stats(StatCounters* g, const TravStats& st, bool shadow)
 {
     unsigned n = st.nodes, t = st.tris, s = st.segs, o = st.overflow;
     for (int off = 16; off > 0; off >>= 1)
@@ -49,11 +49,11 @@ __device__ __forceinline__ void flush_stats(StatCounters* g, const TravStats& st
     if ((threadIdx.x & 31) == 0)
     {
         if (n)
-            atomicAdd(&g->nodes, (unsigned long long)n);
+            atomicAdd(shadow ? &g->nodesSh : &g->nodes, (unsigned long long)n);
         if (t)
-            atomicAdd(&g->tris, (unsigned long long)t);
+            atomicAdd(shadow ? &g->trisSh : &g->tris, (unsigned long long)t);
         if (s)
-            atomicAdd(&g->segs, (unsigned long long)s);
+            atomicAdd(shadow ? &g->segsSh : &g->segs, (unsigned long long)s);
         if (o)
             atomicAdd(&g->overflow, (unsigned long long)o);
     }
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(kBlock) k_extend(FrameParams P, SceneDev S, Qu
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         extend_one<STATS>(P, S, Q, depth, i, &st);
     if (STATS)
-        flush_stats(Q.stats, st);
+        flush_stats(Q.stats, st, false);
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(&Q.stats->radianceRays, (unsigned long long)n);
 }
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kBlock) k_shadow(SceneDev S, Queues Q, uint32_
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         shadow_one<STATS>(S, Q, i, &st);
     if (STATS)
-        flush_stats(Q.stats, st);
+        flush_stats(Q.stats, st, true);
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(&Q.stats->shadowRays, (unsigned long long)n);
 }
@@ -159,6 +159,82 @@ __global__ void __launch_bounds__(256) k_copy_image(const float4* src, void* out
 
 // ---- launchers -------------------------------------------------------------------------------------
 
+cudaEvent_t StageTimer::get()
+{
+    if (!pool.empty())
+    {
+        cudaEvent_t e = pool.back();
+        pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    SB_CUDA_CHECK(cudaEventCreate(&e));
+    return e;
+}
+void StageTimer::collect()
+{
+    for (const Pending& p : pending)
+    {
+        float t = 0.0f;
+        if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess)
+        {
+            ms[p.stage] += t;
+            launches[p.stage] += 1;
+        }
+        else
+        {
+            cudaGetLastError();
+        }
+        pool.push_back(p.a);
+        pool.push_back(p.b);
+    }
+    pending.clear();
+}
+void StageTimer::reset()
+{
+    collect();
+    for (int i = 0; i < kNumStages; ++i)
+    {
+        ms[i] = 0.0;
+        launches[i] = 0;
+    }
+}
+void StageTimer::release()
+{
+    collect();
+    for (cudaEvent_t e : pool)
+        cudaEventDestroy(e);
+    pool.clear();
+}
+
+// counts the launch and, when stage timers are on, brackets it with events
+struct ScopedStage
+{
+    const LaunchCfg& cfg;
+    StageTimer::Pending p;
+    bool on;
+    ScopedStage(const LaunchCfg& c, int stage) : cfg(c), on(c.timer != nullptr)
+    {
+        if (cfg.launchCount)
+            ++*cfg.launchCount;
+        if (on)
+        {
+            p.stage = stage;
+            p.a = cfg.timer->get();
+            p.b = cfg.timer->get();
+            cudaEventRecord(p.a, cfg.stream);
+        }
+    }
+    ~ScopedStage()
+    {
+        if (on)
+        {
+            cudaEventRecord(p.b, cfg.stream);
+            cfg.timer->pending.push_back(p);
+        }
+    }
+};
+
 static inline unsigned grid_for(const LaunchCfg& cfg, int blocksPerSm)
 {
     return unsigned(cfg.numSms * blocksPerSm);
@@ -168,16 +244,26 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
 {
     cudaStream_t st = cfg.stream;
     SB_CUDA_CHECK(cudaMemsetAsync(Q.counts, 0, sizeof(uint32_t) * kNumCounts, st));
-    k_raygen<<<grid_for(cfg, 8), kBlock, 0, st>>>(P, Q);
+    {
+        ScopedStage sc(cfg, kStageRaygen);
+        k_raygen<<<grid_for(cfg, 8), kBlock, 0, st>>>(P, Q);
+    }
     for (uint32_t depth = 0; depth < P.maxDepth; ++depth)
     {
-        if (stats)
-            k_extend<true><<<grid_for(cfg, 8), kBlock, 0, st>>>(P, S, Q, depth);
-        else
-            k_extend<false><<<grid_for(cfg, 8), kBlock, 0, st>>>(P, S, Q, depth);
-        k_shade<<<grid_for(cfg, 8), kBlock, 0, st>>>(P, S, Q, depth);
+        {
+            ScopedStage sc(cfg, kStageExtend);
+            if (stats)
+                k_extend<true><<<grid_for(cfg, 8), kBlock, 0, st>>>(P, S, Q, depth);
+            else
+                k_extend<false><<<grid_for(cfg, 8), kBlock, 0, st>>>(P, S, Q, depth);
+        }
+        {
+            ScopedStage sc(cfg, kStageShade);
+            k_shade<<<grid_for(cfg, 8), kBlock, 0, st>>>(P, S, Q, depth);
+        }
         if (P.debug == 1u)
             break; // debug normals: only the first hit is shaded (OptixRender.cu:151-152)
+        ScopedStage sc(cfg, kStageShadow);
         if (stats)
             k_shadow<true><<<grid_for(cfg, 8), kBlock, 0, st>>>(S, Q, depth);
         else
@@ -188,6 +274,7 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
 
 void launch_accumulate(const LaunchCfg& cfg, const FrameParams& P, const Queues& Q, float4* S, float4* direct, uint32_t mode, uint32_t subframe)
 {
+    ScopedStage sc(cfg, kStageAccumulate);
     k_accumulate<<<grid_for(cfg, 4), 256, 0, cfg.stream>>>(P, Q, S, direct, mode, subframe);
     SB_CUDA_CHECK(cudaGetLastError());
 }
@@ -195,12 +282,14 @@ void launch_accumulate(const LaunchCfg& cfg, const FrameParams& P, const Queues&
 void launch_resolve(const LaunchCfg& cfg, const float4* S, void* out, uint32_t npix, uint32_t n, const float exposure[3], uint32_t tonemapper,
                     float gamma, uint32_t format)
 {
+    ScopedStage sc(cfg, kStageResolve);
     k_resolve<<<grid_for(cfg, 4), 256, 0, cfg.stream>>>(S, out, npix, n, make_float3(exposure[0], exposure[1], exposure[2]), tonemapper, gamma, format);
     SB_CUDA_CHECK(cudaGetLastError());
 }
 
 void launch_copy_image(const LaunchCfg& cfg, const float4* src, void* out, uint32_t npix, uint32_t format)
 {
+    ScopedStage sc(cfg, kStageResolve);
     k_copy_image<<<grid_for(cfg, 4), 256, 0, cfg.stream>>>(src, out, npix, format);
     SB_CUDA_CHECK(cudaGetLastError());
 }

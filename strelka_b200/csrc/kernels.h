@@ -1,14 +1,47 @@
 // Launchers of the kernels in kernels.cu (host-callable).
 #pragma once
 #include "wavefront.cuh"
+#include <vector>
 
 namespace sb
 {
+
+enum Stage
+{
+    kStageRaygen = 0,
+    kStageExtend,
+    kStageShade,
+    kStageShadow,
+    kStageAccumulate,
+    kStageResolve,
+    kNumStages
+};
+
+// Optional per-launch CUDA-event bracketing (SB_CFG_STAGE_TIMERS): events are recorded on the launch
+// stream and only read back (after a synchronize) by collect().
+struct StageTimer
+{
+    struct Pending
+    {
+        int stage;
+        cudaEvent_t a, b;
+    };
+    std::vector<cudaEvent_t> pool;
+    std::vector<Pending> pending;
+    double ms[kNumStages] = { 0, 0, 0, 0, 0, 0 };
+    uint64_t launches[kNumStages] = { 0, 0, 0, 0, 0, 0 };
+    cudaEvent_t get();
+    void collect();
+    void reset();
+    void release();
+};
 
 struct LaunchCfg
 {
     cudaStream_t stream;
     int numSms;
+    StageTimer* timer; // may be null
+    uint64_t* launchCount; // may be null
 };
 
 void upload_sobol_table(cudaStream_t stream);

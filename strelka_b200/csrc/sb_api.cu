@@ -34,8 +34,12 @@ struct sb_ctx
 {
     int device = 0;
     int numSms = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr; // the stream work is issued on (own or caller-provided)
+    cudaStream_t ownStream = nullptr;
     cudaEvent_t evStart = nullptr, evStop = nullptr;
+    StageTimer timer;
+    bool stageTimers = false;
+    uint64_t launchCount = 0;
     std::string error;
     bool trackStats = false;
     uint32_t maxBatchPaths = 4u << 20;
@@ -232,6 +236,8 @@ LaunchCfg launch_cfg(const sb_ctx* c)
     LaunchCfg l;
     l.stream = c->stream;
     l.numSms = c->numSms;
+    l.timer = c->stageTimers ? const_cast<StageTimer*>(&c->timer) : nullptr;
+    l.launchCount = const_cast<uint64_t*>(&c->launchCount);
     return l;
 }
 
@@ -409,7 +415,9 @@ sb_result sb_create(const sb_device_cfg* cfg, sb_ctx** out)
         cudaDeviceProp prop;
         SB_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
         c->numSms = prop.multiProcessorCount;
-        SB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        SB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
+        c->stream = c->ownStream;
+        c->stageTimers = cfg && (cfg->flags & SB_CFG_STAGE_TIMERS);
         SB_CUDA_CHECK(cudaEventCreate(&c->evStart));
         SB_CUDA_CHECK(cudaEventCreate(&c->evStop));
         c->trackStats = cfg && (cfg->flags & SB_CFG_TRAVERSAL_STATS);
@@ -437,13 +445,24 @@ void sb_destroy(sb_ctx* c)
         return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    c->timer.release();
     free_scene(c);
     free_frame(c);
     dev_free(c->stats);
     cudaEventDestroy(c->evStart);
     cudaEventDestroy(c->evStop);
-    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->ownStream);
     delete c;
+}
+
+sb_result sb_set_stream(sb_ctx* c, void* cudaStream)
+{
+    if (!c)
+        return SB_FAIL;
+    SB_API_BEGIN(c)
+    SB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->stream = cudaStream ? static_cast<cudaStream_t>(cudaStream) : c->ownStream;
+    SB_API_END
 }
 
 const char* sb_last_error(const sb_ctx* c)
@@ -769,6 +788,16 @@ sb_result sb_get_counters(sb_ctx* c, sb_counters* out)
     out->tris_tested = h.tris;
     out->segs_tested = h.segs;
     out->stack_overflows = h.overflow;
+    out->nodes_visited_shadow = h.nodesSh;
+    out->tris_tested_shadow = h.trisSh;
+    out->segs_tested_shadow = h.segsSh;
+    out->kernel_launches = c->launchCount;
+    c->timer.collect();
+    for (int i = 0; i < kNumStages; ++i)
+    {
+        out->stage_ms[i] = c->timer.ms[i];
+        out->stage_launches[i] = c->timer.launches[i];
+    }
     out->num_triangles = c->scene.numTris;
     out->num_segments = c->scene.numSegs;
     out->bvh_nodes_tri = c->scene.numTriNodes;
@@ -789,6 +818,9 @@ sb_result sb_reset_counters(sb_ctx* c)
         return SB_FAIL;
     SB_API_BEGIN(c)
     SB_CUDA_CHECK(cudaMemsetAsync(c->stats, 0, sizeof(StatCounters), c->stream));
+    SB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->timer.reset();
+    c->launchCount = 0;
     SB_API_END
 }
 

@@ -40,7 +40,7 @@ struct FrameParams
 
 struct StatCounters // device-resident, persistent across launches
 {
-    unsigned long long paths, radianceRays, shadowRays, nodes, tris, segs, overflow;
+    unsigned long long paths, radianceRays, shadowRays, nodes, tris, segs, overflow, nodesSh, trisSh, segsSh;
 };
 
 struct Queues

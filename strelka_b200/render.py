@@ -119,11 +119,11 @@ class Buffer:
 class Render:
     """oka::Render (render.h:19-56) implemented by the B200 backend (RenderType::eCompute)."""
 
-    def __init__(self, device: int = 0, traversal_stats: bool = False, max_batch_paths: int = 0):
+    def __init__(self, device: int = 0, traversal_stats: bool = False, max_batch_paths: int = 0, stage_timers: bool = False):
         self._lib = _abi.load_library()
         self._ctx = None
         self._device = device
-        self._flags = _abi.SB_CFG_TRAVERSAL_STATS if traversal_stats else 0
+        self._flags = (_abi.SB_CFG_TRAVERSAL_STATS if traversal_stats else 0) | (_abi.SB_CFG_STAGE_TIMERS if stage_timers else 0)
         self._max_batch = max_batch_paths
         self.mSharedCtx: SharedContext | None = None  # noqa: N815
         self.mScene: Scene | None = None  # noqa: N815
@@ -196,6 +196,10 @@ class Render:
         self.mSharedCtx.mSubframeIndex = self._lib.sb_subframe_index(self._ctx)
         self.mSharedCtx.mFrameNumber += iterations
 
+    def set_stream(self, cuda_stream: int | None) -> None:
+        """Render on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)."""
+        _check(self._lib, self._ctx, self._lib.sb_set_stream(self._ctx, C.c_void_p(cuda_stream or 0)), "sb_set_stream")
+
     def synchronize(self) -> None:
         _check(self._lib, self._ctx, self._lib.sb_synchronize(self._ctx), "sb_synchronize")
 
@@ -216,6 +220,30 @@ class Render:
         n = C.c_uint64()
         p = self._lib.sb_accum_device_ptr(self._ctx, C.byref(n))
         return p, n.value
+
+    def upload_scene_view(self, view) -> None:
+        """sb_set_scene on an already flattened (e.g. pinned) sb_scene_view of self.mScene."""
+        _check(self._lib, self._ctx, self._lib.sb_set_scene(self._ctx, C.byref(view)), "sb_set_scene")
+        self._scene_uploaded = True
+
+    def accum_tensor_nosync(self):
+        return self.accum_tensor(sync=False)
+
+    def accum_tensor(self, sync: bool = True):
+        """Zero-copy torch view (float32, [h*w*4]) of the device accumulation buffer S = sum_k T(L_k): the
+        quantity a multi-GPU harness all-reduces (torch.distributed / NCCL).  With sync=True the context's
+        stream is synchronised first; pass sync=False when the context renders on torch's current stream
+        (set_stream), where stream order already guarantees visibility."""
+        import torch
+
+        if sync:
+            self.synchronize()
+        ptr, n = self.accum_device_ptr()
+
+        class _Wrap:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+        return torch.as_tensor(_Wrap(), device=f"cuda:{self._device}")
 
     def resolve(self, output: Buffer, total_samples: int) -> None:
         _check(self._lib, self._ctx, self._lib.sb_resolve(self._ctx, output._h, total_samples), "sb_resolve")

@@ -319,9 +319,26 @@ class Scene:
         a["instances"] = inst
         return a
 
-    def view(self) -> _abi.sb_scene_view:
-        """Borrowed sb_scene_view over freshly flattened arrays (kept alive on self)."""
+    def host_bytes(self) -> int:
+        """Bytes of all scene arrays a backend uploads (the H2D volume of sb_set_scene)."""
+        return int(sum(v.nbytes for v in self.arrays().values()))
+
+    def view(self, pinned: bool = False) -> _abi.sb_scene_view:
+        """Borrowed sb_scene_view over freshly flattened arrays (kept alive on self).  pinned=True stages
+        the arrays in page-locked host memory (torch) so that the upload is a true async DMA."""
         a = self.arrays()
+        if pinned:
+            import torch
+
+            keep = []
+            for k, arr in list(a.items()):
+                if arr.nbytes == 0:
+                    continue
+                t = torch.empty(arr.nbytes, dtype=torch.uint8).pin_memory()
+                t.numpy()[:] = np.frombuffer(arr.tobytes(), dtype=np.uint8)
+                keep.append(t)
+                a[k] = np.frombuffer(t.numpy().data, dtype=arr.dtype).reshape(arr.shape)
+            self._keep_pinned = keep
         self._keep = a
         v = _abi.sb_scene_view()
         p = _abi.np_ptr
