@@ -173,8 +173,9 @@ def run_b200(args) -> None:
         return r
 
     render = make_render()
-    stream = torch.cuda.current_stream()
-    render.set_stream(stream.cuda_stream)  # torch events / NCCL are stream-ordered with the render
+    stream = torch.cuda.Stream()  # a dedicated stream shared by the render, the timing events and NCCL
+    torch.cuda.set_stream(stream)
+    render.set_stream(stream.cuda_stream)
     buf = render.createBuffer(BufferDesc(W, H, BufferFormat.FLOAT4))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 

@@ -220,7 +220,9 @@ enum
 sb_result sb_create(const sb_device_cfg* cfg, sb_ctx** out_ctx);
 /* Run on a caller-owned CUDA stream (cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream) instead
  * of the context's own one, so that the caller's events and collectives are stream-ordered with the
- * render (reference: one created stream, OptixRender.cpp:168-170).  NULL restores the private stream. */
+ * render (reference: one created stream, OptixRender.cpp:168-170).  NULL is CUDA's legacy default
+ * stream; SB_STREAM_PRIVATE restores the context's private non-blocking stream. */
+#define SB_STREAM_PRIVATE ((void*)(intptr_t)-1)
 sb_result sb_set_stream(sb_ctx* ctx, void* cuda_stream);
 /* OptiXRender::~OptiXRender (OptixRender.cpp:159-161; the reference leaks, we free). */
 void sb_destroy(sb_ctx* ctx);

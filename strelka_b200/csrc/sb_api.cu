@@ -461,7 +461,7 @@ sb_result sb_set_stream(sb_ctx* c, void* cudaStream)
         return SB_FAIL;
     SB_API_BEGIN(c)
     SB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    c->stream = cudaStream ? static_cast<cudaStream_t>(cudaStream) : c->ownStream;
+    c->stream = (cudaStream == SB_STREAM_PRIVATE) ? c->ownStream : static_cast<cudaStream_t>(cudaStream);
     SB_API_END
 }
 

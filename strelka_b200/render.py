@@ -197,8 +197,10 @@ class Render:
         self.mSharedCtx.mFrameNumber += iterations
 
     def set_stream(self, cuda_stream: int | None) -> None:
-        """Render on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)."""
-        _check(self._lib, self._ctx, self._lib.sb_set_stream(self._ctx, C.c_void_p(cuda_stream or 0)), "sb_set_stream")
+        """Render on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream; 0 is CUDA's
+        legacy default stream).  None restores the context's private stream (SB_STREAM_PRIVATE)."""
+        h = C.c_void_p(-1) if cuda_stream is None else C.c_void_p(cuda_stream)
+        _check(self._lib, self._ctx, self._lib.sb_set_stream(self._ctx, h), "sb_set_stream")
 
     def synchronize(self) -> None:
         _check(self._lib, self._ctx, self._lib.sb_synchronize(self._ctx), "sb_synchronize")
