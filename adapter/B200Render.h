@@ -1,0 +1,59 @@
+// B200Render -- the third Strelka render backend (next to OptiXRender and MetalRender): a thin C++ host
+// class implementing oka::Render (include/render/render.h:19-56) on top of the C ABI of
+// include/sb/sb_api.h.  Inside a Strelka tree it is compiled against the real headers and registered
+// under RenderType::eCompute; in this repository it is compiled against
+// adapter/shim (minimal stand-ins) so that it can be built and tested without glm/OpenUSD/MDL.
+#pragma once
+#include <render/render.h>
+#include <sb/sb_api.h>
+
+#include <string>
+#include <vector>
+
+namespace oka
+{
+
+class B200Buffer : public Buffer
+{
+public:
+    B200Buffer(sb_ctx* ctx, const BufferDesc& desc);
+    ~B200Buffer() override;
+    void resize(uint32_t width, uint32_t height) override;
+    void* map() override; // blocking D2H; like OptixBuffer::map it returns nullptr -- use getHostPointer()
+    void unmap() override;
+    void* getHostPointer() override;
+    size_t getHostDataSize() override;
+    void* getNativePtr();
+    sb_buffer* handle() { return mHandle; }
+
+private:
+    sb_buffer* mHandle = nullptr;
+};
+
+class B200Render : public Render
+{
+public:
+    B200Render() = default;
+    ~B200Render() override;
+    void init() override;
+    void render(Buffer* output) override;
+    Buffer* createBuffer(const BufferDesc& desc) override;
+    void* getNativeDevicePtr() override;
+
+    // pre-resolve an oka material description into one of the backend's closed-form models by
+    // parameter name (precedent: MetalRender.cpp:84-89)
+    static sb_material resolveMaterial(const Scene::MaterialDescription& desc);
+    const std::string& lastError() const { return mError; }
+    sb_ctx* context() { return mCtx; }
+
+private:
+    void uploadScene();
+    sb_settings readSettings();
+    void fail(const char* what);
+
+    sb_ctx* mCtx = nullptr;
+    bool mSceneUploaded = false;
+    std::string mError;
+};
+
+} // namespace oka
