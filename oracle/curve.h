@@ -254,4 +254,102 @@ inline CurveHit intersect_round_cubic(const f4 q[4], const f3& o, const f3& dir,
     return CurveHit{ true, float(best_s / dl), float(best_u) };
 }
 
+// ------------------------------------------------------------------------------------------
+// The single-precision solver that DEFINES the curve hit for image parity: the same iteration the CUDA
+// kernel runs (strelka_b200/csrc/curve.cuh), restated here.  Hair is a few tens of micrometres thick
+// and metres away, so a float solver and the double bracketing solver above legitimately differ by a
+// fraction of a percent of the radius -- enough to decorrelate individual paths.  The double solver is
+// therefore kept as the VALIDATOR of this one (tests/test_curves.py: |dt| <= 0.05 r, same hit/miss
+// away from silhouettes) while renders use this definition on both sides.
+// ------------------------------------------------------------------------------------------
+// ray vs round cubic B-spline segment; q = world-space control points (w = radius).
+inline bool intersect_round_cubic_f32(const f4 q[4], const f3& o, const f3& dIn, float tmin, float tmax, float& tOut, float& uOut)
+{
+    const float dl2 = dot_fma(dIn, dIn);
+    if (!(dl2 > 0.0f))
+        return false;
+    const float invLen = 1.0f / std::sqrt(dl2);
+    const f3 d = dIn * invLen;
+    // polynomial coefficients relative to the ray origin
+    const float s6 = 1.0f / 6.0f;
+    const f4 a4 = (q[3] - q[0] + (q[1] - q[2]) * 3.0f) * s6;
+    const f4 b4 = (q[0] + q[2]) * 0.5f - q[1];
+    const f4 c4 = (q[2] - q[0]) * 0.5f;
+    f4 e4 = (q[0] + q[2] + q[1] * 4.0f) * s6;
+    e4.x -= o.x;
+    e4.y -= o.y;
+    e4.z -= o.z;
+    // ray-centric frame (b1, b2, d): the curve becomes X(u), Y(u) across the ray, Z(u) along it, R(u).
+    // Working with the perpendicular components avoids the |P|^2 - z^2 cancellation that would swamp
+    // hair-thin radii a few metres from the ray origin.
+    f3 b1, b2;
+    {
+        const float sg = std::copysign(1.0f, d.z);
+        const float k = -1.0f / (sg + d.z);
+        const float m = d.x * d.y * k;
+        b1 = f3{ 1.0f + sg * d.x * d.x * k, sg * m, -sg * d.x };
+        b2 = f3{ m, sg + d.y * d.y * k, -d.y };
+    }
+    const f3 a3 = mk3(a4), b3 = mk3(b4), c3 = mk3(c4), e3 = mk3(e4);
+    const float ax = dot_fma(a3, b1), bx = dot_fma(b3, b1), cx = dot_fma(c3, b1), ex = dot_fma(e3, b1);
+    const float ay = dot_fma(a3, b2), by = dot_fma(b3, b2), cy = dot_fma(c3, b2), ey = dot_fma(e3, b2);
+    const float az = dot_fma(a3, d), bz = dot_fma(b3, d), cz = dot_fma(c3, d), ez = dot_fma(e3, d);
+    const float ar = a4.w, br = b4.w, cr = c4.w, er = e4.w;
+    // initial guess: closest approach of the ray axis to the chord P(0)P(1), in the 2-D cross-section
+    const float Bx = ax + bx + cx, By = ay + by + cy;
+    const float bb = std::fmaf(Bx, Bx, By * By);
+    float u = (bb > 1e-30f) ? clampf(-std::fmaf(ex, Bx, ey * By) / bb, 0.0f, 1.0f) : 0.5f;
+    for (int it = 0; it < 10; ++it)
+    {
+        const float X = std::fmaf(std::fmaf(std::fmaf(ax, u, bx), u, cx), u, ex), X1 = std::fmaf(std::fmaf(3.0f * ax, u, 2.0f * bx), u, cx), X2 = std::fmaf(6.0f * ax, u, 2.0f * bx);
+        const float Y = std::fmaf(std::fmaf(std::fmaf(ay, u, by), u, cy), u, ey), Y1 = std::fmaf(std::fmaf(3.0f * ay, u, 2.0f * by), u, cy), Y2 = std::fmaf(6.0f * ay, u, 2.0f * by);
+        const float R = std::fmaf(std::fmaf(std::fmaf(ar, u, br), u, cr), u, er), R1 = std::fmaf(std::fmaf(3.0f * ar, u, 2.0f * br), u, cr), R2 = std::fmaf(6.0f * ar, u, 2.0f * br);
+        const float z1 = std::fmaf(std::fmaf(3.0f * az, u, 2.0f * bz), u, cz);
+        const float g0 = std::fmaf(X, X, std::fmaf(Y, Y, -(R * R)));
+        const float g1 = 2.0f * std::fmaf(X, X1, std::fmaf(Y, Y1, -(R * R1)));
+        const float g2 = 2.0f * (std::fmaf(X1, X1, std::fmaf(X, X2, std::fmaf(Y1, Y1, Y * Y2))) - std::fmaf(R1, R1, R * R2));
+        float delta;
+        if (!(g2 > 0.0f))
+        {
+            delta = (g1 > 0.0f) ? -0.25f : 0.25f;
+        }
+        else
+        {
+            const float m = std::fmaf(g1, g1, -2.0f * g2 * g0); // model of g has real roots <=> the ray pierces the tube here
+            if (m >= 0.0f)
+            {
+                const float zz = 2.0f * z1 * z1;
+                const float disc = zz * m / (g2 + zz);
+                delta = (-g1 - std::copysign(std::sqrt(disc), z1)) / g2;
+            }
+            else
+            {
+                delta = -g1 / g2;
+            }
+        }
+        const float un = clampf(u + delta, 0.0f, 1.0f);
+        const float step = std::fabs(un - u);
+        u = un;
+        if (step < 2e-6f)
+            break;
+    }
+    if (!(u > 0.0f && u < 1.0f))
+        return false; // pinned at an end: that would be an end cap / belongs to the neighbouring segment
+    const float X = std::fmaf(std::fmaf(std::fmaf(ax, u, bx), u, cx), u, ex);
+    const float Y = std::fmaf(std::fmaf(std::fmaf(ay, u, by), u, cy), u, ey);
+    const float Z = std::fmaf(std::fmaf(std::fmaf(az, u, bz), u, cz), u, ez);
+    const float R = std::fmaf(std::fmaf(std::fmaf(ar, u, br), u, cr), u, er);
+    const float g = std::fmaf(X, X, std::fmaf(Y, Y, -(R * R)));
+    if (!(g < 0.0f))
+        return false;
+    const float sHit = Z - std::sqrt(-g);
+    const float t = sHit * invLen;
+    if (!(t > tmin && t < tmax))
+        return false;
+    tOut = t;
+    uOut = u;
+    return true;
+}
+
+
 } // namespace orc

@@ -335,7 +335,8 @@ Hit trace_closest(const orc_scene& S, const f3& o, const f3& d, float tmin, floa
         Hit hc = h;
         S.segBvh.traverse(o, d, tmin, tmaxC, [&](uint32_t id, float& tmax) {
             const WorldSeg& W = S.segs[id];
-            const CurveHit ch = intersect_round_cubic(W.q, o, d, tmin, tmax);
+            CurveHit ch{ false, 0.0f, 0.0f };
+            ch.hit = intersect_round_cubic_f32(W.q, o, d, tmin, tmax, ch.t, ch.u);
             if (ch.hit && (ch.t < tmax || (curveWon && ch.t == tmax && id < bestSeg)))
             {
                 hc = Hit{ ch.t, ch.u, 0.0f, W.prim, W.inst, 2 };
@@ -371,8 +372,8 @@ bool trace_any(const orc_scene& S, const f3& o, const f3& d, float tmin, float t
     if (occluded || !(rayMask & kMaskCurve))
         return occluded;
     S.segBvh.traverse(o, d, tmin, tmaxIn, [&](uint32_t id, float& tmax) {
-        const CurveHit ch = intersect_round_cubic(S.segs[id].q, o, d, tmin, tmax);
-        if (ch.hit)
+        float tc, uc;
+        if (intersect_round_cubic_f32(S.segs[id].q, o, d, tmin, tmax, tc, uc))
         {
             occluded = true;
             return true;
@@ -988,7 +989,20 @@ void orc_curve_eval(const float* q, float u, const float* ps, float* out)
     std::memcpy(out, r, sizeof(r));
 }
 
-// ray: o[3], d[3], tmin, tmax; out: hit, t, u
+// the float solver used by renders; out: hit, t, u
+void orc_curve_intersect_f32(const float* q, const float* ray, float* out)
+{
+    f4 cp[4];
+    for (int k = 0; k < 4; ++k)
+        cp[k] = f4{ q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3] };
+    float t = 0.0f, u = 0.0f;
+    const bool hit = intersect_round_cubic_f32(cp, f3{ ray[0], ray[1], ray[2] }, f3{ ray[3], ray[4], ray[5] }, ray[6], ray[7], t, u);
+    out[0] = hit ? 1.0f : 0.0f;
+    out[1] = t;
+    out[2] = u;
+}
+
+// the double-precision bracketing solver (validator); ray: o[3], d[3], tmin, tmax; out: hit, t, u
 void orc_curve_intersect(const float* q, const float* ray, float* out)
 {
     f4 cp[4];

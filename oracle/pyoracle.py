@@ -48,6 +48,7 @@ def lib() -> C.CDLL:
         _lib.orc_tonemap.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         _lib.orc_curve_eval.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
         _lib.orc_curve_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_curve_intersect_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.orc_offset_ray.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.orc_bsdf.argtypes = [C.c_void_p] * 8
         _lib.orc_camera_matrices.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
@@ -178,11 +179,12 @@ def curve_eval(q, u, ps) -> np.ndarray:
     return out
 
 
-def curve_intersect(q, o, d, tmin=0.0, tmax=1e16):
+def curve_intersect(q, o, d, tmin=0.0, tmax=1e16, f32=False):
+    """Ray vs round cubic B-spline segment: the double bracketing solver, or (f32=True) the float solver."""
     q = np.ascontiguousarray(q, dtype=np.float32)
     ray = np.array([*o, *d, tmin, tmax], dtype=np.float32)
     out = np.zeros(3, dtype=np.float32)
-    lib().orc_curve_intersect(_p(q), _p(ray), _p(out))
+    (lib().orc_curve_intersect_f32 if f32 else lib().orc_curve_intersect)(_p(q), _p(ray), _p(out))
     return bool(out[0]), float(out[1]), float(out[2])
 
 

@@ -95,6 +95,22 @@ def rotate_matrix(axis, degrees) -> np.ndarray:
     return m
 
 
+def light_look_at(pos, target, up=(0.0, 1.0, 0.0)) -> np.ndarray:
+    """Transform for a light at `pos` whose emission axis (local -Z, scene.cpp:353-408) points at `target`."""
+    pos = np.asarray(pos, dtype=np.float64)
+    d = np.asarray(target, dtype=np.float64) - pos
+    d /= np.linalg.norm(d)
+    z = -d
+    x = np.cross(np.asarray(up, dtype=np.float64), z)
+    if np.linalg.norm(x) < 1e-6:
+        x = np.cross(np.array([1.0, 0.0, 0.0]), z)
+    x /= np.linalg.norm(x)
+    y = np.cross(z, x)
+    m = np.eye(4)
+    m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = x, y, z, pos
+    return m
+
+
 @dataclass
 class UniformLightDesc:
     """Scene::UniformLightDesc, scene.h:158-179 (only the useXform path the Hydra delegate uses)."""
