@@ -54,9 +54,10 @@ inline void onb(const f3& n, f3& t, f3& b)
 inline f3 cosine_hemisphere(float u1, float u2, const f3& n)
 {
     const float r = std::sqrt(u1);
-    const float phi = 2.0f * kPi * u2;
-    const float x = r * std::cos(phi);
-    const float y = r * std::sin(phi);
+    float sphi, cphi;
+    sincos2pi(u2, sphi, cphi);
+    const float x = r * cphi;
+    const float y = r * sphi;
     const float z = std::sqrt(std::fmax(0.0f, 1.0f - u1));
     f3 t, b;
     onb(n, t, b);
@@ -104,9 +105,10 @@ inline f3 ggx_sample_vndf(float a, const f3& n, const f3& v, float u1, float u2)
     const f3 T1 = lensq > 0.0f ? f3{ -vh.y, vh.x, 0.0f } * (1.0f / std::sqrt(lensq)) : f3{ 1.0f, 0.0f, 0.0f };
     const f3 T2 = cross(vh, T1);
     const float r = std::sqrt(u1);
-    const float phi = 2.0f * kPi * u2;
-    const float t1 = r * std::cos(phi);
-    float t2 = r * std::sin(phi);
+    float sphi, cphi;
+    sincos2pi(u2, sphi, cphi);
+    const float t1 = r * cphi;
+    float t2 = r * sphi;
     const float s = 0.5f * (1.0f + vh.z);
     t2 = (1.0f - s) * std::sqrt(std::fmax(0.0f, 1.0f - t1 * t1)) + s * t2;
     const f3 nh = t1 * T1 + t2 * T2 + std::sqrt(std::fmax(0.0f, 1.0f - t1 * t1 - t2 * t2)) * vh;

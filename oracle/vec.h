@@ -201,6 +201,28 @@ inline float i2f(int32_t u)
     return f;
 }
 
+// sin(2*pi*u), cos(2*pi*u), u in [0,1): the fixed-polynomial routine shared BY SPECIFICATION with the
+// CUDA kernels (strelka_b200/csrc/hd.cuh) so that BSDF sampling yields identical bits on both sides.
+inline void sincos2pi(float u, float& s, float& c)
+{
+    const float q = std::floor(std::fmaf(u, 4.0f, 0.5f));
+    const float r = std::fmaf(q, -0.25f, u);
+    const float x = r * 6.283185307179586f;
+    const float x2 = x * x;
+    float sp = std::fmaf(x2, 2.7557319e-6f, -1.9841270e-4f);
+    sp = std::fmaf(sp, x2, 8.3333333e-3f);
+    sp = std::fmaf(sp, x2, -1.6666667e-1f);
+    sp = std::fmaf(sp * x2, x, x);
+    float cp = std::fmaf(x2, -2.7557319e-7f, 2.4801587e-5f);
+    cp = std::fmaf(cp, x2, -1.3888889e-3f);
+    cp = std::fmaf(cp, x2, 4.1666667e-2f);
+    cp = std::fmaf(cp, x2, -0.5f);
+    cp = std::fmaf(cp, x2, 1.0f);
+    const int k = int(q) & 3;
+    s = (k == 0) ? sp : (k == 1) ? cp : (k == 2) ? -sp : -cp;
+    c = (k == 0) ? cp : (k == 1) ? -sp : (k == 2) ? -cp : sp;
+}
+
 // Affine 3x4 transform (rows), applied with the fixed fma chain
 //   r = fma(m0,x, fma(m1,y, fma(m2,z, m3)))
 struct Affine

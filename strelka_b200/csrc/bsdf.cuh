@@ -48,9 +48,10 @@ SB_HD void onb(const float3& n, float3& t, float3& b)
 SB_HD float3 cosine_hemisphere(float u1, float u2, const float3& n)
 {
     const float r = sqrtf(u1);
-    const float phi = 2.0f * kPi * u2;
-    const float x = r * cosf(phi);
-    const float y = r * sinf(phi);
+    float sphi, cphi;
+    sincos2pi(u2, sphi, cphi);
+    const float x = r * cphi;
+    const float y = r * sphi;
     const float z = sqrtf(fmaxf(0.0f, 1.0f - u1));
     float3 t, b;
     onb(n, t, b);
@@ -98,9 +99,10 @@ SB_HD float3 ggx_sample_vndf(float a, const float3& n, const float3& v, float u1
     const float3 T1 = lensq > 0.0f ? mk3(-vh.y, vh.x, 0.0f) * (1.0f / sqrtf(lensq)) : mk3(1.0f, 0.0f, 0.0f);
     const float3 T2 = cross(vh, T1);
     const float r = sqrtf(u1);
-    const float phi = 2.0f * kPi * u2;
-    const float t1 = r * cosf(phi);
-    float t2 = r * sinf(phi);
+    float sphi, cphi;
+    sincos2pi(u2, sphi, cphi);
+    const float t1 = r * cphi;
+    float t2 = r * sphi;
     const float s = 0.5f * (1.0f + vh.z);
     t2 = (1.0f - s) * sqrtf(fmaxf(0.0f, 1.0f - t1 * t1)) + s * t2;
     const float3 nh = t1 * T1 + t2 * T2 + sqrtf(fmaxf(0.0f, 1.0f - t1 * t1 - t2 * t2)) * vh;

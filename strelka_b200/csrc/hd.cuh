@@ -244,6 +244,30 @@ SB_HD float maxcomp(const float3& v)
     return fmaxf(v.x, fmaxf(v.y, v.z));
 }
 
+// sin(2*pi*u), cos(2*pi*u) for u in [0,1): quadrant reduction in turns + fixed fmaf polynomials.
+// libm's sinf/cosf differ by an ulp or two between CUDA and glibc, and on hair-thin geometry that is
+// enough to flip hits; the BSDF samplers (whose definition is ours anyway) therefore use this routine,
+// which evaluates to the same bits on the device and in the CPU oracle (max error ~1 ulp).
+SB_HD void sincos2pi(float u, float& s, float& c)
+{
+    const float q = floorf(fmaf(u, 4.0f, 0.5f)); // nearest quarter turn: 0..4
+    const float r = fmaf(q, -0.25f, u); // |r| <= 1/8 turn, exact
+    const float x = r * 6.283185307179586f; // |x| <= pi/4
+    const float x2 = x * x;
+    float sp = fmaf(x2, 2.7557319e-6f, -1.9841270e-4f); // x^9/9!, x^7/7!
+    sp = fmaf(sp, x2, 8.3333333e-3f);
+    sp = fmaf(sp, x2, -1.6666667e-1f);
+    sp = fmaf(sp * x2, x, x);
+    float cp = fmaf(x2, -2.7557319e-7f, 2.4801587e-5f); // x^10/10!, x^8/8!
+    cp = fmaf(cp, x2, -1.3888889e-3f);
+    cp = fmaf(cp, x2, 4.1666667e-2f);
+    cp = fmaf(cp, x2, -0.5f);
+    cp = fmaf(cp, x2, 1.0f);
+    const int k = int(q) & 3;
+    s = (k == 0) ? sp : (k == 1) ? cp : (k == 2) ? -sp : -cp;
+    c = (k == 0) ? cp : (k == 1) ? -sp : (k == 2) ? -cp : sp;
+}
+
 // ---- affine transforms (row-major 3x4) ---------------------------------------------------------------
 struct Affine
 {
