@@ -17,11 +17,17 @@ uint32_t h_sobol[5][32];
 namespace sb
 {
 
-void upload_sobol_table(cudaStream_t stream)
+uint32_t* upload_sobol_table(cudaStream_t stream)
 {
     sobol_generate(h_sobol);
     SB_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_sobol, h_sobol, sizeof(h_sobol), 0, cudaMemcpyHostToDevice, stream));
+    static uint32_t tab[kSobolTabWords];
+    sobol_build_tables(h_sobol, tab);
+    uint32_t* d = nullptr;
+    SB_CUDA_CHECK(cudaMalloc(&d, sizeof(tab)));
+    SB_CUDA_CHECK(cudaMemcpyAsync(d, tab, sizeof(tab), cudaMemcpyHostToDevice, stream));
     SB_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return d;
 }
 
 constexpr int kBlock = 128;
@@ -59,37 +65,194 @@ __device__ __forceinline__ void flush_stats(StatCounters* g, const TravStats& st
     }
 }
 
+// ---- persistent traversal kernels with dynamic ray fetch ----------------------------------------------
+// Incoherent secondary rays finish after very different numbers of steps; with one ray per thread the first
+// ncu capture on the 2 M-triangle scene showed 7 of 32 lanes active on average.  Here every warp keeps its
+// lanes busy: a lane whose ray is done pulls the next ray from the queue (one warp-aggregated atomic), and
+// refills happen whenever fewer than kRefill lanes still hold a ray (Aila & Laine 2009 style, using
+// trav_step so that node visits and primitive tests of different lanes interleave).
+constexpr int kRefill = 24;
+
+struct WarpFetch
+{
+    bool exhausted;
+};
+
+// hands out queue slots to the lanes with need == true; returns the slot or 0xffffffff
+__device__ __forceinline__ uint32_t fetch_slots(uint32_t* head, uint32_t n, bool need, bool& exhausted)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned mask = __ballot_sync(0xffffffffu, need);
+    if (mask == 0u || exhausted)
+        return 0xffffffffu;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (int(lane) == leader)
+        base = atomicAdd(head, uint32_t(__popc(mask)));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (base + uint32_t(__popc(mask)) >= n)
+        exhausted = true; // warp-uniform: the queue has been handed out completely
+    const uint32_t idx = base + uint32_t(__popc(mask & ((1u << lane) - 1u)));
+    return (need && idx < n) ? idx : 0xffffffffu;
+}
+
 template <bool STATS>
 __global__ void __launch_bounds__(kBlock) k_extend(FrameParams P, SceneDev S, Queues Q, uint32_t depth)
 {
     const uint32_t n = Q.counts[depth];
+    uint32_t* head = &Q.counts[kHeadExtendBase + depth];
+    const int qi = int(depth & 1u);
+    const bool haveTris = S.numTriNodes != 0u, haveSegs = S.numSegNodes != 0u;
     TravStats st = { 0, 0, 0, 0 };
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        extend_one<STATS>(P, S, Q, depth, i, &st);
+    bool active = false, exhausted = false;
+    uint32_t slot = 0;
+    int phase = 0;
+    Ray ray;
+    RayPrep rp;
+    HitRec hit;
+    Traversal T;
+    for (;;)
+    {
+        const uint32_t got = fetch_slots(head, n, !active, exhausted);
+        if (got != 0xffffffffu)
+        {
+            slot = got;
+            const float4 ro = Q.rayO[qi][slot], rd = Q.rayD[qi][slot];
+            ray.o = mk3(ro);
+            ray.d = mk3(rd);
+            ray.tmin = P.materialTmin;
+            ray.tmax = 1e16f;
+            rp = prepare_ray(ray.d);
+            hit.t = hit.u = hit.v = 0.0f;
+            hit.prim = hit.inst = hit.kind = 0u;
+            hit.gid = 0xffffffffu;
+            trav_init(T);
+            phase = haveTris ? 0 : (haveSegs ? 1 : 2);
+            active = true;
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0u)
+            break;
+        for (;;)
+        {
+            if (active)
+            {
+                bool more = false, anyHit = false;
+                if (phase == 0)
+                    more = trav_step<1, false, STATS>(T, S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
+                else if (phase == 1)
+                    more = trav_step<2, false, STATS>(T, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
+                if (!more)
+                {
+                    if (phase == 0 && haveSegs)
+                    {
+                        phase = 1;
+                        trav_init(T);
+                    }
+                    else
+                    {
+                        if (hit.kind == 2u)
+                            hit.inst = S.segInfo[hit.prim].inst;
+                        Q.hitA[slot] = mk4(hit.t, hit.u, hit.v, u2f(hit.prim));
+                        Q.hitB[slot] = hit.inst | (hit.kind << 30);
+                        active = false;
+                    }
+                }
+            }
+            const int busy = __popc(__ballot_sync(0xffffffffu, active));
+            if (busy == 0 || (!exhausted && busy < kRefill))
+                break;
+        }
+    }
     if (STATS)
         flush_stats(Q.stats, st, false);
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(&Q.stats->radianceRays, (unsigned long long)n);
 }
 
-__global__ void __launch_bounds__(kBlock) k_shade(FrameParams P, SceneDev S, Queues Q, uint32_t depth)
-{
-    const uint32_t n = Q.counts[depth];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        shade_one(P, S, Q, depth, i);
-}
-
 template <bool STATS>
 __global__ void __launch_bounds__(kBlock) k_shadow(SceneDev S, Queues Q, uint32_t depth)
 {
     const uint32_t n = Q.counts[kCountShadowBase + depth];
+    uint32_t* head = &Q.counts[kHeadShadowBase + depth];
+    const bool haveTris = S.numTriNodes != 0u, haveSegs = S.numSegNodes != 0u;
     TravStats st = { 0, 0, 0, 0 };
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        shadow_one<STATS>(S, Q, i, &st);
+    bool active = false, exhausted = false;
+    uint32_t slot = 0;
+    int phase = 0;
+    Ray ray;
+    RayPrep rp;
+    HitRec hit;
+    Traversal T;
+    for (;;)
+    {
+        const uint32_t got = fetch_slots(head, n, !active, exhausted);
+        if (got != 0xffffffffu)
+        {
+            slot = got;
+            const float4 so = Q.shO[slot], sd = Q.shD[slot];
+            ray.o = mk3(so);
+            ray.tmin = so.w;
+            ray.d = mk3(sd);
+            ray.tmax = sd.w;
+            rp = prepare_ray(ray.d);
+            hit.kind = 0u;
+            hit.gid = 0xffffffffu;
+            trav_init(T);
+            phase = haveTris ? 0 : (haveSegs ? 1 : 2);
+            active = true;
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0u)
+            break;
+        for (;;)
+        {
+            if (active)
+            {
+                bool more = false, occluded = false;
+                if (phase == 0)
+                    more = trav_step<1, true, STATS>(T, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st);
+                else if (phase == 1)
+                    more = trav_step<2, true, STATS>(T, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st);
+                if (!more)
+                {
+                    if (!occluded && phase == 0 && haveSegs)
+                    {
+                        phase = 1;
+                        trav_init(T);
+                    }
+                    else
+                    {
+                        if (!occluded)
+                        {
+                            const float4 sc = Q.shC[slot];
+                            const uint32_t pathId = f2u(sc.w);
+                            const float4 L = Q.Lacc[pathId];
+                            Q.Lacc[pathId] = mk4(L.x + sc.x, L.y + sc.y, L.z + sc.z, 0.0f);
+                        }
+                        active = false;
+                    }
+                }
+            }
+            const int busy = __popc(__ballot_sync(0xffffffffu, active));
+            if (busy == 0 || (!exhausted && busy < kRefill))
+                break;
+        }
+    }
     if (STATS)
         flush_stats(Q.stats, st, true);
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(&Q.stats->shadowRays, (unsigned long long)n);
+}
+
+__global__ void __launch_bounds__(kBlock) k_shade(FrameParams P, SceneDev S, Queues Q, uint32_t depth)
+{
+    // 12 KB of byte-sliced Sobol tables per CTA (L2-resident source; 6 x 128-bit loads per thread)
+    __shared__ __align__(16) uint32_t s_tab[kSobolTabWords];
+    for (uint32_t i = threadIdx.x; i < kSobolTabWords / 4; i += blockDim.x)
+        reinterpret_cast<uint4*>(s_tab)[i] = __ldg(reinterpret_cast<const uint4*>(Q.sobolTab) + i);
+    __syncthreads();
+    const uint32_t n = Q.counts[depth];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        shade_one(P, S, Q, depth, i, s_tab);
 }
 
 __global__ void __launch_bounds__(256) k_accumulate(FrameParams P, Queues Q, float4* S, float4* direct, uint32_t mode, uint32_t subframe)

@@ -44,7 +44,7 @@ struct LaunchCfg
     uint64_t* launchCount; // may be null
 };
 
-void upload_sobol_table(cudaStream_t stream);
+uint32_t* upload_sobol_table(cudaStream_t stream); // also returns the device copy of the byte-sliced tables
 // one wavefront batch: raygen, then per bounce extend -> shade -> shadow
 void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const SceneDev& S, const Queues& Q, bool stats);
 void launch_accumulate(const LaunchCfg& cfg, const FrameParams& P, const Queues& Q, float4* S, float4* direct, uint32_t mode, uint32_t subframe);

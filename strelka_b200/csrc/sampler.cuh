@@ -112,10 +112,48 @@ SB_HD uint32_t owen_scramble(uint32_t v, uint32_t seed) // nested_uniform_scramb
 {
     return brev32(lk_permute(brev32(v), seed));
 }
+// Dimension 1 (polynomial x+1): the generator matrix is Pascal's triangle mod 2, column k = (1+S)^k e_31, so by
+// Lucas' theorem output bit (31-j) is the parity of the index bits k that are supersets of j -- a
+// superset-XOR (zeta) transform over the 5-bit positions: five masked shift-XORs and one bit reversal.
+SB_HD uint32_t sobol_dim1(uint32_t g)
+{
+    g ^= (g >> 1) & 0x55555555u;
+    g ^= (g >> 2) & 0x33333333u;
+    g ^= (g >> 4) & 0x0f0f0f0fu;
+    g ^= (g >> 8) & 0x00ff00ffu;
+    g ^= (g >> 16) & 0x0000ffffu;
+    return brev32(g);
+}
+
+// Byte-sliced tables for dimensions 2..4: tab[(d-2)*1024 + k*256 + b] = XOR of the direction numbers of the
+// bits set in byte value b at byte position k.  4 lookups + 3 XORs replace the 32-step bit loop; the shade
+// kernel keeps the 12 KB table in shared memory (random 4-byte gathers: ~3 bank-conflict wavefronts each).
+constexpr uint32_t kSobolTabWords = 3u * 4u * 256u;
+inline void sobol_build_tables(const uint32_t v[5][32], uint32_t* tab)
+{
+    for (uint32_t d = 2; d < 5; ++d)
+        for (uint32_t k = 0; k < 4; ++k)
+            for (uint32_t b = 0; b < 256; ++b)
+            {
+                uint32_t x = 0;
+                for (uint32_t bit = 0; bit < 8; ++bit)
+                    if ((b >> bit) & 1u)
+                        x ^= v[d][8 * k + bit];
+                tab[(d - 2) * 1024 + k * 256 + b] = x;
+            }
+}
+SB_HD uint32_t sobol_tab(const uint32_t* tab, uint32_t index, uint32_t dim) // dim in 2..4
+{
+    const uint32_t* t = tab + (dim - 2u) * 1024u;
+    return t[index & 0xffu] ^ t[256u + ((index >> 8) & 0xffu)] ^ t[512u + ((index >> 16) & 0xffu)] ^ t[768u + (index >> 24)];
+}
+
 SB_HD uint32_t sobol_u32(uint32_t index, uint32_t dim) // sobol_uint, :166-175
 {
     if (dim == 0)
         return brev32(index); // dimension 0 is the identity matrix: van der Corput == bit reversal
+    if (dim == 1)
+        return sobol_dim1(index);
     uint32_t x = 0;
 #pragma unroll
     for (int bit = 0; bit < 32; ++bit)
@@ -145,14 +183,17 @@ struct Sample5
 {
     float v[5];
 };
-SB_HD Sample5 sampler_sample5(uint32_t sampleIdx, uint32_t depth, uint32_t seed = 52u)
+// tab: byte-sliced tables (sobol_build_tables) or nullptr for the plain bit loop -- same bits either way
+SB_HD Sample5 sampler_sample5(uint32_t sampleIdx, uint32_t depth, const uint32_t* tab = nullptr, uint32_t seed = 52u)
 {
     Sample5 r;
     const uint32_t s = fmix32(seed + depth);
     const uint32_t index = owen_scramble(sampleIdx, s);
+    r.v[0] = u32_to_unit(owen_scramble(brev32(index), seed_combine(s, 0u)));
+    r.v[1] = u32_to_unit(owen_scramble(sobol_dim1(index), seed_combine(s, 1u)));
 #pragma unroll
-    for (uint32_t d = 0; d < 5; ++d)
-        r.v[d] = u32_to_unit(owen_scramble(sobol_u32(index, d), seed_combine(s, d)));
+    for (uint32_t d = 2; d < 5; ++d)
+        r.v[d] = u32_to_unit(owen_scramble(tab ? sobol_tab(tab, index, d) : sobol_u32(index, d), seed_combine(s, d)));
     return r;
 }
 

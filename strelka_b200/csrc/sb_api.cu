@@ -66,6 +66,7 @@ struct sb_ctx
     float4* direct = nullptr; // non-accumulated launch result
     Queues Q = {};
     StatCounters* stats = nullptr;
+    uint32_t* sobolTab = nullptr;
 
     double buildMs = 0.0, renderMs = 0.0;
 };
@@ -176,6 +177,7 @@ void ensure_frame(sb_ctx* c, uint32_t w, uint32_t h)
     c->Q.shC = dev_alloc<float4>(np);
     c->Q.counts = dev_alloc<uint32_t>(kNumCounts);
     c->Q.stats = c->stats;
+    c->Q.sobolTab = c->sobolTab;
     SB_CUDA_CHECK(cudaMemsetAsync(c->S, 0, sizeof(float4) * size_t(w) * h, c->stream));
     SB_CUDA_CHECK(cudaMemsetAsync(c->direct, 0, sizeof(float4) * size_t(w) * h, c->stream));
     c->subframe = 0; // new dimensions reset rendering (OptixRender.cpp:834)
@@ -425,7 +427,7 @@ sb_result sb_create(const sb_device_cfg* cfg, sb_ctx** out)
             c->maxBatchPaths = cfg->max_batch_paths;
         c->stats = dev_alloc<StatCounters>(1);
         SB_CUDA_CHECK(cudaMemsetAsync(c->stats, 0, sizeof(StatCounters), c->stream));
-        upload_sobol_table(c->stream);
+        c->sobolTab = upload_sobol_table(c->stream);
         sb_settings_default(&c->settings);
         c->haveSettings = true;
         *out = c;
@@ -449,6 +451,7 @@ void sb_destroy(sb_ctx* c)
     free_scene(c);
     free_frame(c);
     dev_free(c->stats);
+    dev_free(c->sobolTab);
     cudaEventDestroy(c->evStart);
     cudaEventDestroy(c->evStop);
     cudaStreamDestroy(c->ownStream);

@@ -67,6 +67,17 @@ SB_HD uint32_t byte_of(uint32_t w, int j)
 {
     return (w >> (8 * j)) & 0xffu;
 }
+// float(byte j of w), exactly.  On the device the conversion is kept off the XU pipe (I2F runs at 16
+// lanes/clk/SM and was 59 % busy in the first ncu capture): PRMT builds 2^23 + b as a float bit pattern,
+// one FADD removes the 2^23 -- both exact, so the result equals float(b) bit for bit.
+SB_HD float byte_to_float(uint32_t w, int j)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + uint32_t(j))) - 8388608.0f;
+#else
+    return float(byte_of(w, j));
+#endif
+}
 
 // Ray/child-box tests of one wide node -> 32-bit hit mask: bits 24..31 inner children in traversal
 // priority (highest first), bits 0..23 leaf primitives relative to primBase.
@@ -97,12 +108,12 @@ SB_HD uint32_t wide_node_hits(const uint4& n0, const uint4& n1, const uint4& n2,
 #pragma unroll
         for (int j = 0; j < 4; ++j)
         {
-            const float t0x = fmaf(float(byte_of(nearx, j)), ax, bx);
-            const float t0y = fmaf(float(byte_of(neary, j)), ay, by);
-            const float t0z = fmaf(float(byte_of(nearz, j)), az, bz);
-            const float t1x = fmaf(float(byte_of(farx, j)), ax, bx);
-            const float t1y = fmaf(float(byte_of(fary, j)), ay, by);
-            const float t1z = fmaf(float(byte_of(farz, j)), az, bz);
+            const float t0x = fmaf(byte_to_float(nearx, j), ax, bx);
+            const float t0y = fmaf(byte_to_float(neary, j), ay, by);
+            const float t0z = fmaf(byte_to_float(nearz, j), az, bz);
+            const float t1x = fmaf(byte_to_float(farx, j), ax, bx);
+            const float t1y = fmaf(byte_to_float(fary, j), ay, by);
+            const float t1z = fmaf(byte_to_float(farz, j), az, bz);
             const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
             // 1 + 2*gamma(3): conservative far plane (Ize 2013); also used by the CPU oracle's BVH
             const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tmax)) * 1.0000004f;
@@ -157,68 +168,55 @@ SB_HD RayPrep prepare_ray(const float3& d)
     return r;
 }
 
-// KIND 1: triangles (prims = TriRec), KIND 2: curve segments (prims = SegRec).
-// ANY: stop at the first accepted hit (shadow rays).  hit/ray.tmax are updated in place.
-template <int KIND, bool ANY, bool STATS>
-SB_HD bool traverse_bvh(const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask, Ray& ray, const RayPrep& rp,
-                        HitRec& hit, TravStats* st)
+// Traversal state of one ray in one BVH.  A "node group" is (child base index, hit bits | inner mask), a
+// "primitive group" is (primitive base index, hit bits); the stack holds postponed node groups only.
+struct Traversal
 {
+    uint2 ngroup, tgroup;
+    int sp;
     uint2 stack[kStackSize];
-    int sp = 0;
-    uint2 ngroup;
-    ngroup.x = 0u;
-    ngroup.y = 0x80000000u; // the root: one inner "child" at base 0
-    bool found = false;
-    for (;;)
+};
+SB_HD void trav_init(Traversal& T)
+{
+    T.ngroup.x = 0u;
+    T.ngroup.y = 0x80000000u; // the root: one inner "child" at base 0
+    T.tgroup.x = 0u;
+    T.tgroup.y = 0u;
+    T.sp = 0;
+}
+
+// ONE unit of traversal work -- either one primitive test or one node visit -- so that a warp of
+// incoherent rays interleaves node and leaf work lane by lane instead of serialising whole phases.
+// KIND 1: triangles (prims = TriRec), KIND 2: curve segments (prims = SegRec).  ANY: shadow rays (anyHit is
+// set and the traversal ends at the first accepted hit).  Returns false when the traversal is finished.
+template <int KIND, bool ANY, bool STATS>
+SB_HD bool trav_step(Traversal& T, const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask, Ray& ray,
+                     const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st)
+{
+    if (T.tgroup.y != 0u)
     {
-        uint2 tgroup;
-        tgroup.x = 0u;
-        tgroup.y = 0u;
-        if (ngroup.y > 0x00ffffffu)
+        const uint32_t rel = bfind32(T.tgroup.y);
+        T.tgroup.y &= ~(1u << rel);
+        const uint32_t pi = T.tgroup.x + rel;
+        if (KIND == 1)
         {
-            const uint32_t hits = ngroup.y;
-            const uint32_t bit = bfind32(hits);
-            ngroup.y &= ~(1u << bit);
-            if (ngroup.y > 0x00ffffffu)
-            {
-                if (sp < kStackSize)
-                    stack[sp++] = ngroup;
-                else if (STATS)
-                    st->overflow++;
-            }
-            const uint32_t slot = (bit - 24u) ^ (rp.octinv & 7u);
-            const uint32_t rel = popc32(hits & ~(0xffffffffu << slot) & 0xffu);
-            const WideNode* np = nodes + (ngroup.x + rel);
-            const uint4 n0 = SB_LDG4(&np->n0), n1 = SB_LDG4(&np->n1), n2 = SB_LDG4(&np->n2), n3 = SB_LDG4(&np->n3), n4 = SB_LDG4(&np->n4);
+            const TriRec* tr = reinterpret_cast<const TriRec*>(prims) + pi;
+            const float4 a = SB_LDGF4(&tr->v0), b = SB_LDGF4(&tr->e1), c = SB_LDGF4(&tr->e2);
             if (STATS)
-                st->nodes++;
-            const uint32_t hm = wide_node_hits(n0, n1, n2, n3, n4, ray.o, rp.idir, rp.octinv4, rp.negx, rp.negy, rp.negz, ray.tmin, ray.tmax);
-            ngroup.x = n1.x;
-            ngroup.y = (hm & 0xff000000u) | (n0.w >> 24);
-            tgroup.x = n1.y;
-            tgroup.y = hm & 0x00ffffffu;
-        }
-        while (tgroup.y != 0u)
-        {
-            const uint32_t rel = bfind32(tgroup.y);
-            tgroup.y &= ~(1u << rel);
-            const uint32_t pi = tgroup.x + rel;
-            if (KIND == 1)
+                st->tris++;
+            const uint32_t instMask = f2u(b.w);
+            if ((instMask >> 28) & rayMask)
             {
-                const TriRec* tr = reinterpret_cast<const TriRec*>(prims) + pi;
-                const float4 a = SB_LDGF4(&tr->v0), b = SB_LDGF4(&tr->e1), c = SB_LDGF4(&tr->e2);
-                if (STATS)
-                    st->tris++;
-                const uint32_t instMask = f2u(b.w);
-                if (!((instMask >> 28) & rayMask))
-                    continue;
                 float t, u, v;
                 if (intersect_tri(mk3(a), mk3(b), mk3(c), ray.o, ray.d, ray.tmin, ray.tmax, t, u, v))
                 {
                     if (ANY)
-                        return true;
+                    {
+                        anyHit = true;
+                        return false;
+                    }
                     const uint32_t gid = f2u(c.w);
-                    if (t < ray.tmax || !found || gid < hit.gid)
+                    if (t < ray.tmax || hit.kind != 1u || gid < hit.gid)
                     {
                         hit.t = t;
                         hit.u = u;
@@ -228,44 +226,86 @@ SB_HD bool traverse_bvh(const WideNode* __restrict__ nodes, const void* __restri
                         hit.kind = 1u;
                         hit.gid = gid;
                         ray.tmax = t;
-                        found = true;
                     }
                 }
             }
-            else
+        }
+        else
+        {
+            const SegRec* sr = reinterpret_cast<const SegRec*>(prims) + pi;
+            float4 q[4];
+            q[0] = SB_LDGF4(&sr->q[0]);
+            q[1] = SB_LDGF4(&sr->q[1]);
+            q[2] = SB_LDGF4(&sr->q[2]);
+            q[3] = SB_LDGF4(&sr->q[3]);
+            if (STATS)
+                st->segs++;
+            float t, u;
+            if (intersect_round_cubic(q, ray.o, ray.d, ray.tmin, ray.tmax, t, u))
             {
-                const SegRec* sr = reinterpret_cast<const SegRec*>(prims) + pi;
-                float4 q[4];
-                q[0] = SB_LDGF4(&sr->q[0]);
-                q[1] = SB_LDGF4(&sr->q[1]);
-                q[2] = SB_LDGF4(&sr->q[2]);
-                q[3] = SB_LDGF4(&sr->q[3]);
-                if (STATS)
-                    st->segs++;
-                float t, u;
-                if (intersect_round_cubic(q, ray.o, ray.d, ray.tmin, ray.tmax, t, u))
+                if (ANY)
                 {
-                    if (ANY)
-                        return true;
-                    hit.t = t;
-                    hit.u = u;
-                    hit.v = 0.0f;
-                    hit.prim = pi; // index into the SegInfo table; resolved by the caller
-                    hit.kind = 2u;
-                    hit.gid = pi;
-                    ray.tmax = t;
-                    found = true;
+                    anyHit = true;
+                    return false;
                 }
+                hit.t = t;
+                hit.u = u;
+                hit.v = 0.0f;
+                hit.prim = pi; // index into the SegInfo table; resolved by the caller
+                hit.kind = 2u;
+                hit.gid = pi;
+                ray.tmax = t;
             }
         }
-        if (ngroup.y <= 0x00ffffffu)
-        {
-            if (sp == 0)
-                break;
-            ngroup = stack[--sp];
-        }
+        return true;
     }
-    return found;
+    if (T.ngroup.y <= 0x00ffffffu)
+    {
+        if (T.sp == 0)
+            return false;
+        T.ngroup = T.stack[--T.sp];
+    }
+    const uint32_t hits = T.ngroup.y;
+    const uint32_t bit = bfind32(hits);
+    T.ngroup.y &= ~(1u << bit);
+    if (T.ngroup.y > 0x00ffffffu)
+    {
+        if (T.sp < kStackSize)
+            T.stack[T.sp++] = T.ngroup;
+        else if (STATS)
+            st->overflow++;
+    }
+    const uint32_t slot = (bit - 24u) ^ (rp.octinv & 7u);
+    const uint32_t rel = popc32(hits & ~(0xffffffffu << slot) & 0xffu);
+    const WideNode* np = nodes + (T.ngroup.x + rel);
+    const uint4 n0 = SB_LDG4(&np->n0), n1 = SB_LDG4(&np->n1), n2 = SB_LDG4(&np->n2), n3 = SB_LDG4(&np->n3), n4 = SB_LDG4(&np->n4);
+    if (STATS)
+        st->nodes++;
+    const uint32_t hm = wide_node_hits(n0, n1, n2, n3, n4, ray.o, rp.idir, rp.octinv4, rp.negx, rp.negy, rp.negz, ray.tmin, ray.tmax);
+    T.ngroup.x = n1.x;
+    T.ngroup.y = (hm & 0xff000000u) | (n0.w >> 24);
+    T.tgroup.x = n1.y;
+    T.tgroup.y = hm & 0x00ffffffu;
+    return true;
+}
+
+// Whole traversal of one BVH for one ray (test hooks, host emulation).  Returns true if a hit was found
+// (closest: hit updated and ray.tmax shrunk; any: first accepted hit).
+template <int KIND, bool ANY, bool STATS>
+SB_HD bool traverse_bvh(const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask, Ray& ray, const RayPrep& rp,
+                        HitRec& hit, TravStats* st)
+{
+    Traversal T;
+    trav_init(T);
+    const uint32_t kindBefore = hit.kind;
+    const float tBefore = ray.tmax;
+    bool anyHit = false;
+    while (trav_step<KIND, ANY, STATS>(T, nodes, prims, rayMask, ray, rp, hit, anyHit, st))
+    {
+    }
+    if (ANY)
+        return anyHit;
+    return hit.kind == uint32_t(KIND) && (kindBefore != uint32_t(KIND) || ray.tmax < tBefore);
 }
 
 } // namespace sb

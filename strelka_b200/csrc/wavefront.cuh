@@ -22,7 +22,9 @@ namespace sb
 
 constexpr uint32_t kMaxDepth = 32;
 constexpr uint32_t kCountShadowBase = 32; // counts[0..31] path queues per depth, counts[32..63] shadow queues
-constexpr uint32_t kNumCounts = 64;
+constexpr uint32_t kHeadExtendBase = 64; // counts[64..95] / [96..127]: dynamic-fetch cursors of k_extend / k_shadow
+constexpr uint32_t kHeadShadowBase = 96;
+constexpr uint32_t kNumCounts = 128;
 
 // per-path flag bits (stored in thr.w)
 constexpr uint32_t kFlagInside = 1u, kFlagSpecular = 2u;
@@ -56,6 +58,7 @@ struct Queues
     float4* shC; // contribution.xyz, bits(pathId)
     uint32_t* counts; // kNumCounts
     StatCounters* stats;
+    const uint32_t* sobolTab; // kSobolTabWords, byte-sliced Sobol tables (global memory copy)
 };
 
 // Warp-aggregated slot allocation: one atomicAdd per warp instead of one per surviving lane.
@@ -192,7 +195,7 @@ SB_HD Surface curve_surface(const SceneDev& S, const InstDev& I, uint32_t segInd
 }
 
 // One bounce of one path after its closest-hit query.  `depth` == prd.depth == sampler.depth.
-SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, uint32_t depth, uint32_t slot)
+SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, uint32_t depth, uint32_t slot, const uint32_t* sobolTab)
 {
     const int qi = int(depth & 1u), qo = qi ^ 1;
     const float4 ro = Q.rayO[qi][slot], rd = Q.rayD[qi][slot], th = Q.thr[qi][slot];
@@ -250,7 +253,7 @@ SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, u
     const uint32_t sidx = sampler_index(px, py, P.sampleBase + pk * P.sampleStride, P.sppTotal);
     // the five distinct Sobol values of this bounce (quirk Q2): xi = v[0..3], lightId = v[2],
     // lightPoint = (v[3], v[4]), russian roulette = v[4]
-    const Sample5 rn = sampler_sample5(sidx, depth);
+    const Sample5 rn = sampler_sample5(sidx, depth, sobolTab);
     const float3 k1 = -rayD;
     const BsdfSample bs = bsdf_sample(mat, sf.normal, sf.geomNormal, k1, mk4(rn.v[0], rn.v[1], rn.v[2], rn.v[3]));
     if (bs.event == EV_ABSORB)
