@@ -48,6 +48,7 @@ struct SceneDev
     uint64_t numCurvePoints = 0, numCurveRadii = 0;
     // world-space geometry + BVHs
     TriRec* tris = nullptr;
+    uint4* triShade = nullptr; // per GLOBAL triangle id: absolute vertex indices of its 3 corners + instance
     SegRec* segs = nullptr;
     SegInfo* segInfo = nullptr; // per SegRec (leaf order)
     WideNode* triNodes = nullptr;
@@ -327,17 +328,28 @@ inline void build_scene_bvhs(Exec& ex, SceneDev& S, const uint32_t* instTriFirst
     {
         TriRec* unsorted = ex.alloc<TriRec>(numTris);
         Aabb* boxes = ex.alloc<Aabb>(numTris);
+        // shading-side record: one 16-byte load replaces the mesh -> index-buffer chain of the reference's
+        // fillTriangleGeomData (closest_hit.cu:369-377) so that the three vertex fetches can start at once
+        uint4* shade = ex.alloc<uint4>(numTris);
         ex.pfor(numTris, SB_LAMBDA(size_t g) {
             const uint32_t inst = upper_owner(instTriFirst, numInst + 1, uint32_t(g));
             const InstDev& I = Sv.instances[inst];
             const uint32_t t = uint32_t(g) - instTriFirst[inst];
             const sb_mesh m = Sv.meshes[I.geom];
             float3 p[3];
+            uint32_t vi[3];
             for (int k = 0; k < 3; ++k)
             {
-                const sb_vertex& vx = Sv.vertices[m.vb_offset + Sv.indices[m.index + 3 * t + k]];
+                vi[k] = m.vb_offset + Sv.indices[m.index + 3 * t + k];
+                const sb_vertex& vx = Sv.vertices[vi[k]];
                 p[k] = xform_point(I.o2w, mk3(vx.pos[0], vx.pos[1], vx.pos[2]));
             }
+            uint4 sh;
+            sh.x = vi[0];
+            sh.y = vi[1];
+            sh.z = vi[2];
+            sh.w = inst;
+            shade[g] = sh;
             TriRec r;
             r.v0 = mk4(p[0], u2f(t));
             r.e1 = mk4(p[1] - p[0], u2f(inst | (I.mask << 28)));
@@ -357,6 +369,7 @@ inline void build_scene_bvhs(Exec& ex, SceneDev& S, const uint32_t* instTriFirst
         ex.free(boxes);
         ex.free(bvh.primOrder);
         S.tris = ordered;
+        S.triShade = shade;
         S.triNodes = bvh.nodes;
         S.numTriNodes = bvh.numNodes;
     }

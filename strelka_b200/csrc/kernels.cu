@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kBlock) k_extend(FrameParams P, SceneDev S, Qu
                     {
                         if (hit.kind == 2u)
                             hit.inst = S.segInfo[hit.prim].inst;
-                        Q.hitA[slot] = mk4(hit.t, hit.u, hit.v, u2f(hit.prim));
+                        Q.hitA[slot] = mk4(hit.t, hit.u, hit.v, u2f(hit.kind == 1u ? hit.gid : hit.prim));
                         Q.hitB[slot] = hit.inst | (hit.kind << 30);
                         active = false;
                     }

@@ -108,6 +108,7 @@ void free_scene(sb_ctx* c)
     dev_free(s.materials);
     dev_free(s.instances);
     dev_free(s.tris);
+    dev_free(s.triShade);
     dev_free(s.segs);
     dev_free(s.segInfo);
     dev_free(s.triNodes);

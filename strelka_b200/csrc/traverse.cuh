@@ -185,80 +185,14 @@ SB_HD void trav_init(Traversal& T)
     T.sp = 0;
 }
 
-// ONE unit of traversal work -- either one primitive test or one node visit -- so that a warp of
-// incoherent rays interleaves node and leaf work lane by lane instead of serialising whole phases.
-// KIND 1: triangles (prims = TriRec), KIND 2: curve segments (prims = SegRec).  ANY: shadow rays (anyHit is
-// set and the traversal ends at the first accepted hit).  Returns false when the traversal is finished.
-template <int KIND, bool ANY, bool STATS>
-SB_HD bool trav_step(Traversal& T, const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask, Ray& ray,
-                     const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st)
+// Traversal is driven in two half-steps so that a warp of incoherent rays interleaves node visits and
+// primitive tests lane by lane, while coherent rays stay in lock-step:
+//   trav_node : if the lane has no primitives pending, visit the next node (returns false when nothing is left)
+//   trav_prim : if the lane has primitives pending, test exactly one
+// KIND 1: triangles (prims = TriRec), KIND 2: curve segments (prims = SegRec).  ANY: shadow rays.
+template <bool STATS>
+SB_HD bool trav_node(Traversal& T, const WideNode* __restrict__ nodes, const Ray& ray, const RayPrep& rp, TravStats* st)
 {
-    if (T.tgroup.y != 0u)
-    {
-        const uint32_t rel = bfind32(T.tgroup.y);
-        T.tgroup.y &= ~(1u << rel);
-        const uint32_t pi = T.tgroup.x + rel;
-        if (KIND == 1)
-        {
-            const TriRec* tr = reinterpret_cast<const TriRec*>(prims) + pi;
-            const float4 a = SB_LDGF4(&tr->v0), b = SB_LDGF4(&tr->e1), c = SB_LDGF4(&tr->e2);
-            if (STATS)
-                st->tris++;
-            const uint32_t instMask = f2u(b.w);
-            if ((instMask >> 28) & rayMask)
-            {
-                float t, u, v;
-                if (intersect_tri(mk3(a), mk3(b), mk3(c), ray.o, ray.d, ray.tmin, ray.tmax, t, u, v))
-                {
-                    if (ANY)
-                    {
-                        anyHit = true;
-                        return false;
-                    }
-                    const uint32_t gid = f2u(c.w);
-                    if (t < ray.tmax || hit.kind != 1u || gid < hit.gid)
-                    {
-                        hit.t = t;
-                        hit.u = u;
-                        hit.v = v;
-                        hit.prim = f2u(a.w);
-                        hit.inst = instMask & 0x0fffffffu;
-                        hit.kind = 1u;
-                        hit.gid = gid;
-                        ray.tmax = t;
-                    }
-                }
-            }
-        }
-        else
-        {
-            const SegRec* sr = reinterpret_cast<const SegRec*>(prims) + pi;
-            float4 q[4];
-            q[0] = SB_LDGF4(&sr->q[0]);
-            q[1] = SB_LDGF4(&sr->q[1]);
-            q[2] = SB_LDGF4(&sr->q[2]);
-            q[3] = SB_LDGF4(&sr->q[3]);
-            if (STATS)
-                st->segs++;
-            float t, u;
-            if (intersect_round_cubic(q, ray.o, ray.d, ray.tmin, ray.tmax, t, u))
-            {
-                if (ANY)
-                {
-                    anyHit = true;
-                    return false;
-                }
-                hit.t = t;
-                hit.u = u;
-                hit.v = 0.0f;
-                hit.prim = pi; // index into the SegInfo table; resolved by the caller
-                hit.kind = 2u;
-                hit.gid = pi;
-                ray.tmax = t;
-            }
-        }
-        return true;
-    }
     if (T.ngroup.y <= 0x00ffffffu)
     {
         if (T.sp == 0)
@@ -286,6 +220,91 @@ SB_HD bool trav_step(Traversal& T, const WideNode* __restrict__ nodes, const voi
     T.ngroup.y = (hm & 0xff000000u) | (n0.w >> 24);
     T.tgroup.x = n1.y;
     T.tgroup.y = hm & 0x00ffffffu;
+    return true;
+}
+
+// tests one pending primitive; returns true if an any-hit query is satisfied (ANY only)
+template <int KIND, bool ANY, bool STATS>
+SB_HD bool trav_prim(Traversal& T, const void* __restrict__ prims, uint32_t rayMask, Ray& ray, HitRec& hit, TravStats* st)
+{
+    const uint32_t rel = bfind32(T.tgroup.y);
+    T.tgroup.y &= ~(1u << rel);
+    const uint32_t pi = T.tgroup.x + rel;
+    if (KIND == 1)
+    {
+        const TriRec* tr = reinterpret_cast<const TriRec*>(prims) + pi;
+        const float4 a = SB_LDGF4(&tr->v0), b = SB_LDGF4(&tr->e1), c = SB_LDGF4(&tr->e2);
+        if (STATS)
+            st->tris++;
+        const uint32_t instMask = f2u(b.w);
+        if ((instMask >> 28) & rayMask)
+        {
+            float t, u, v;
+            if (intersect_tri(mk3(a), mk3(b), mk3(c), ray.o, ray.d, ray.tmin, ray.tmax, t, u, v))
+            {
+                if (ANY)
+                    return true;
+                const uint32_t gid = f2u(c.w);
+                if (t < ray.tmax || hit.kind != 1u || gid < hit.gid)
+                {
+                    hit.t = t;
+                    hit.u = u;
+                    hit.v = v;
+                    hit.prim = f2u(a.w);
+                    hit.inst = instMask & 0x0fffffffu;
+                    hit.kind = 1u;
+                    hit.gid = gid;
+                    ray.tmax = t;
+                }
+            }
+        }
+    }
+    else
+    {
+        const SegRec* sr = reinterpret_cast<const SegRec*>(prims) + pi;
+        float4 q[4];
+        q[0] = SB_LDGF4(&sr->q[0]);
+        q[1] = SB_LDGF4(&sr->q[1]);
+        q[2] = SB_LDGF4(&sr->q[2]);
+        q[3] = SB_LDGF4(&sr->q[3]);
+        if (STATS)
+            st->segs++;
+        float t, u;
+        if (intersect_round_cubic(q, ray.o, ray.d, ray.tmin, ray.tmax, t, u))
+        {
+            if (ANY)
+                return true;
+            hit.t = t;
+            hit.u = u;
+            hit.v = 0.0f;
+            hit.prim = pi; // index into the SegInfo table; resolved by the caller
+            hit.kind = 2u;
+            hit.gid = pi;
+            ray.tmax = t;
+        }
+    }
+    return false;
+}
+
+// one full step of one lane: node half-step if idle, then one primitive if any is pending.
+// Returns false when the traversal is finished; anyHit is set when an ANY query found an occluder.
+template <int KIND, bool ANY, bool STATS>
+SB_HD bool trav_step(Traversal& T, const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask, Ray& ray,
+                     const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st)
+{
+    if (T.tgroup.y == 0u)
+    {
+        if (!trav_node<STATS>(T, nodes, ray, rp, st))
+            return false;
+    }
+    if (T.tgroup.y != 0u)
+    {
+        if (trav_prim<KIND, ANY, STATS>(T, prims, rayMask, ray, hit, st))
+        {
+            anyHit = true;
+            return false;
+        }
+    }
     return true;
 }
 

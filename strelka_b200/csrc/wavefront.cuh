@@ -50,7 +50,7 @@ struct Queues
     float4* rayO[2]; // origin.xyz, bits(pathId)
     float4* rayD[2]; // dir.xyz, lastBsdfPdf
     float4* thr[2]; // throughput.xyz, bits(flags)
-    float4* hitA; // t, u, v, bits(prim)
+    float4* hitA; // t, u, v, bits(global triangle id | curve SegInfo index)
     uint32_t* hitB; // instance | kind << 30
     float4* Lacc; // per pathId: radiance accumulated along the path (w unused)
     float4* shO; // origin.xyz, tmin
@@ -154,11 +154,9 @@ struct Surface
 };
 
 // fillTriangleGeomData, closest_hit.cu:365-421 (quirks Q11, Q12)
-SB_HD Surface tri_surface(const SceneDev& S, const InstDev& I, uint32_t prim, float bu, float bv, bool inside)
+SB_HD Surface tri_surface(const SceneDev& S, const InstDev& I, const uint4& corners, float bu, float bv, bool inside)
 {
-    const sb_mesh m = S.meshes[I.geom];
-    const uint32_t i0 = S.indices[m.index + prim * 3 + 0], i1 = S.indices[m.index + prim * 3 + 1], i2 = S.indices[m.index + prim * 3 + 2];
-    const sb_vertex v0 = S.vertices[m.vb_offset + i0], v1 = S.vertices[m.vb_offset + i1], v2 = S.vertices[m.vb_offset + i2];
+    const sb_vertex v0 = S.vertices[corners.x], v1 = S.vertices[corners.y], v2 = S.vertices[corners.z];
     const float3 p0 = mk3(v0.pos[0], v0.pos[1], v0.pos[2]), p1 = mk3(v1.pos[0], v1.pos[1], v1.pos[2]), p2 = mk3(v2.pos[0], v2.pos[1], v2.pos[2]);
     Surface s;
     s.position = xform_point(I.o2w, interp3(p0, p1, p2, bu, bv));
@@ -209,7 +207,12 @@ SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, u
     const uint32_t kind = hb >> 30;
     if (kind == 0u)
         return; // __miss__ms: radiance += throughput * bg_color(0); path ends
+    // independent loads issued together: instance record, corner indices (triangles), path radiance
     const InstDev I = S.instances[hb & 0x0fffffffu];
+    uint4 corners;
+    corners.x = corners.y = corners.z = corners.w = 0u;
+    if (kind == 1u)
+        corners = S.triShade[f2u(ha.w)];
     float3 Lpath = mk3(Q.Lacc[pathId]);
 
     if (I.type == SB_INSTANCE_LIGHT)
@@ -241,7 +244,7 @@ SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, u
 
     // ---- __closesthit__radiance, closest_hit.cu:456-606 --------------------------------------------
     const bool isInside = (flags & kFlagInside) != 0u;
-    const Surface sf = (kind == 1u) ? tri_surface(S, I, f2u(ha.w), ha.y, ha.z, isInside) : curve_surface(S, I, f2u(ha.w), ha.y, ha.x, rayO, rayD, isInside);
+    const Surface sf = (kind == 1u) ? tri_surface(S, I, corners, ha.y, ha.z, isInside) : curve_surface(S, I, f2u(ha.w), ha.y, ha.x, rayO, rayD, isInside);
     if (P.debug == 1u)
     {
         Q.Lacc[pathId] = mk4((sf.normal + mk3(1.0f)) * 0.5f, 0.0f); // closest_hit.cu:504-508
@@ -373,7 +376,7 @@ SB_HD void extend_one(const FrameParams& P, const SceneDev& S, const Queues& Q, 
         if (traverse_bvh<2, false, STATS>(S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, st))
             hit.inst = S.segInfo[hit.prim].inst;
     }
-    Q.hitA[slot] = mk4(hit.t, hit.u, hit.v, u2f(hit.prim));
+    Q.hitA[slot] = mk4(hit.t, hit.u, hit.v, u2f(hit.kind == 1u ? hit.gid : hit.prim)); // triangles: global id; curves: SegInfo index
     Q.hitB[slot] = hit.inst | (hit.kind << 30);
 }
 

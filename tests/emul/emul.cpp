@@ -100,6 +100,7 @@ void emul_scene_destroy(emul_scene* e)
     for (void* p : e->owned)
         std::free(p);
     std::free(e->S.tris);
+    std::free(e->S.triShade);
     std::free(e->S.segs);
     std::free(e->S.segInfo);
     std::free(e->S.triNodes);
