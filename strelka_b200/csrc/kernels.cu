@@ -72,6 +72,7 @@ __device__ __forceinline__ void flush_stats(StatCounters* g, const TravStats& st
 // refills happen whenever fewer than kRefill lanes still hold a ray (Aila & Laine 2009 style, using
 // trav_step so that node visits and primitive tests of different lanes interleave).
 constexpr int kRefill = 24;
+constexpr int kPrimBatch = 8; // primitive tests run once this many lanes have one pending (or a lane has nothing else to do)
 
 struct WarpFetch
 {
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(kBlock) k_extend(FrameParams P, SceneDev S, Qu
     const int qi = int(depth & 1u);
     const bool haveTris = S.numTriNodes != 0u, haveSegs = S.numSegNodes != 0u;
     TravStats st = { 0, 0, 0, 0 };
-    bool active = false, exhausted = false;
+    bool active = false, exhausted = false, forced = false;
     uint32_t slot = 0;
     int phase = 0;
     Ray ray;
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(kBlock) k_extend(FrameParams P, SceneDev S, Qu
             hit.prim = hit.inst = hit.kind = 0u;
             hit.gid = 0xffffffffu;
             trav_init(T);
+            forced = false;
             phase = haveTris ? 0 : (haveSegs ? 1 : 2);
             active = true;
         }
@@ -134,28 +136,58 @@ __global__ void __launch_bounds__(kBlock) k_extend(FrameParams P, SceneDev S, Qu
             break;
         for (;;)
         {
-            if (active)
+            // ---- node half-step for the lanes without pending primitives ----
+            bool finished = false;
+            if (active && T.tgroup.y == 0u)
             {
-                bool more = false, anyHit = false;
-                if (phase == 0)
-                    more = trav_step<1, false, STATS>(T, S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
-                else if (phase == 1)
-                    more = trav_step<2, false, STATS>(T, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
+                const bool hadGroup = T.ngroup.y > 0x00ffffffu;
+                const bool more = (phase == 0) ? trav_node<STATS>(T, S.triNodes, ray, rp, &st) : (phase == 1 ? trav_node<STATS>(T, S.segNodes, ray, rp, &st) : false);
                 if (!more)
+                    finished = true;
+                else if (!hadGroup && T.ngroup.y == 0u && T.tgroup.y != 0u)
+                    forced = true; // popped a postponed primitive group: it must be processed now
+            }
+            // ---- primitive half-step, batched across the warp (primitive postponing, Ylitie et al. 2017) ----
+            const bool wantPrim = active && !finished && T.tgroup.y != 0u;
+            const unsigned primMask = __ballot_sync(0xffffffffu, wantPrim);
+            if (primMask)
+            {
+                const unsigned forceMask = __ballot_sync(0xffffffffu, wantPrim && forced);
+                if (__popc(primMask) >= kPrimBatch || forceMask)
                 {
-                    if (phase == 0 && haveSegs)
+                    if (wantPrim)
                     {
-                        phase = 1;
-                        trav_init(T);
+                        if (phase == 0)
+                            trav_prim<1, false, STATS>(T, S.tris, kRayMaskPrimary, ray, hit, &st);
+                        else
+                            trav_prim<2, false, STATS>(T, S.segs, kRayMaskPrimary, ray, hit, &st);
+                        if (T.tgroup.y == 0u)
+                            forced = false;
                     }
+                }
+                else if (wantPrim)
+                {
+                    if (T.sp < kStackSize)
+                        trav_postpone_prims(T);
                     else
-                    {
-                        if (hit.kind == 2u)
-                            hit.inst = S.segInfo[hit.prim].inst;
-                        Q.hitA[slot] = mk4(hit.t, hit.u, hit.v, u2f(hit.kind == 1u ? hit.gid : hit.prim));
-                        Q.hitB[slot] = hit.inst | (hit.kind << 30);
-                        active = false;
-                    }
+                        forced = true; // no room to park it: process it on the next pass
+                }
+            }
+            if (finished)
+            {
+                if (phase == 0 && haveSegs)
+                {
+                    phase = 1;
+                    trav_init(T);
+                    forced = false;
+                }
+                else
+                {
+                    if (hit.kind == 2u)
+                        hit.inst = S.segInfo[hit.prim].inst;
+                    Q.hitA[slot] = mk4(hit.t, hit.u, hit.v, u2f(hit.kind == 1u ? hit.gid : hit.prim));
+                    Q.hitB[slot] = hit.inst | (hit.kind << 30);
+                    active = false;
                 }
             }
             const int busy = __popc(__ballot_sync(0xffffffffu, active));
@@ -176,7 +208,7 @@ __global__ void __launch_bounds__(kBlock) k_shadow(SceneDev S, Queues Q, uint32_
     uint32_t* head = &Q.counts[kHeadShadowBase + depth];
     const bool haveTris = S.numTriNodes != 0u, haveSegs = S.numSegNodes != 0u;
     TravStats st = { 0, 0, 0, 0 };
-    bool active = false, exhausted = false;
+    bool active = false, exhausted = false, forced = false;
     uint32_t slot = 0;
     int phase = 0;
     Ray ray;
@@ -198,6 +230,7 @@ __global__ void __launch_bounds__(kBlock) k_shadow(SceneDev S, Queues Q, uint32_
             hit.kind = 0u;
             hit.gid = 0xffffffffu;
             trav_init(T);
+            forced = false;
             phase = haveTris ? 0 : (haveSegs ? 1 : 2);
             active = true;
         }
@@ -205,31 +238,60 @@ __global__ void __launch_bounds__(kBlock) k_shadow(SceneDev S, Queues Q, uint32_
             break;
         for (;;)
         {
-            if (active)
+            bool finished = false, occluded = false;
+            if (active && T.tgroup.y == 0u)
             {
-                bool more = false, occluded = false;
-                if (phase == 0)
-                    more = trav_step<1, true, STATS>(T, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st);
-                else if (phase == 1)
-                    more = trav_step<2, true, STATS>(T, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st);
+                const bool hadGroup = T.ngroup.y > 0x00ffffffu;
+                const bool more = (phase == 0) ? trav_node<STATS>(T, S.triNodes, ray, rp, &st) : (phase == 1 ? trav_node<STATS>(T, S.segNodes, ray, rp, &st) : false);
                 if (!more)
+                    finished = true;
+                else if (!hadGroup && T.ngroup.y == 0u && T.tgroup.y != 0u)
+                    forced = true;
+            }
+            const bool wantPrim = active && !finished && T.tgroup.y != 0u;
+            const unsigned primMask = __ballot_sync(0xffffffffu, wantPrim);
+            if (primMask)
+            {
+                const unsigned forceMask = __ballot_sync(0xffffffffu, wantPrim && forced);
+                if (__popc(primMask) >= kPrimBatch || forceMask)
                 {
-                    if (!occluded && phase == 0 && haveSegs)
+                    if (wantPrim)
                     {
-                        phase = 1;
-                        trav_init(T);
+                        if (phase == 0)
+                            occluded = trav_prim<1, true, STATS>(T, S.tris, kRayMaskShadow, ray, hit, &st);
+                        else
+                            occluded = trav_prim<2, true, STATS>(T, S.segs, kRayMaskShadow, ray, hit, &st);
+                        if (T.tgroup.y == 0u)
+                            forced = false;
                     }
+                }
+                else if (wantPrim)
+                {
+                    if (T.sp < kStackSize)
+                        trav_postpone_prims(T);
                     else
-                    {
-                        if (!occluded)
-                        {
-                            const float4 sc = Q.shC[slot];
-                            const uint32_t pathId = f2u(sc.w);
-                            const float4 L = Q.Lacc[pathId];
-                            Q.Lacc[pathId] = mk4(L.x + sc.x, L.y + sc.y, L.z + sc.z, 0.0f);
-                        }
-                        active = false;
-                    }
+                        forced = true; // no room to park it: process it on the next pass
+                }
+            }
+            if (occluded)
+            {
+                active = false; // any hit ends the query; nothing is added
+            }
+            else if (finished)
+            {
+                if (phase == 0 && haveSegs)
+                {
+                    phase = 1;
+                    trav_init(T);
+                    forced = false;
+                }
+                else
+                {
+                    const float4 sc = Q.shC[slot];
+                    const uint32_t pathId = f2u(sc.w);
+                    const float4 L = Q.Lacc[pathId];
+                    Q.Lacc[pathId] = mk4(L.x + sc.x, L.y + sc.y, L.z + sc.z, 0.0f);
+                    active = false;
                 }
             }
             const int busy = __popc(__ballot_sync(0xffffffffu, active));
