@@ -74,7 +74,7 @@ SB_HD uint32_t byte_of(uint32_t w, int j)
 SB_HD float byte_to_unit_float(uint32_t w, int j)
 {
 #if defined(__CUDA_ARCH__)
-    return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7640u | (uint32_t(j) << 4)));
+    return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (uint32_t(j) << 4)));
 #else
     return u2f(0x3F800000u | (byte_of(w, j) << 8));
 #endif
