@@ -255,27 +255,64 @@ inline CurveHit intersect_round_cubic(const f4 q[4], const f3& o, const f3& dir,
 }
 
 // ------------------------------------------------------------------------------------------
-// The single-precision solver that DEFINES the curve hit for image parity: the same iteration the CUDA
-// kernel runs (strelka_b200/csrc/curve.cuh), restated here.  Hair is a few tens of micrometres thick
-// and metres away, so a float solver and the double bracketing solver above legitimately differ by a
-// fraction of a percent of the radius -- enough to decorrelate individual paths.  The double solver is
-// therefore kept as the VALIDATOR of this one (tests/test_curves.py: |dt| <= 0.05 r, same hit/miss
-// away from silhouettes) while renders use this definition on both sides.
+// The single-precision solver that DEFINES the curve hit for image parity, and the span records it works on:
+// the same definitions the CUDA kernels use (strelka_b200/csrc/curve.cuh), restated here.  Hair is a few tens
+// of micrometres thick and metres away, so a float solver and the double bracketing solver above legitimately
+// differ by a fraction of a percent of the radius -- enough to decorrelate individual paths.  The double solver
+// is therefore kept as the VALIDATOR of this one (tests/test_curves.py: |dt| <= 0.05 r, same hit/miss away
+// from silhouettes) while renders use this definition on both sides.
 // ------------------------------------------------------------------------------------------
-// ray vs round cubic B-spline segment; q = world-space control points (w = radius).
-inline bool intersect_round_cubic_f32(const f4 q[4], const f3& o, const f3& dIn, float tmin, float tmax, float& tOut, float& uOut)
+struct CurveSpan
+{
+    f4 c[4];
+};
+// span k of K of the B-spline segment with control points q (w = radius).  Fixed expression order: the CPU
+// oracle evaluates the same tree so that both sides hold identical records.
+inline CurveSpan curve_span(const f4 q[4], uint32_t k, uint32_t K)
+{
+    const float s6 = 1.0f / 6.0f;
+    const f4 a = (q[3] - q[0] + (q[1] - q[2]) * 3.0f) * s6;
+    const f4 b = (q[0] + q[2]) * 0.5f - q[1];
+    const f4 c = (q[2] - q[0]) * 0.5f;
+    const f4 e = (q[0] + q[2] + q[1] * 4.0f) * s6;
+    const float h = 1.0f / float(K);
+    const float u0 = float(k) * h;
+    CurveSpan r;
+    r.c[0] = a * (h * h * h);
+    r.c[1] = (a * (3.0f * u0) + b) * (h * h);
+    r.c[2] = ((a * (3.0f * u0) + b * 2.0f) * u0 + c) * h;
+    r.c[3] = ((a * u0 + b) * u0 + c) * u0 + e;
+    return r;
+}
+// conservative box: Bezier control points of the span (convex hull) grown by the largest Bezier radius weight
+inline void curve_span_bounds(const CurveSpan& r, f3& lo, f3& hi)
+{
+    const float third = 1.0f / 3.0f;
+    const f4 B0 = r.c[3];
+    const f4 B1 = r.c[3] + r.c[2] * third;
+    const f4 B2 = r.c[3] + r.c[2] * (2.0f * third) + r.c[1] * third;
+    const f4 B3 = r.c[3] + r.c[2] + r.c[1] + r.c[0];
+    const float rmax = std::fmax(std::fmax(std::fabs(B0.w), std::fabs(B1.w)), std::fmax(std::fabs(B2.w), std::fabs(B3.w))) * 1.0001f;
+    lo = f3{ std::fmin(std::fmin(B0.x, B1.x), std::fmin(B2.x, B3.x)) - rmax, std::fmin(std::fmin(B0.y, B1.y), std::fmin(B2.y, B3.y)) - rmax,
+             std::fmin(std::fmin(B0.z, B1.z), std::fmin(B2.z, B3.z)) - rmax };
+    hi = mk3(std::fmax(std::fmax(B0.x, B1.x), std::fmax(B2.x, B3.x)) + rmax, std::fmax(std::fmax(B0.y, B1.y), std::fmax(B2.y, B3.y)) + rmax,
+             std::fmax(std::fmax(B0.z, B1.z), std::fmax(B2.z, B3.z)) + rmax);
+    // the power -> Bezier conversion rounds: pad by a few ulps of the coordinates
+    const float pad = 4.0e-7f * std::fmax(std::fmax(std::fabs(lo.x), std::fabs(hi.x)), std::fmax(std::fmax(std::fabs(lo.y), std::fabs(hi.y)), std::fmax(std::fabs(lo.z), std::fabs(hi.z))));
+    lo = lo - mk3(pad);
+    hi = hi + mk3(pad);
+}
+
+// ray vs one span of a round cubic curve; cf = power-basis coefficients (w = radius).  s in (0,1) on a hit.
+inline bool intersect_round_cubic_f32(const f4 cf[4], const f3& o, const f3& dIn, float tmin, float tmax, float& tOut, float& uOut)
 {
     const float dl2 = dot_fma(dIn, dIn);
     if (!(dl2 > 0.0f))
         return false;
     const float invLen = 1.0f / std::sqrt(dl2);
     const f3 d = dIn * invLen;
-    // polynomial coefficients relative to the ray origin
-    const float s6 = 1.0f / 6.0f;
-    const f4 a4 = (q[3] - q[0] + (q[1] - q[2]) * 3.0f) * s6;
-    const f4 b4 = (q[0] + q[2]) * 0.5f - q[1];
-    const f4 c4 = (q[2] - q[0]) * 0.5f;
-    f4 e4 = (q[0] + q[2] + q[1] * 4.0f) * s6;
+    const f4 a4 = cf[0], b4 = cf[1], c4 = cf[2];
+    f4 e4 = cf[3];
     e4.x -= o.x;
     e4.y -= o.y;
     e4.z -= o.z;

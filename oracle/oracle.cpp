@@ -51,10 +51,11 @@ struct WorldTri
 };
 struct WorldSeg
 {
-    f4 q[4]; // world-space control points, w = radius
+    CurveSpan span; // power-basis coefficients of span k of K of the segment, world space (w = radius)
     uint32_t prim; // index into the curve's segment list (optixGetPrimitiveIndex)
     uint32_t inst;
     uint32_t firstPoint; // global index of the first control point (segmentIndices[prim])
+    uint32_t k, K;
 };
 
 struct Hit
@@ -166,6 +167,7 @@ struct orc_scene
     std::vector<WorldTri> tris;
     std::vector<WorldSeg> segs;
     Bvh2 triBvh, segBvh;
+    uint32_t curveSplit = 8;
 };
 
 namespace
@@ -252,28 +254,28 @@ void build_scene(orc_scene& S, const sb_scene_view& v)
                 for (int s = 0; s < nseg; ++s)
                 {
                     const uint32_t first = c.points_start + offsetInside + uint32_t(s);
-                    WorldSeg ws;
-                    Aabb b;
-                    b.reset();
-                    float rmax = 0.0f;
+                    f4 q[4];
                     for (int k = 0; k < 4; ++k)
                     {
                         const f3 pw = xform_point(d.o2w, S.curvePoints[first + k]);
                         const float r = (first + k < S.curveRadii.size() ? S.curveRadii[first + k] : 0.0f) * scale;
-                        ws.q[k] = mk4(pw, r);
-                        rmax = std::fmax(rmax, r);
+                        q[k] = mk4(pw, r);
                     }
-                    // the B-spline segment lies in the convex hull of its 4 control points; so do
-                    // the radii (non-negative basis) -> hull box grown by the largest radius
-                    for (int k = 0; k < 4; ++k)
-                        b.grow(mk3(ws.q[k]));
-                    b.lo = b.lo - mk3(rmax);
-                    b.hi = b.hi + mk3(rmax);
-                    ws.prim = prim++;
-                    ws.inst = i;
-                    ws.firstPoint = first;
-                    S.segs.push_back(ws);
-                    segBoxes.push_back(b);
+                    for (uint32_t k = 0; k < S.curveSplit; ++k)
+                    {
+                        WorldSeg ws;
+                        ws.span = curve_span(q, k, S.curveSplit);
+                        ws.prim = prim;
+                        ws.inst = i;
+                        ws.firstPoint = first;
+                        ws.k = k;
+                        ws.K = S.curveSplit;
+                        Aabb b;
+                        curve_span_bounds(ws.span, b.lo, b.hi);
+                        S.segs.push_back(ws);
+                        segBoxes.push_back(b);
+                    }
+                    ++prim;
                 }
                 offsetInside += ncp;
             }
@@ -336,10 +338,11 @@ Hit trace_closest(const orc_scene& S, const f3& o, const f3& d, float tmin, floa
         S.segBvh.traverse(o, d, tmin, tmaxC, [&](uint32_t id, float& tmax) {
             const WorldSeg& W = S.segs[id];
             CurveHit ch{ false, 0.0f, 0.0f };
-            ch.hit = intersect_round_cubic_f32(W.q, o, d, tmin, tmax, ch.t, ch.u);
+            ch.hit = intersect_round_cubic_f32(W.span.c, o, d, tmin, tmax, ch.t, ch.u);
             if (ch.hit && (ch.t < tmax || (curveWon && ch.t == tmax && id < bestSeg)))
             {
-                hc = Hit{ ch.t, ch.u, 0.0f, W.prim, W.inst, 2 };
+                const float useg = (float(W.k) + ch.u) * (1.0f / float(W.K)); // span-local -> segment parameter
+                hc = Hit{ ch.t, useg, 0.0f, W.prim, W.inst, 2 };
                 bestSeg = id;
                 curveWon = true;
                 tmax = ch.t;
@@ -373,7 +376,7 @@ bool trace_any(const orc_scene& S, const f3& o, const f3& d, float tmin, float t
         return occluded;
     S.segBvh.traverse(o, d, tmin, tmaxIn, [&](uint32_t id, float& tmax) {
         float tc, uc;
-        if (intersect_round_cubic_f32(S.segs[id].q, o, d, tmin, tmax, tc, uc))
+        if (intersect_round_cubic_f32(S.segs[id].span.c, o, d, tmin, tmax, tc, uc))
         {
             occluded = true;
             return true;
@@ -707,9 +710,10 @@ f3 compute_exposure(const sb_settings& st)
 
 extern "C" {
 
-orc_scene* orc_scene_create(const sb_scene_view* view)
+orc_scene* orc_scene_create(const sb_scene_view* view, uint32_t curveSplit)
 {
     orc_scene* s = new orc_scene();
+    s->curveSplit = curveSplit ? curveSplit : 8u;
     build_scene(*s, *view);
     return s;
 }
@@ -996,7 +1000,8 @@ void orc_curve_intersect_f32(const float* q, const float* ray, float* out)
     for (int k = 0; k < 4; ++k)
         cp[k] = f4{ q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3] };
     float t = 0.0f, u = 0.0f;
-    const bool hit = intersect_round_cubic_f32(cp, f3{ ray[0], ray[1], ray[2] }, f3{ ray[3], ray[4], ray[5] }, ray[6], ray[7], t, u);
+    const CurveSpan sp = curve_span(cp, 0, 1); // the whole segment as one span
+    const bool hit = intersect_round_cubic_f32(sp.c, f3{ ray[0], ray[1], ray[2] }, f3{ ray[3], ray[4], ray[5] }, ray[6], ray[7], t, u);
     out[0] = hit ? 1.0f : 0.0f;
     out[1] = t;
     out[2] = u;

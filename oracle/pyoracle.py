@@ -31,7 +31,7 @@ def lib() -> C.CDLL:
         build()
         _lib = C.CDLL(_LIB)
         _lib.orc_scene_create.restype = C.c_void_p
-        _lib.orc_scene_create.argtypes = [C.POINTER(_abi.sb_scene_view)]
+        _lib.orc_scene_create.argtypes = [C.POINTER(_abi.sb_scene_view), C.c_uint32]
         _lib.orc_scene_destroy.argtypes = [C.c_void_p]
         _lib.orc_scene_info.argtypes = [C.c_void_p, C.c_void_p]
         _lib.orc_render.restype = C.c_uint32
@@ -64,10 +64,10 @@ def _p(a):
 class OracleScene:
     """CPU scene (world-space BVH2s) built from a strelka_b200.Scene."""
 
-    def __init__(self, scene):
+    def __init__(self, scene, curve_split=8):
         self._scene = scene
         self._view = scene.view()
-        self._h = lib().orc_scene_create(C.byref(self._view))
+        self._h = lib().orc_scene_create(C.byref(self._view), curve_split)
 
     def info(self) -> dict:
         out = np.zeros(4, dtype=np.uint64)

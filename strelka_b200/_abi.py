@@ -19,7 +19,8 @@ class SbError(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, _LIB_NAME)
+    # STRELKA_B200_LIB: alternative build of the same library (kernel-variant experiments); never a fallback
+    return os.environ.get("STRELKA_B200_LIB") or os.path.join(_HERE, _LIB_NAME)
 
 
 # ---- numpy dtypes of the scene arrays (byte-identical to the structs in sb_api.h) -------------
@@ -111,7 +112,7 @@ class sb_settings(C.Structure):
 
 
 class sb_device_cfg(C.Structure):
-    _fields_ = [("device", C.c_int32), ("max_batch_paths", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+    _fields_ = [("device", C.c_int32), ("max_batch_paths", C.c_uint32), ("flags", C.c_uint32), ("curve_split", C.c_uint32)]
 
 
 class sb_counters(C.Structure):

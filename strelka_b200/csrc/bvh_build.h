@@ -318,8 +318,10 @@ inline WideBvh build_wide_bvh(Exec& ex, const Aabb* boxes, uint32_t n, uint32_t 
 // device arrays of length numInstances+1 with the exclusive prefix sums of triangles / segments per
 // instance; segFirstPoint (per world segment) is precomputed on the host from the curve tables.
 inline void build_scene_bvhs(Exec& ex, SceneDev& S, const uint32_t* instTriFirst, uint32_t numTris, const uint32_t* instSegFirst,
-                             uint32_t numSegs, const SegInfo* segInfoUnsorted)
+                             uint32_t numSegments, const SegInfo* segInfoUnsorted, uint32_t curveSplit)
 {
+    const uint32_t K = curveSplit ? curveSplit : 1u;
+    const uint32_t numSegs = numSegments * K; // one traversal record per span
     S.numTris = numTris;
     S.numSegs = numSegs;
     const SceneDev Sv = S; // by-value copy for the lambdas
@@ -378,22 +380,23 @@ inline void build_scene_bvhs(Exec& ex, SceneDev& S, const uint32_t* instTriFirst
         SegRec* unsorted = ex.alloc<SegRec>(numSegs);
         Aabb* boxes = ex.alloc<Aabb>(numSegs);
         ex.pfor(numSegs, SB_LAMBDA(size_t g) {
-            const SegInfo si = segInfoUnsorted[g];
+            const SegInfo si = segInfoUnsorted[g / K];
+            const uint32_t k = uint32_t(g % K);
             const InstDev& I = Sv.instances[si.inst];
-            SegRec r;
-            Aabb b = aabb_empty();
-            float rmax = 0.0f;
-            for (int k = 0; k < 4; ++k)
+            float4 q[4];
+            for (int j = 0; j < 4; ++j)
             {
-                const uint32_t pi = si.firstPoint + k;
+                const uint32_t pi = si.firstPoint + j;
                 const float3 pw = xform_point(I.o2w, mk3(Sv.curvePoints[3 * pi], Sv.curvePoints[3 * pi + 1], Sv.curvePoints[3 * pi + 2]));
                 const float rad = (pi < Sv.numCurveRadii ? Sv.curveRadii[pi] : 0.0f) * I.scale;
-                r.q[k] = mk4(pw, rad);
-                rmax = fmaxf(rmax, rad);
-                aabb_grow(b, pw);
+                q[j] = mk4(pw, rad);
             }
-            b.lo = b.lo - mk3(rmax);
-            b.hi = b.hi + mk3(rmax);
+            const CurveSpan sp = curve_span(q, k, K);
+            SegRec r;
+            for (int j = 0; j < 4; ++j)
+                r.q[j] = sp.c[j];
+            Aabb b;
+            curve_span_bounds(sp, b.lo, b.hi);
             unsorted[g] = r;
             boxes[g] = b;
         });
@@ -402,8 +405,11 @@ inline void build_scene_bvhs(Exec& ex, SceneDev& S, const uint32_t* instTriFirst
         SegInfo* info = ex.alloc<SegInfo>(numSegs);
         const uint32_t* order = bvh.primOrder;
         ex.pfor(numSegs, SB_LAMBDA(size_t i) {
-            ordered[i] = unsorted[order[i]];
-            info[i] = segInfoUnsorted[order[i]];
+            const uint32_t g = order[i];
+            ordered[i] = unsorted[g];
+            SegInfo si = segInfoUnsorted[g / K];
+            si.span = (g % K) | (K << 16);
+            info[i] = si;
         });
         ex.free(unsorted);
         ex.free(boxes);

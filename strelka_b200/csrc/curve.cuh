@@ -5,8 +5,8 @@
 //     :246-254, acceleration4 :266-269, surfaceNormal<.,2> :306-353, curveTangent :412-417).
 // (2) This backend's own ray / round-curve intersector.  The reference has none: it relies on OptiX's
 //     closed built-in ROUND_CUBIC_BSPLINE primitive (OptixRender.cpp:553-560) -> parity unpinned; the
-//     CPU oracle implements the SAME surface definition with a slow bracketing solver and the two are
-//     compared in tests/test_gpu_curves.py.
+//     CPU oracle holds the same float solver (for image parity) plus a slow double-precision bracketing
+//     solver that validates it (tests/test_curves.py).
 //
 // Surface definition: union of spheres |x - c(u)| <= r(u), u in [0,1], no end caps.  With a unit ray
 // direction d, z(u) = (c(u)-o).d, rho(u) = distance of c(u) to the ray axis and g = rho^2 - r^2, the
@@ -83,20 +83,62 @@ SB_HD float3 cubic_tangent(const CubicSeg& bc, float u)
     return normalize(mk3(cubic_velocity4(bc, u)));
 }
 
-// ray vs round cubic B-spline segment; q = world-space control points (w = radius).
-SB_HD bool intersect_round_cubic(const float4 q[4], const float3& o, const float3& dIn, float tmin, float tmax, float& tOut, float& uOut)
+// A traversal record holds the POWER-BASIS coefficients of one sub-span of a segment in world space:
+// P(s) = c0 s^3 + c1 s^2 + c2 s + c3, s in [0,1], xyz + radius in w.  Splitting every segment into K spans
+// gives the BVH K short, nearly straight pieces with tight boxes (a 1.5 cm hair segment that runs diagonally
+// has an AABB hundreds of hair widths thick; K = 8 cut the primitives tested per ray by >10x on the 1 M-segment
+// scene) and lets the solver below start from a good chord guess.
+struct CurveSpan
+{
+    float4 c[4];
+};
+// span k of K of the B-spline segment with control points q (w = radius).  Fixed expression order: the CPU
+// oracle evaluates the same tree so that both sides hold identical records.
+SB_HD CurveSpan curve_span(const float4 q[4], uint32_t k, uint32_t K)
+{
+    const float s6 = 1.0f / 6.0f;
+    const float4 a = (q[3] - q[0] + (q[1] - q[2]) * 3.0f) * s6;
+    const float4 b = (q[0] + q[2]) * 0.5f - q[1];
+    const float4 c = (q[2] - q[0]) * 0.5f;
+    const float4 e = (q[0] + q[2] + q[1] * 4.0f) * s6;
+    const float h = 1.0f / float(K);
+    const float u0 = float(k) * h;
+    CurveSpan r;
+    r.c[0] = a * (h * h * h);
+    r.c[1] = (a * (3.0f * u0) + b) * (h * h);
+    r.c[2] = ((a * (3.0f * u0) + b * 2.0f) * u0 + c) * h;
+    r.c[3] = ((a * u0 + b) * u0 + c) * u0 + e;
+    return r;
+}
+// conservative box: Bezier control points of the span (convex hull) grown by the largest Bezier radius weight
+SB_HD void curve_span_bounds(const CurveSpan& r, float3& lo, float3& hi)
+{
+    const float third = 1.0f / 3.0f;
+    const float4 B0 = r.c[3];
+    const float4 B1 = r.c[3] + r.c[2] * third;
+    const float4 B2 = r.c[3] + r.c[2] * (2.0f * third) + r.c[1] * third;
+    const float4 B3 = r.c[3] + r.c[2] + r.c[1] + r.c[0];
+    const float rmax = fmaxf(fmaxf(fabsf(B0.w), fabsf(B1.w)), fmaxf(fabsf(B2.w), fabsf(B3.w))) * 1.0001f;
+    lo = mk3(fminf(fminf(B0.x, B1.x), fminf(B2.x, B3.x)) - rmax, fminf(fminf(B0.y, B1.y), fminf(B2.y, B3.y)) - rmax,
+             fminf(fminf(B0.z, B1.z), fminf(B2.z, B3.z)) - rmax);
+    hi = mk3(fmaxf(fmaxf(B0.x, B1.x), fmaxf(B2.x, B3.x)) + rmax, fmaxf(fmaxf(B0.y, B1.y), fmaxf(B2.y, B3.y)) + rmax,
+             fmaxf(fmaxf(B0.z, B1.z), fmaxf(B2.z, B3.z)) + rmax);
+    // the power -> Bezier conversion rounds: pad by a few ulps of the coordinates
+    const float pad = 4.0e-7f * fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fmaxf(fabsf(lo.y), fabsf(hi.y)), fmaxf(fabsf(lo.z), fabsf(hi.z))));
+    lo = lo - mk3(pad);
+    hi = hi + mk3(pad);
+}
+
+// ray vs one span of a round cubic curve; cf = power-basis coefficients (w = radius).  s in (0,1) on a hit.
+SB_HD bool intersect_round_cubic(const float4 cf[4], const float3& o, const float3& dIn, float tmin, float tmax, float& tOut, float& uOut)
 {
     const float dl2 = dot_fma(dIn, dIn);
     if (!(dl2 > 0.0f))
         return false;
     const float invLen = 1.0f / sqrtf(dl2);
     const float3 d = dIn * invLen;
-    // polynomial coefficients relative to the ray origin
-    const float s6 = 1.0f / 6.0f;
-    const float4 a4 = (q[3] - q[0] + (q[1] - q[2]) * 3.0f) * s6;
-    const float4 b4 = (q[0] + q[2]) * 0.5f - q[1];
-    const float4 c4 = (q[2] - q[0]) * 0.5f;
-    float4 e4 = (q[0] + q[2] + q[1] * 4.0f) * s6;
+    const float4 a4 = cf[0], b4 = cf[1], c4 = cf[2];
+    float4 e4 = cf[3];
     e4.x -= o.x;
     e4.y -= o.y;
     e4.z -= o.z;

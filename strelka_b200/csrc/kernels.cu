@@ -71,9 +71,15 @@ __device__ __forceinline__ void flush_stats(StatCounters* g, const TravStats& st
 // lanes busy: a lane whose ray is done pulls the next ray from the queue (one warp-aggregated atomic), and
 // refills happen whenever fewer than kRefill lanes still hold a ray (Aila & Laine 2009 style, using
 // trav_step so that node visits and primitive tests of different lanes interleave).
-constexpr int kRefill = 24;
-constexpr int kPrimBatch = 8; // primitive tests run once this many lanes have one pending (or a lane has nothing else to do)
-
+// Measured on the 2 M-triangle scene (profiles/r01_b_*): (1) batching primitive tests across the warp
+// ("primitive postponing") did not pay off: the extra convergence points stop independent thread scheduling
+// from interleaving the divergent node/primitive groups while they wait on loads; (2) the loop is extremely
+// sensitive to its control-flow shape -- one extra early-return inside trav_node cost 50 % -- so keep it flat:
+// one trav_step per lane, ONE warp-wide ballot per iteration.
+#ifndef SB_REFILL
+#define SB_REFILL 24
+#endif
+constexpr int kRefill = SB_REFILL;
 struct WarpFetch
 {
     bool exhausted;
@@ -105,7 +111,7 @@ __global__ void __launch_bounds__(kBlock) k_extend(FrameParams P, SceneDev S, Qu
     const int qi = int(depth & 1u);
     const bool haveTris = S.numTriNodes != 0u, haveSegs = S.numSegNodes != 0u;
     TravStats st = { 0, 0, 0, 0 };
-    bool active = false, exhausted = false, forced = false;
+    bool active = false, exhausted = false;
     uint32_t slot = 0;
     int phase = 0;
     Ray ray;
@@ -128,7 +134,6 @@ __global__ void __launch_bounds__(kBlock) k_extend(FrameParams P, SceneDev S, Qu
             hit.prim = hit.inst = hit.kind = 0u;
             hit.gid = 0xffffffffu;
             trav_init(T);
-            forced = false;
             phase = haveTris ? 0 : (haveSegs ? 1 : 2);
             active = true;
         }
@@ -136,58 +141,32 @@ __global__ void __launch_bounds__(kBlock) k_extend(FrameParams P, SceneDev S, Qu
             break;
         for (;;)
         {
-            // ---- node half-step for the lanes without pending primitives ----
-            bool finished = false;
-            if (active && T.tgroup.y == 0u)
+            if (active)
             {
-                const bool hadGroup = T.ngroup.y > 0x00ffffffu;
-                const bool more = (phase == 0) ? trav_node<STATS>(T, S.triNodes, ray, rp, &st) : (phase == 1 ? trav_node<STATS>(T, S.segNodes, ray, rp, &st) : false);
+                bool more = false, anyHit = false;
+                if (phase == 0)
+                    more = trav_step<1, false, STATS>(T, S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
+                else if (phase == 1)
+                    more = trav_step<2, false, STATS>(T, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
                 if (!more)
-                    finished = true;
-                else if (!hadGroup && T.ngroup.y == 0u && T.tgroup.y != 0u)
-                    forced = true; // popped a postponed primitive group: it must be processed now
-            }
-            // ---- primitive half-step, batched across the warp (primitive postponing, Ylitie et al. 2017) ----
-            const bool wantPrim = active && !finished && T.tgroup.y != 0u;
-            const unsigned primMask = __ballot_sync(0xffffffffu, wantPrim);
-            if (primMask)
-            {
-                const unsigned forceMask = __ballot_sync(0xffffffffu, wantPrim && forced);
-                if (__popc(primMask) >= kPrimBatch || forceMask)
                 {
-                    if (wantPrim)
+                    if (phase == 0 && haveSegs)
                     {
-                        if (phase == 0)
-                            trav_prim<1, false, STATS>(T, S.tris, kRayMaskPrimary, ray, hit, &st);
-                        else
-                            trav_prim<2, false, STATS>(T, S.segs, kRayMaskPrimary, ray, hit, &st);
-                        if (T.tgroup.y == 0u)
-                            forced = false;
+                        phase = 1;
+                        trav_init(T);
                     }
-                }
-                else if (wantPrim)
-                {
-                    if (T.sp < kStackSize)
-                        trav_postpone_prims(T);
                     else
-                        forced = true; // no room to park it: process it on the next pass
-                }
-            }
-            if (finished)
-            {
-                if (phase == 0 && haveSegs)
-                {
-                    phase = 1;
-                    trav_init(T);
-                    forced = false;
-                }
-                else
-                {
-                    if (hit.kind == 2u)
-                        hit.inst = S.segInfo[hit.prim].inst;
-                    Q.hitA[slot] = mk4(hit.t, hit.u, hit.v, u2f(hit.kind == 1u ? hit.gid : hit.prim));
-                    Q.hitB[slot] = hit.inst | (hit.kind << 30);
-                    active = false;
+                    {
+                        if (hit.kind == 2u)
+                        {
+                            const SegInfo si = S.segInfo[hit.prim];
+                            hit.inst = si.inst;
+                            hit.u = span_to_segment_u(si.span, hit.u);
+                        }
+                        Q.hitA[slot] = mk4(hit.t, hit.u, hit.v, u2f(hit.kind == 1u ? hit.gid : hit.prim));
+                        Q.hitB[slot] = hit.inst | (hit.kind << 30);
+                        active = false;
+                    }
                 }
             }
             const int busy = __popc(__ballot_sync(0xffffffffu, active));
@@ -208,7 +187,7 @@ __global__ void __launch_bounds__(kBlock) k_shadow(SceneDev S, Queues Q, uint32_
     uint32_t* head = &Q.counts[kHeadShadowBase + depth];
     const bool haveTris = S.numTriNodes != 0u, haveSegs = S.numSegNodes != 0u;
     TravStats st = { 0, 0, 0, 0 };
-    bool active = false, exhausted = false, forced = false;
+    bool active = false, exhausted = false;
     uint32_t slot = 0;
     int phase = 0;
     Ray ray;
@@ -230,7 +209,6 @@ __global__ void __launch_bounds__(kBlock) k_shadow(SceneDev S, Queues Q, uint32_
             hit.kind = 0u;
             hit.gid = 0xffffffffu;
             trav_init(T);
-            forced = false;
             phase = haveTris ? 0 : (haveSegs ? 1 : 2);
             active = true;
         }
@@ -238,60 +216,31 @@ __global__ void __launch_bounds__(kBlock) k_shadow(SceneDev S, Queues Q, uint32_
             break;
         for (;;)
         {
-            bool finished = false, occluded = false;
-            if (active && T.tgroup.y == 0u)
+            if (active)
             {
-                const bool hadGroup = T.ngroup.y > 0x00ffffffu;
-                const bool more = (phase == 0) ? trav_node<STATS>(T, S.triNodes, ray, rp, &st) : (phase == 1 ? trav_node<STATS>(T, S.segNodes, ray, rp, &st) : false);
+                bool more = false, occluded = false;
+                if (phase == 0)
+                    more = trav_step<1, true, STATS>(T, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st);
+                else if (phase == 1)
+                    more = trav_step<2, true, STATS>(T, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st);
                 if (!more)
-                    finished = true;
-                else if (!hadGroup && T.ngroup.y == 0u && T.tgroup.y != 0u)
-                    forced = true;
-            }
-            const bool wantPrim = active && !finished && T.tgroup.y != 0u;
-            const unsigned primMask = __ballot_sync(0xffffffffu, wantPrim);
-            if (primMask)
-            {
-                const unsigned forceMask = __ballot_sync(0xffffffffu, wantPrim && forced);
-                if (__popc(primMask) >= kPrimBatch || forceMask)
                 {
-                    if (wantPrim)
+                    if (!occluded && phase == 0 && haveSegs)
                     {
-                        if (phase == 0)
-                            occluded = trav_prim<1, true, STATS>(T, S.tris, kRayMaskShadow, ray, hit, &st);
-                        else
-                            occluded = trav_prim<2, true, STATS>(T, S.segs, kRayMaskShadow, ray, hit, &st);
-                        if (T.tgroup.y == 0u)
-                            forced = false;
+                        phase = 1;
+                        trav_init(T);
                     }
-                }
-                else if (wantPrim)
-                {
-                    if (T.sp < kStackSize)
-                        trav_postpone_prims(T);
                     else
-                        forced = true; // no room to park it: process it on the next pass
-                }
-            }
-            if (occluded)
-            {
-                active = false; // any hit ends the query; nothing is added
-            }
-            else if (finished)
-            {
-                if (phase == 0 && haveSegs)
-                {
-                    phase = 1;
-                    trav_init(T);
-                    forced = false;
-                }
-                else
-                {
-                    const float4 sc = Q.shC[slot];
-                    const uint32_t pathId = f2u(sc.w);
-                    const float4 L = Q.Lacc[pathId];
-                    Q.Lacc[pathId] = mk4(L.x + sc.x, L.y + sc.y, L.z + sc.z, 0.0f);
-                    active = false;
+                    {
+                        if (!occluded)
+                        {
+                            const float4 sc = Q.shC[slot];
+                            const uint32_t pathId = f2u(sc.w);
+                            const float4 L = Q.Lacc[pathId];
+                            Q.Lacc[pathId] = mk4(L.x + sc.x, L.y + sc.y, L.z + sc.z, 0.0f);
+                        }
+                        active = false;
+                    }
                 }
             }
             const int busy = __popc(__ballot_sync(0xffffffffu, active));
@@ -584,6 +533,7 @@ __global__ void k_test_trace(SceneDev S, uint32_t n, const float* rays, uint32_t
                     const SegInfo si = S.segInfo[hit.prim];
                     hit.inst = si.inst;
                     hit.prim = si.prim;
+                    hit.u = span_to_segment_u(si.span, hit.u);
                 }
             }
             h.t = hit.t;

@@ -43,6 +43,7 @@ struct sb_ctx
     std::string error;
     bool trackStats = false;
     uint32_t maxBatchPaths = 4u << 20;
+    uint32_t curveSplit = 8;
 
     SceneDev scene;
     bool haveScene = false;
@@ -426,6 +427,8 @@ sb_result sb_create(const sb_device_cfg* cfg, sb_ctx** out)
         c->trackStats = cfg && (cfg->flags & SB_CFG_TRAVERSAL_STATS);
         if (cfg && cfg->max_batch_paths)
             c->maxBatchPaths = cfg->max_batch_paths;
+        if (cfg && cfg->curve_split)
+            c->curveSplit = std::min<uint32_t>(cfg->curve_split, 64u);
         c->stats = dev_alloc<StatCounters>(1);
         SB_CUDA_CHECK(cudaMemsetAsync(c->stats, 0, sizeof(StatCounters), c->stream));
         c->sobolTab = upload_sobol_table(c->stream);
@@ -531,7 +534,7 @@ sb_result sb_set_scene(sb_ctx* c, const sb_scene_view* v)
     ex.numSms = c->numSms;
     try
     {
-        build_scene_bvhs(ex, s, c->instTriFirst, uint32_t(numTris), nullptr, uint32_t(segInfo.size()), c->segInfoUnsorted);
+        build_scene_bvhs(ex, s, c->instTriFirst, uint32_t(numTris), nullptr, uint32_t(segInfo.size()), c->segInfoUnsorted, c->curveSplit);
     }
     catch (...)
     {

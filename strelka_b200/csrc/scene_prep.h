@@ -99,7 +99,7 @@ inline void prepare_scene(const sb_scene_view* v, ScenePrep& out)
                     si.prim = prim++;
                     si.inst = i;
                     si.firstPoint = cc.points_start + offsetInside + uint32_t(s);
-                    si.pad = 0;
+                    si.span = 1u << 16;
                     segInfo.push_back(si);
                 }
                 offsetInside += ncp;

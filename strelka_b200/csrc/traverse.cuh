@@ -31,7 +31,7 @@ struct TriRec // 48 B
     float4 e1; // v1 - v0, w = bits(instance | visibilityMask << 28)
     float4 e2; // v2 - v0, w = bits(global triangle id)
 };
-struct SegRec // 64 B: world-space control points, w = radius
+struct SegRec // 64 B: power-basis coefficients of one span of a curve segment in world space (curve.cuh)
 {
     float4 q[4];
 };
@@ -40,8 +40,14 @@ struct SegInfo
     uint32_t prim; // optixGetPrimitiveIndex: index into the curve prim's segment list
     uint32_t inst;
     uint32_t firstPoint; // global index of the first control point
-    uint32_t pad;
+    uint32_t span; // k | K << 16: this record covers u in [k/K, (k+1)/K] of the segment
 };
+// segment parameter of a hit at span-local parameter s
+SB_HD float span_to_segment_u(uint32_t span, float s)
+{
+    const float K = float(span >> 16);
+    return (float(span & 0xffffu) + s) * (1.0f / K);
+}
 
 struct Ray
 {
@@ -71,12 +77,15 @@ SB_HD uint32_t byte_of(uint32_t w, int j)
 // conversion: I2F runs on the XU pipe at 16 lanes/clk/SM and was 59 % busy in the first ncu capture).
 // The scale 2^15 and the offset are folded into the per-node slab coefficients below, so a child plane
 // costs PRMT + FFMA.  Rounding: the offset term carries 2^15 cells -> at most 2^-9 of a quantisation cell.
-SB_HD float byte_to_unit_float(uint32_t w, int j)
+// float(byte j of w), exactly, without an int->float conversion: I2F runs on the XU pipe (16 lanes/clk/SM) and
+// was 59 % busy in the first ncu capture of this kernel.  One byte-permute builds the bit pattern of
+// 2^23 + b, one FADD removes the 2^23 -- both steps are exact, so the result equals float(b) bit for bit.
+SB_HD float byte_to_float(uint32_t w, int j)
 {
 #if defined(__CUDA_ARCH__)
-    return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (uint32_t(j) << 4)));
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + uint32_t(j))) - 8388608.0f;
 #else
-    return u2f(0x3F800000u | (byte_of(w, j) << 8));
+    return float(byte_of(w, j));
 #endif
 }
 
@@ -86,22 +95,13 @@ SB_HD uint32_t wide_node_hits(const uint4& n0, const uint4& n1, const uint4& n2,
                               const float3& idir, uint32_t octinv4, bool negx, bool negy, bool negz, float tmin, float tmax)
 {
     const float3 p = mk3(u2f(n0.x), u2f(n0.y), u2f(n0.z));
-    // plane distance t = q * (2^e * idir) + (p - o) * idir, evaluated as (1 + q 2^-15) * A + B with
-    // A = 2^15 * 2^e * idir and B = (p - o) * idir - A
-    const float ax = u2f((n0.w & 0xffu) << 23) * idir.x * 32768.0f;
-    const float ay = u2f(((n0.w >> 8) & 0xffu) << 23) * idir.y * 32768.0f;
-    const float az = u2f(((n0.w >> 16) & 0xffu) << 23) * idir.z * 32768.0f;
-    const float bx = fmaf(p.x - o.x, idir.x, -ax);
-    const float by = fmaf(p.y - o.y, idir.y, -ay);
-    const float bz = fmaf(p.z - o.z, idir.z, -az);
-    // Conservativeness, hoisted out of the child loop: near planes are pulled in and far planes pushed out
-    // by 2^-8 of a cell (covers the rounding of B), far planes additionally carry the 1 + 2*gamma(3)
-    // factor of Ize 2013 that the CPU oracle's slab test uses as well.
-    const float kFar = 1.0000004f, kCell = 0x1p-23f; // 2^-8 cell = |A| * 2^-23
-    const float bxN = bx - fabsf(ax) * kCell, byN = by - fabsf(ay) * kCell, bzN = bz - fabsf(az) * kCell;
-    const float axF = ax * kFar, ayF = ay * kFar, azF = az * kFar;
-    const float bxF = (bx + fabsf(ax) * kCell) * kFar, byF = (by + fabsf(ay) * kCell) * kFar, bzF = (bz + fabsf(az) * kCell) * kFar;
-    const float tmaxF = tmax * kFar;
+    // child plane distance t = q * (2^e * idir) + (p - o) * idir
+    const float ax = u2f((n0.w & 0xffu) << 23) * idir.x;
+    const float ay = u2f(((n0.w >> 8) & 0xffu) << 23) * idir.y;
+    const float az = u2f(((n0.w >> 16) & 0xffu) << 23) * idir.z;
+    const float bx = (p.x - o.x) * idir.x;
+    const float by = (p.y - o.y) * idir.y;
+    const float bz = (p.z - o.z) * idir.z;
     uint32_t hitmask = 0;
 #pragma unroll
     for (int half = 0; half < 2; ++half)
@@ -119,14 +119,16 @@ SB_HD uint32_t wide_node_hits(const uint4& n0, const uint4& n1, const uint4& n2,
 #pragma unroll
         for (int j = 0; j < 4; ++j)
         {
-            const float t0x = fmaf(byte_to_unit_float(nearx, j), ax, bxN);
-            const float t0y = fmaf(byte_to_unit_float(neary, j), ay, byN);
-            const float t0z = fmaf(byte_to_unit_float(nearz, j), az, bzN);
-            const float t1x = fmaf(byte_to_unit_float(farx, j), axF, bxF);
-            const float t1y = fmaf(byte_to_unit_float(fary, j), ayF, byF);
-            const float t1z = fmaf(byte_to_unit_float(farz, j), azF, bzF);
+            const float t0x = fmaf(byte_to_float(nearx, j), ax, bx);
+            const float t0y = fmaf(byte_to_float(neary, j), ay, by);
+            const float t0z = fmaf(byte_to_float(nearz, j), az, bz);
+            const float t1x = fmaf(byte_to_float(farx, j), ax, bx);
+            const float t1y = fmaf(byte_to_float(fary, j), ay, by);
+            const float t1z = fmaf(byte_to_float(farz, j), az, bz);
             const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
-            const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tmaxF));
+            // conservative far plane: the 1 + 2*gamma(3) factor of Ize 2013 (the CPU oracle's slab test uses it
+            // too).  It must scale the RESULT: pre-scaled plane coefficients lose it to cancellation.
+            const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tmax)) * 1.0000004f;
             if (cmin <= cmax)
                 hitmask |= byte_of(childBits4, j) << byte_of(bitIndex4, j);
         }
@@ -179,23 +181,13 @@ SB_HD RayPrep prepare_ray(const float3& d)
 }
 
 // Traversal state of one ray in one BVH.  A "node group" is (child base index, hit bits | inner mask), a
-// "primitive group" is (primitive base index, hit bits); the stack holds postponed node groups and, in the
-// persistent kernels, postponed primitive groups (told apart by the empty top byte of .y).
+// "primitive group" is (primitive base index, hit bits); the stack holds postponed node groups only.
 struct Traversal
 {
     uint2 ngroup, tgroup;
     int sp;
     uint2 stack[kStackSize];
 };
-// park the pending primitive group so that the lane can go on visiting nodes
-SB_HD void trav_postpone_prims(Traversal& T)
-{
-    if (T.sp < kStackSize)
-    {
-        T.stack[T.sp++] = T.tgroup;
-        T.tgroup.y = 0u;
-    }
-}
 SB_HD void trav_init(Traversal& T)
 {
     T.ngroup.x = 0u;
@@ -218,13 +210,6 @@ SB_HD bool trav_node(Traversal& T, const WideNode* __restrict__ nodes, const Ray
         if (T.sp == 0)
             return false;
         T.ngroup = T.stack[--T.sp];
-        if (T.ngroup.y <= 0x00ffffffu)
-        {
-            // a postponed primitive group (the persistent kernels park them on the same stack)
-            T.tgroup = T.ngroup;
-            T.ngroup.y = 0u;
-            return true;
-        }
     }
     const uint32_t hits = T.ngroup.y;
     const uint32_t bit = bfind32(hits);

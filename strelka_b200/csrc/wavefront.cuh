@@ -374,7 +374,11 @@ SB_HD void extend_one(const FrameParams& P, const SceneDev& S, const Queues& Q, 
     if (S.numSegNodes)
     {
         if (traverse_bvh<2, false, STATS>(S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, st))
-            hit.inst = S.segInfo[hit.prim].inst;
+        {
+            const SegInfo si = S.segInfo[hit.prim];
+            hit.inst = si.inst;
+            hit.u = span_to_segment_u(si.span, hit.u);
+        }
     }
     Q.hitA[slot] = mk4(hit.t, hit.u, hit.v, u2f(hit.kind == 1u ? hit.gid : hit.prim)); // triangles: global id; curves: SegInfo index
     Q.hitB[slot] = hit.inst | (hit.kind << 30);

@@ -119,12 +119,14 @@ class Buffer:
 class Render:
     """oka::Render (render.h:19-56) implemented by the B200 backend (RenderType::eCompute)."""
 
-    def __init__(self, device: int = 0, traversal_stats: bool = False, max_batch_paths: int = 0, stage_timers: bool = False):
+    def __init__(self, device: int = 0, traversal_stats: bool = False, max_batch_paths: int = 0, stage_timers: bool = False,
+                 curve_split: int = 0):
         self._lib = _abi.load_library()
         self._ctx = None
         self._device = device
         self._flags = (_abi.SB_CFG_TRAVERSAL_STATS if traversal_stats else 0) | (_abi.SB_CFG_STAGE_TIMERS if stage_timers else 0)
         self._max_batch = max_batch_paths
+        self._curve_split = curve_split
         self.mSharedCtx: SharedContext | None = None  # noqa: N815
         self.mScene: Scene | None = None  # noqa: N815
         self._scene_uploaded = False
@@ -148,7 +150,7 @@ class Render:
 
     # -- virtuals
     def init(self) -> None:
-        cfg = sb_device_cfg(self._device, self._max_batch, self._flags, 0)
+        cfg = sb_device_cfg(self._device, self._max_batch, self._flags, self._curve_split)
         h = C.c_void_p()
         rc = self._lib.sb_create(C.byref(cfg), C.byref(h))
         if rc != 0:

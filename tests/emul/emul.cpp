@@ -39,7 +39,7 @@ static T* dup(emul_scene* e, const T* src, size_t n)
 
 extern "C" {
 
-emul_scene* emul_scene_create(const sb_scene_view* v, char* err, int errLen)
+emul_scene* emul_scene_create(const sb_scene_view* v, uint32_t curveSplit, char* err, int errLen)
 {
     sobol_generate(h_sobol);
     emul_scene* e = new emul_scene();
@@ -78,7 +78,7 @@ emul_scene* emul_scene_create(const sb_scene_view* v, char* err, int errLen)
         uint32_t* triFirst = dup(e, prep.triFirst.data(), prep.triFirst.size());
         SegInfo* segInfo = dup(e, prep.segInfo.data(), prep.segInfo.size());
         ExecHost ex;
-        build_scene_bvhs(ex, s, triFirst, uint32_t(prep.numTris), nullptr, uint32_t(prep.segInfo.size()), segInfo);
+        build_scene_bvhs(ex, s, triFirst, uint32_t(prep.numTris), nullptr, uint32_t(prep.segInfo.size()), segInfo, curveSplit);
     }
     catch (const std::exception& ex)
     {
@@ -146,6 +146,7 @@ void emul_trace(const emul_scene* e, uint32_t n, const float* rays, uint32_t mod
                     const SegInfo si = S.segInfo[hit.prim];
                     hit.inst = si.inst;
                     hit.prim = si.prim;
+                    hit.u = span_to_segment_u(si.span, hit.u);
                 }
             }
             h.t = hit.t;
@@ -312,7 +313,8 @@ void emul_curve_intersect(const float* q, const float* ray, float* out)
     for (int k = 0; k < 4; ++k)
         cp[k] = mk4(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
     float t = 0.0f, u = 0.0f;
-    const bool hit = intersect_round_cubic(cp, mk3(ray[0], ray[1], ray[2]), mk3(ray[3], ray[4], ray[5]), ray[6], ray[7], t, u);
+    const CurveSpan sp = curve_span(cp, 0, 1); // the whole segment as one span
+    const bool hit = intersect_round_cubic(sp.c, mk3(ray[0], ray[1], ray[2]), mk3(ray[3], ray[4], ray[5]), ray[6], ray[7], t, u);
     out[0] = hit ? 1.0f : 0.0f;
     out[1] = t;
     out[2] = u;

@@ -21,7 +21,7 @@ def lib():
         subprocess.check_call(["make", "-C", _HERE, "-s"])
         _lib = C.CDLL(_LIB)
         _lib.emul_scene_create.restype = C.c_void_p
-        _lib.emul_scene_create.argtypes = [C.POINTER(_abi.sb_scene_view), C.c_char_p, C.c_int]
+        _lib.emul_scene_create.argtypes = [C.POINTER(_abi.sb_scene_view), C.c_uint32, C.c_char_p, C.c_int]
         _lib.emul_scene_destroy.argtypes = [C.c_void_p]
         _lib.emul_scene_info.argtypes = [C.c_void_p, C.c_void_p]
         _lib.emul_trace.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
@@ -35,11 +35,11 @@ def lib():
 
 
 class EmulScene:
-    def __init__(self, scene):
+    def __init__(self, scene, curve_split=8):
         self._scene = scene
         self._view = scene.view()
         err = C.create_string_buffer(512)
-        self._h = lib().emul_scene_create(C.byref(self._view), err, 512)
+        self._h = lib().emul_scene_create(C.byref(self._view), curve_split, err, 512)
         if not self._h:
             raise RuntimeError(err.value.decode())
 
