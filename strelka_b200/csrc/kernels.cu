@@ -31,6 +31,7 @@ uint32_t* upload_sobol_table(cudaStream_t stream)
 }
 
 constexpr int kBlock = 128;
+constexpr uint32_t kTinyBvhNodes = 64; // at or below this many wide nodes traversal is a few steps: no dynamic fetch
 
 __global__ void __launch_bounds__(kBlock) k_raygen(FrameParams P, Queues Q)
 {
@@ -266,6 +267,35 @@ __global__ void __launch_bounds__(kBlock) k_shade(FrameParams P, SceneDev S, Que
         shade_one(P, S, Q, depth, i, s_tab);
 }
 
+// ---- one-ray-per-thread variants -------------------------------------------------------------------------
+// Coherent or very short traversals (primary rays; scenes whose whole BVH is a handful of nodes) finish within a
+// few steps of each other: there the dynamic-fetch machinery only adds ballots and an L2 atomic per refill.
+template <bool STATS>
+__global__ void __launch_bounds__(kBlock) k_extend_simple(FrameParams P, SceneDev S, Queues Q, uint32_t depth)
+{
+    const uint32_t n = Q.counts[depth];
+    TravStats st = { 0, 0, 0, 0 };
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        extend_one<STATS>(P, S, Q, depth, i, &st);
+    if (STATS)
+        flush_stats(Q.stats, st, false);
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&Q.stats->radianceRays, (unsigned long long)n);
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(kBlock) k_shadow_simple(SceneDev S, Queues Q, uint32_t depth)
+{
+    const uint32_t n = Q.counts[kCountShadowBase + depth];
+    TravStats st = { 0, 0, 0, 0 };
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        shadow_one<STATS>(S, Q, i, &st);
+    if (STATS)
+        flush_stats(Q.stats, st, true);
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&Q.stats->shadowRays, (unsigned long long)n);
+}
+
 __global__ void __launch_bounds__(256) k_accumulate(FrameParams P, Queues Q, float4* S, float4* direct, uint32_t mode, uint32_t subframe)
 {
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P.nPixPadded; p += gridDim.x * blockDim.x)
@@ -417,6 +447,7 @@ static inline unsigned grid_for(const LaunchCfg& cfg, int blocksPerSm)
 void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const SceneDev& S, const Queues& Q, bool stats)
 {
     cudaStream_t st = cfg.stream;
+    const bool tiny = (S.numTriNodes + S.numSegNodes) <= kTinyBvhNodes;
     SB_CUDA_CHECK(cudaMemsetAsync(Q.counts, 0, sizeof(uint32_t) * kNumCounts, st));
     {
         ScopedStage sc(cfg, kStageRaygen);
@@ -426,10 +457,22 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
     {
         {
             ScopedStage sc(cfg, kStageExtend);
-            if (stats)
-                k_extend<true><<<grid_for(cfg, 8), kBlock, 0, st>>>(P, S, Q, depth);
+            // primary rays are coherent, and a scene of a few nodes is traversed in a few steps: one ray per thread
+            const bool persistent = !tiny && depth > 0;
+            if (persistent)
+            {
+                if (stats)
+                    k_extend<true><<<grid_for(cfg, 8), kBlock, 0, st>>>(P, S, Q, depth);
+                else
+                    k_extend<false><<<grid_for(cfg, 8), kBlock, 0, st>>>(P, S, Q, depth);
+            }
             else
-                k_extend<false><<<grid_for(cfg, 8), kBlock, 0, st>>>(P, S, Q, depth);
+            {
+                if (stats)
+                    k_extend_simple<true><<<grid_for(cfg, 16), kBlock, 0, st>>>(P, S, Q, depth);
+                else
+                    k_extend_simple<false><<<grid_for(cfg, 16), kBlock, 0, st>>>(P, S, Q, depth);
+            }
         }
         {
             ScopedStage sc(cfg, kStageShade);
@@ -438,10 +481,20 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
         if (P.debug == 1u)
             break; // debug normals: only the first hit is shaded (OptixRender.cu:151-152)
         ScopedStage sc(cfg, kStageShadow);
-        if (stats)
-            k_shadow<true><<<grid_for(cfg, 8), kBlock, 0, st>>>(S, Q, depth);
+        if (!tiny)
+        {
+            if (stats)
+                k_shadow<true><<<grid_for(cfg, 8), kBlock, 0, st>>>(S, Q, depth);
+            else
+                k_shadow<false><<<grid_for(cfg, 8), kBlock, 0, st>>>(S, Q, depth);
+        }
         else
-            k_shadow<false><<<grid_for(cfg, 8), kBlock, 0, st>>>(S, Q, depth);
+        {
+            if (stats)
+                k_shadow_simple<true><<<grid_for(cfg, 16), kBlock, 0, st>>>(S, Q, depth);
+            else
+                k_shadow_simple<false><<<grid_for(cfg, 16), kBlock, 0, st>>>(S, Q, depth);
+        }
     }
     SB_CUDA_CHECK(cudaGetLastError());
 }
