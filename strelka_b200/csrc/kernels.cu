@@ -255,16 +255,23 @@ __global__ void __launch_bounds__(kBlock) k_shadow(SceneDev S, Queues Q, uint32_
         atomicAdd(&Q.stats->shadowRays, (unsigned long long)n);
 }
 
-__global__ void __launch_bounds__(kBlock) k_shade(FrameParams P, SceneDev S, Queues Q, uint32_t depth)
+#ifndef SB_SHADE_MIN_BLOCKS
+#define SB_SHADE_MIN_BLOCKS 8 // measured: 64 registers + a few L1 spills beat 111 registers at 25 % occupancy (latency-bound kernel)
+#endif
+__global__ void __launch_bounds__(kBlock, SB_SHADE_MIN_BLOCKS) k_shade(FrameParams P, SceneDev S, Queues Q, uint32_t depth)
 {
     // 12 KB of byte-sliced Sobol tables per CTA (L2-resident source; 6 x 128-bit loads per thread)
     __shared__ __align__(16) uint32_t s_tab[kSobolTabWords];
     for (uint32_t i = threadIdx.x; i < kSobolTabWords / 4; i += blockDim.x)
         reinterpret_cast<uint4*>(s_tab)[i] = __ldg(reinterpret_cast<const uint4*>(Q.sobolTab) + i);
+    // 4 KB table of the 1024 possible unpacked normal components (exact same expression as the scalar path)
+    __shared__ float s_unpack[kUnpackLutSize];
+    for (uint32_t i = threadIdx.x; i < kUnpackLutSize; i += blockDim.x)
+        s_unpack[i] = unpack_component(i);
     __syncthreads();
     const uint32_t n = Q.counts[depth];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        shade_one(P, S, Q, depth, i, s_tab);
+        shade_one(P, S, Q, depth, i, s_tab, s_unpack);
 }
 
 // ---- one-ray-per-thread variants -------------------------------------------------------------------------

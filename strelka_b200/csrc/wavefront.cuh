@@ -121,13 +121,22 @@ SB_HD void raygen_one(const FrameParams& P, const Queues& Q, uint32_t pathId)
     Q.thr[0][slot] = mk4(1.0f, 1.0f, 1.0f, u2f(0u));
 }
 
-// unpackNormal, closest_hit.cu:236-244
-SB_HD float3 unpack_normal(uint32_t val)
+// unpackNormal, closest_hit.cu:236-244.  A packed component has 10 bits (12 for z, of which a valid packing
+// uses 10), so q / 511.99999f * 2 - 1 takes 1024 distinct values: the shade kernel reads them from a
+// shared-memory table built with exactly this expression (unpack_lut_fill) instead of paying an int->float
+// conversion and an IEEE division per component -- same bits.
+constexpr uint32_t kUnpackLutSize = 1024;
+SB_HD float unpack_component(uint32_t q)
 {
+    return float(q) / 511.99999f * 2.0f - 1.0f;
+}
+SB_HD float3 unpack_normal(uint32_t val, const float* lut = nullptr)
+{
+    const uint32_t qz = (val & 0xfff00000u) >> 20, qy = (val & 0x000ffc00u) >> 10, qx = val & 0x000003ffu;
     float3 n;
-    n.z = ((val & 0xfff00000u) >> 20) / 511.99999f * 2.0f - 1.0f;
-    n.y = ((val & 0x000ffc00u) >> 10) / 511.99999f * 2.0f - 1.0f;
-    n.x = (val & 0x000003ffu) / 511.99999f * 2.0f - 1.0f;
+    n.z = (lut && qz < kUnpackLutSize) ? lut[qz] : unpack_component(qz);
+    n.y = lut ? lut[qy] : unpack_component(qy);
+    n.x = lut ? lut[qx] : unpack_component(qx);
     return n;
 }
 // offset_ray, closest_hit.cu:218-233 (Ray Tracing Gems ch. 6)
@@ -154,15 +163,15 @@ struct Surface
 };
 
 // fillTriangleGeomData, closest_hit.cu:365-421 (quirks Q11, Q12)
-SB_HD Surface tri_surface(const SceneDev& S, const InstDev& I, const uint4& corners, float bu, float bv, bool inside)
+SB_HD Surface tri_surface(const SceneDev& S, const InstDev& I, const uint4& corners, float bu, float bv, bool inside, const float* lut)
 {
     const sb_vertex v0 = S.vertices[corners.x], v1 = S.vertices[corners.y], v2 = S.vertices[corners.z];
     const float3 p0 = mk3(v0.pos[0], v0.pos[1], v0.pos[2]), p1 = mk3(v1.pos[0], v1.pos[1], v1.pos[2]), p2 = mk3(v2.pos[0], v2.pos[1], v2.pos[2]);
     Surface s;
     s.position = xform_point(I.o2w, interp3(p0, p1, p2, bu, bv));
-    s.normal = normalize(xform_normal(I.w2o, interp3(unpack_normal(v0.normal), unpack_normal(v1.normal), unpack_normal(v2.normal), bu, bv)));
+    s.normal = normalize(xform_normal(I.w2o, interp3(unpack_normal(v0.normal, lut), unpack_normal(v1.normal, lut), unpack_normal(v2.normal, lut), bu, bv)));
     s.geomNormal = normalize(xform_normal(I.w2o, cross(p1 - p0, p2 - p0)));
-    s.tangent = normalize(xform_normal(I.w2o, interp3(unpack_normal(v0.tangent), unpack_normal(v1.tangent), unpack_normal(v2.tangent), bu, bv)));
+    s.tangent = normalize(xform_normal(I.w2o, interp3(unpack_normal(v0.tangent, lut), unpack_normal(v1.tangent, lut), unpack_normal(v2.tangent, lut), bu, bv)));
     const float flip = inside ? -1.0f : 1.0f;
     s.geomNormal *= flip;
     s.normal *= flip;
@@ -193,7 +202,8 @@ SB_HD Surface curve_surface(const SceneDev& S, const InstDev& I, uint32_t segInd
 }
 
 // One bounce of one path after its closest-hit query.  `depth` == prd.depth == sampler.depth.
-SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, uint32_t depth, uint32_t slot, const uint32_t* sobolTab)
+SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, uint32_t depth, uint32_t slot, const uint32_t* sobolTab,
+                     const float* unpackLut)
 {
     const int qi = int(depth & 1u), qo = qi ^ 1;
     const float4 ro = Q.rayO[qi][slot], rd = Q.rayD[qi][slot], th = Q.thr[qi][slot];
@@ -244,7 +254,7 @@ SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, u
 
     // ---- __closesthit__radiance, closest_hit.cu:456-606 --------------------------------------------
     const bool isInside = (flags & kFlagInside) != 0u;
-    const Surface sf = (kind == 1u) ? tri_surface(S, I, corners, ha.y, ha.z, isInside) : curve_surface(S, I, f2u(ha.w), ha.y, ha.x, rayO, rayD, isInside);
+    const Surface sf = (kind == 1u) ? tri_surface(S, I, corners, ha.y, ha.z, isInside, unpackLut) : curve_surface(S, I, f2u(ha.w), ha.y, ha.x, rayO, rayD, isInside);
     if (P.debug == 1u)
     {
         Q.Lacc[pathId] = mk4((sf.normal + mk3(1.0f)) * 0.5f, 0.0f); // closest_hit.cu:504-508

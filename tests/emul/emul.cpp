@@ -231,6 +231,9 @@ void emul_render(const emul_scene* e, const sb_settings* st, const float* view, 
     std::vector<uint32_t> sobolTab(kSobolTabWords);
     sobol_build_tables(h_sobol, sobolTab.data());
     Q.sobolTab = sobolTab.data();
+    std::vector<float> unpackLut(kUnpackLutSize);
+    for (uint32_t i = 0; i < kUnpackLutSize; ++i)
+        unpackLut[i] = unpack_component(i);
     float4* Sacc = reinterpret_cast<float4*>(Sbuf);
     std::vector<float4> direct(size_t(width) * height);
     const bool debugNormals = P.debug == 1u;
@@ -253,7 +256,7 @@ void emul_render(const emul_scene* e, const sb_settings* st, const float* view, 
             for (uint32_t i = 0; i < n; ++i)
                 extend_one<false>(P, S, Q, depth, i, &ts);
             for (uint32_t i = 0; i < n; ++i)
-                shade_one(P, S, Q, depth, i, (depth & 1u) ? Q.sobolTab : nullptr); // both code paths, same bits
+                shade_one(P, S, Q, depth, i, (depth & 1u) ? Q.sobolTab : nullptr, (depth & 1u) ? unpackLut.data() : nullptr); // both code paths, same bits
             if (debugNormals)
                 break;
             const uint32_t ns = counts[kCountShadowBase + depth];
