@@ -283,9 +283,16 @@ def run_b200(args) -> None:
         trav = top if top in per_ray else "extend"  # the roofline is defined for the traversal kernels
         n_rays = tc["radiance_rays"] if trav == "extend" else tc["shadow_rays"]
         achieved = per_ray[trav] * n_rays / (stage_ms[trav] * 1e-3) / 1e9 if stage_ms[trav] > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("c2", {}).get(f"k_{trav}", {}).get("dram_bytes_per_launch")
         roofline = {
             "bound": "hbm", "kernel": f"k_{trav}", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-            "traffic": None, "peak_source": peak_src, "alg_bytes_per_ray": per_ray[trav],
+            "traffic": traffic, "traffic_unit": "bytes per launch (ncu --set full, profiles/ncu_traffic.json)",
+            "alg_bytes_per_launch": per_ray[trav] * n_rays / max(stage_n[trav], 1),
+            "peak_source": peak_src, "alg_bytes_per_ray": per_ray[trav],
             "avg_launch_ms": stage_ms[trav] / max(stage_n[trav], 1), "launches": stage_n[trav],
             "nodes_per_ray": pc["nodes_visited"] / rr, "tris_per_ray": pc["tris_tested"] / rr,
             "stage_ms_share": {s: stage_ms[s] / max(sum(stage_ms.values()), 1e-9) for s in stages},

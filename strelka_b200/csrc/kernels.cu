@@ -145,10 +145,20 @@ __global__ void __launch_bounds__(kBlock) k_extend(FrameParams P, SceneDev S, Qu
             if (active)
             {
                 bool more = false, anyHit = false;
+#ifndef SB_EXTEND_UNIT_STEP
+#define SB_EXTEND_UNIT_STEP 0
+#endif
+#if SB_EXTEND_UNIT_STEP
+                if (phase == 0)
+                    more = trav_step_unit<1, false, STATS>(T, S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
+                else if (phase == 1)
+                    more = trav_step_unit<2, false, STATS>(T, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
+#else
                 if (phase == 0)
                     more = trav_step<1, false, STATS>(T, S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
                 else if (phase == 1)
                     more = trav_step<2, false, STATS>(T, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
+#endif
                 if (!more)
                 {
                     if (phase == 0 && haveSegs)
@@ -220,10 +230,20 @@ __global__ void __launch_bounds__(kBlock) k_shadow(SceneDev S, Queues Q, uint32_
             if (active)
             {
                 bool more = false, occluded = false;
+#ifndef SB_SHADOW_UNIT_STEP
+#define SB_SHADOW_UNIT_STEP 1
+#endif
+#if SB_SHADOW_UNIT_STEP
+                if (phase == 0)
+                    more = trav_step_unit<1, true, STATS>(T, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st);
+                else if (phase == 1)
+                    more = trav_step_unit<2, true, STATS>(T, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st);
+#else
                 if (phase == 0)
                     more = trav_step<1, true, STATS>(T, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st);
                 else if (phase == 1)
                     more = trav_step<2, true, STATS>(T, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st);
+#endif
                 if (!more)
                 {
                     if (!occluded && phase == 0 && haveSegs)

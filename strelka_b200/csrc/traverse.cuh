@@ -320,6 +320,25 @@ SB_HD bool trav_step(Traversal& T, const WideNode* __restrict__ nodes, const voi
     return true;
 }
 
+// Single-unit variant of trav_step: ONE primitive test if any is pending, else ONE node visit.  Measured on the
+// 2 M-triangle scene the any-hit (shadow) kernel runs 1.5x faster with this shape, the closest-hit kernel
+// slightly faster with the node+primitive shape above (profiles/r01_b_*).
+template <int KIND, bool ANY, bool STATS>
+SB_HD bool trav_step_unit(Traversal& T, const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask, Ray& ray,
+                          const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st)
+{
+    if (T.tgroup.y != 0u)
+    {
+        if (trav_prim<KIND, ANY, STATS>(T, prims, rayMask, ray, hit, st))
+        {
+            anyHit = true;
+            return false;
+        }
+        return true;
+    }
+    return trav_node<STATS>(T, nodes, ray, rp, st);
+}
+
 // Whole traversal of one BVH for one ray (test hooks, host emulation).  Returns true if a hit was found
 // (closest: hit updated and ray.tmax shrunk; any: first accepted hit).
 template <int KIND, bool ANY, bool STATS>
