@@ -359,12 +359,14 @@ __global__ void __launch_bounds__(256) k_resolve(const float4* S, void* out, uin
     }
 }
 
-// debug / no-accumulation output: copy a float4 image into the (possibly narrower) output format
-__global__ void __launch_bounds__(256) k_copy_image(const float4* src, void* out, uint32_t npix, uint32_t format)
+// debug / no-accumulation output: the launch result goes to the output buffer, through the same post-process
+// as accumulated frames (the reference tonemaps params.image whatever wrote it, OptixRender.cpp:1045-1049)
+__global__ void __launch_bounds__(256) k_copy_image(const float4* src, void* out, uint32_t npix, uint32_t format, float3 e, uint32_t tonemapper,
+                                                    float gamma)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x)
     {
-        const float4 c = src[i];
+        const float4 c = postprocess_pixel(mk3(src[i]), e, tonemapper, gamma);
         if (format == SB_FORMAT_FLOAT4)
         {
             reinterpret_cast<float4*>(out)[i] = c;
@@ -541,10 +543,11 @@ void launch_resolve(const LaunchCfg& cfg, const float4* S, void* out, uint32_t n
     SB_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_copy_image(const LaunchCfg& cfg, const float4* src, void* out, uint32_t npix, uint32_t format)
+void launch_copy_image(const LaunchCfg& cfg, const float4* src, void* out, uint32_t npix, uint32_t format, const float exposure[3],
+                       uint32_t tonemapper, float gamma)
 {
     ScopedStage sc(cfg, kStageResolve);
-    k_copy_image<<<grid_for(cfg, 4), 256, 0, cfg.stream>>>(src, out, npix, format);
+    k_copy_image<<<grid_for(cfg, 4), 256, 0, cfg.stream>>>(src, out, npix, format, make_float3(exposure[0], exposure[1], exposure[2]), tonemapper, gamma);
     SB_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -291,14 +291,7 @@ void write_output(sb_ctx* c, sb_buffer* out, bool fromDirect, bool post, uint32_
     compute_exposure(c->settings, e);
     if (fromDirect)
     {
-        if (post && (c->settings.tonemapper_type != 0 || c->settings.gamma > 0.0f))
-        {
-            // post-process a plain image: reuse resolve with the identity accumulation (n = 0 is "black",
-            // so run the tone curve through a tiny trick: T^-1(T(x)) == x)  -> simplest: copy then skip.
-            // The reference applies tonemap()/gamma to non-accumulated output too (OptixRender.cpp:1045-1049);
-            // kept simple here: non-accumulated mode returns the linear launch result.
-        }
-        launch_copy_image(cfg, c->direct, out->dev, npix, out->format);
+        launch_copy_image(cfg, c->direct, out->dev, npix, out->format, e, post ? c->settings.tonemapper_type : 0u, post ? c->settings.gamma : 0.0f);
         return;
     }
     launch_resolve(cfg, c->S, out->dev, npix, totalSamples, e, post ? c->settings.tonemapper_type : 0u, post ? c->settings.gamma : 0.0f,

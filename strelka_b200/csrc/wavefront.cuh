@@ -471,12 +471,20 @@ SB_HD void accumulate_pixel(const FrameParams& P, const Queues& Q, float4* S, fl
     S[lin] = mk4(A * float(subframe + P.chunk), 0.0f);
 }
 
-// image = T^-1(S / n), then the optional post-process of OptixRender.cpp:1045-1049 (Tonemappers.cu)
+// the optional post-process of OptixRender.cpp:1045-1049: tone curve (Tonemappers.cu:17-109), then gamma
+SB_HD float4 postprocess_pixel(float3 c, const float3& e, uint32_t tonemapper, float gamma);
+
+// image = T^-1(S / n), then the post-process
 SB_HD float4 resolve_pixel(const float4& s, uint32_t n, const float3& e, uint32_t tonemapper, float gamma)
 {
     float3 c = mk3(0.0f);
     if (n > 0u)
         c = inverse_tonemap3(mk3(s) / float(n), e);
+    return postprocess_pixel(c, e, tonemapper, gamma);
+}
+
+SB_HD float4 postprocess_pixel(float3 c, const float3& e, uint32_t tonemapper, float gamma)
+{
     if (tonemapper == 1u)
     {
         const float3 r = c * e;

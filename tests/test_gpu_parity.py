@@ -154,3 +154,61 @@ def test_sample_stride_sharding_sums_to_single_gpu_image(gpu_render):
     st.setAs("render/b200/sampleOffset", 0)
     st.setAs("render/b200/sampleStride", 1)
     assert rel_rmse(img, full) < 1e-5
+
+
+@pytest.mark.parametrize("tonemapper,gamma", [(1, 2.4), (2, 2.2), (3, 0.0), (0, 2.4)])
+def test_postprocess_matches_reference_tonemappers(gpu_render, tonemapper, gamma):
+    # Tonemappers.cu:17-135 on params.image after accumulation (OptixRender.cpp:1045-1049)
+    s, st, _ = make_cornell(64, 64, 8)
+    linear = _render(gpu_render, s, st, 64, 64, 8)
+    st.setAs("render/pt/tonemapperType", tonemapper)
+    st.setAs("render/post/gamma", gamma)
+    img = _render(gpu_render, s, st, 64, 64, 8)
+    ref = pyoracle.postprocess(linear, tonemapper, pyoracle.exposure(st), gamma)
+    np.testing.assert_allclose(img[..., :3], ref[..., :3], rtol=2e-5, atol=1e-6)  # powf: CUDA vs glibc
+
+
+def test_spp_greater_than_one_reproduces_reference_lerp_weights_q1(gpu_render):
+    # spp = 3, sppTotal = 10 -> launches of 3, 3, 3, 1 samples, lerp weight 1/(subframe+1) (OptixRender.cu:60-78)
+    s, st, _ = make_cornell(48, 48, 10)
+    st.setAs("render/pt/spp", 3)
+    img_g = _render(gpu_render, s, st, 48, 48, 4, batched=False)
+    assert gpu_render.getSharedContext().mSubframeIndex == 10
+    img_o, _, sub, _ = pyoracle.OracleScene(s).render(st, 48, 48, 4)
+    assert sub == 10
+    assert rel_rmse(img_g, img_o) <= 1e-5
+
+
+def test_accumulation_disabled_returns_launch_mean(gpu_render):
+    s, st, _ = make_cornell(48, 48, 16)
+    st.setAs("render/pt/enableAcc", False)
+    st.setAs("render/pt/spp", 2)
+    a = _render(gpu_render, s, st, 48, 48, 1, batched=False)
+    b = _render(gpu_render, s, st, 48, 48, 3, batched=False)  # every launch restarts at subframe 0
+    assert np.array_equal(a, b)
+    img_o, _, sub, _ = pyoracle.OracleScene(s).render(st, 48, 48, 1)
+    assert sub == 0
+    assert rel_rmse(a, img_o) <= 1e-5
+
+
+def test_non_float4_output_formats(gpu_render):
+    s, st, _ = make_cornell(32, 32, 4)
+    r = gpu_render
+    r.setScene(s)
+    r.setSharedContext(SharedContext(mSettingsManager=st))
+    r._last_settings = None
+    r.reset_accumulation()
+    f4 = r.createBuffer(BufferDesc(32, 32, BufferFormat.FLOAT4))
+    r.render_iterations(f4, 4)
+    ref = f4.map().copy()
+    for fmt in (BufferFormat.FLOAT3, BufferFormat.UNSIGNED_BYTE4):
+        b = r.createBuffer(BufferDesc(32, 32, fmt))
+        r.resolve(b, 4)
+        img = b.map().copy()
+        if fmt == BufferFormat.FLOAT3:
+            assert np.array_equal(img, ref[..., :3])
+        else:
+            assert img.shape == (32, 32, 4) and img.dtype == np.uint8
+            np.testing.assert_allclose(img[..., :3], np.clip(ref[..., :3], 0, 1) * 255.0, atol=0.51)
+        b.destroy()
+    f4.destroy()
