@@ -737,7 +737,7 @@ void orc_scene_info(const orc_scene* s, uint64_t* out /* [4]: tris, segs, triNod
 // post-process tonemap).  counters: [paths, radiance rays, shadow rays].  Returns the new subframe.
 uint32_t orc_render(const orc_scene* scene, const sb_settings* st, const float* clipToView, const float* viewToWorld,
                     uint32_t width, uint32_t height, uint32_t subframe, uint32_t launches, float* accum, float* image,
-                    uint64_t* counters, int nthreads)
+                    uint64_t* counters, int nthreads, float* aov)
 {
     RenderParams P;
     P.scene = scene;
@@ -786,18 +786,84 @@ uint32_t orc_render(const orc_scene* scene, const sb_settings* st, const float* 
                 const size_t pix = size_t(y) * width + x;
                 f3 accumC = accum ? f3{ accum[pix * 4], accum[pix * 4 + 1], accum[pix * 4 + 2] } : mk3(0.0f);
                 f3 img = accumC;
+                // AOV state of this pixel: params.diffuse / specular + their uint16 counters (OptixRender.cu:169-221)
+                f3 aovD = aov ? f3{ aov[pix * 10], aov[pix * 10 + 1], aov[pix * 10 + 2] } : mk3(0.0f);
+                f3 aovS = aov ? f3{ aov[pix * 10 + 4], aov[pix * 10 + 5], aov[pix * 10 + 6] } : mk3(0.0f);
+                uint32_t cntD = aov ? uint32_t(aov[pix * 10 + 8]) : 0u, cntS = aov ? uint32_t(aov[pix * 10 + 9]) : 0u;
                 for (size_t l = 0; l < launchSamples.size(); ++l)
                 {
                     const uint32_t n = launchSamples[l];
                     if (n == 0)
                     {
-                        img = accumC; // copy of accum to image, OptixRender.cpp:1022-1030
+                        // copy of accum / diffuse / specular to image, OptixRender.cpp:1020-1043
+                        img = st->debug == 2 ? aovD : (st->debug == 3 ? aovS : accumC);
                         continue;
                     }
-                    f3 result = mk3(0.0f);
+                    f3 result = mk3(0.0f), diffuse = mk3(0.0f), specular = mk3(0.0f);
+                    uint32_t nD = 0, nS = 0;
                     for (uint32_t sidx = 0; sidx < n; ++sidx)
-                        result += trace_path(P, x, y, launchStart[l] + sidx, cnt, nullptr);
+                    {
+                        uint8_t ev = 0;
+                        const f3 r = trace_path(P, x, y, launchStart[l] + sidx, cnt, &ev);
+                        result += r;
+                        if (ev == 2)
+                        {
+                            diffuse += r;
+                            ++nD;
+                        }
+                        if (ev == 3)
+                        {
+                            specular += r;
+                            ++nS;
+                        }
+                    }
                     result = result / float(n);
+                    const uint32_t sub0 = launchStart[l];
+                    f3 diffuseOut, specularOut;
+                    if (nD > 0)
+                    {
+                        diffuse = diffuse / float(nD);
+                        const uint32_t prev = sub0 > 0 ? cntD : 0u;
+                        aovD = ref_accumulate(aovD, diffuse, P.exposure, prev);
+                        diffuseOut = aovD;
+                        cntD = uint16_t(prev + nD);
+                    }
+                    else
+                    {
+                        if (sub0 == 0)
+                        {
+                            aovD = mk3(0.0f);
+                            cntD = 0;
+                        }
+                        diffuseOut = aovD;
+                    }
+                    if (nS > 0)
+                    {
+                        specular = specular / float(nS);
+                        const uint32_t prev = sub0 > 0 ? cntS : 0u;
+                        aovS = ref_accumulate(aovS, specular, P.exposure, prev);
+                        specularOut = aovS;
+                        cntS = uint16_t(prev + nS);
+                    }
+                    else
+                    {
+                        if (sub0 == 0)
+                        {
+                            aovS = mk3(0.0f);
+                            cntS = 0;
+                        }
+                        specularOut = cntS > 0 ? aovS : mk3(0.0f);
+                    }
+                    if (st->debug == 2)
+                    {
+                        img = diffuseOut;
+                        continue;
+                    }
+                    if (st->debug == 3)
+                    {
+                        img = specularOut;
+                        continue;
+                    }
                     if (acc && st->debug == 0)
                     {
                         accumC = ref_accumulate(accumC, result, P.exposure, launchStart[l]);
@@ -814,6 +880,11 @@ uint32_t orc_render(const orc_scene* scene, const sb_settings* st, const float* 
                     accum[pix * 4 + 1] = accumC.y;
                     accum[pix * 4 + 2] = accumC.z;
                     accum[pix * 4 + 3] = 1.0f;
+                }
+                if (aov)
+                {
+                    const float a[10] = { aovD.x, aovD.y, aovD.z, 1.0f, aovS.x, aovS.y, aovS.z, 1.0f, float(cntD), float(cntS) };
+                    std::memcpy(aov + pix * 10, a, sizeof(a));
                 }
                 image[pix * 4] = img.x;
                 image[pix * 4 + 1] = img.y;

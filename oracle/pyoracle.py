@@ -36,7 +36,7 @@ def lib() -> C.CDLL:
         _lib.orc_scene_info.argtypes = [C.c_void_p, C.c_void_p]
         _lib.orc_render.restype = C.c_uint32
         _lib.orc_render.argtypes = [C.c_void_p, C.POINTER(_abi.sb_settings), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
-                                    C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+                                    C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib.orc_path_radiance.argtypes = [C.c_void_p, C.POINTER(_abi.sb_settings), C.c_void_p, C.c_void_p, C.c_uint32,
                                            C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.orc_trace.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
@@ -83,7 +83,7 @@ class OracleScene:
         lib().orc_camera_matrices(_p(view), C.c_float(cam.fov), C.c_float(width / float(height)), _p(c2v), _p(v2w))
         return c2v, v2w
 
-    def render(self, settings, width: int, height: int, launches: int, subframe: int = 0, accum=None, threads: int = 0):
+    def render(self, settings, width: int, height: int, launches: int, subframe: int = 0, accum=None, threads: int = 0, aov=None):
         """Emulate `launches` reference render() calls.  Returns (image, accum, new_subframe, counters)."""
         st = settings.to_sb_settings() if hasattr(settings, "to_sb_settings") else settings
         c2v, v2w = self.camera_matrices(width, height)
@@ -92,7 +92,7 @@ class OracleScene:
         image = np.zeros((height, width, 4), dtype=np.float32)
         counters = np.zeros(3, dtype=np.uint64)
         sub = lib().orc_render(self._h, C.byref(st), _p(c2v), _p(v2w), width, height, subframe, launches, _p(accum), _p(image),
-                               _p(counters), threads)
+                               _p(counters), threads, _p(aov) if aov is not None else None)
         return image, accum, sub, {"paths": int(counters[0]), "radiance_rays": int(counters[1]), "shadow_rays": int(counters[2])}
 
     def path_radiance(self, settings, width, height, xs, ys, samples) -> np.ndarray:

@@ -323,10 +323,11 @@ __global__ void __launch_bounds__(kBlock) k_shadow_simple(SceneDev S, Queues Q, 
         atomicAdd(&Q.stats->shadowRays, (unsigned long long)n);
 }
 
-__global__ void __launch_bounds__(256) k_accumulate(FrameParams P, Queues Q, float4* S, float4* direct, uint32_t mode, uint32_t subframe)
+__global__ void __launch_bounds__(256) k_accumulate(FrameParams P, Queues Q, float4* S, float4* direct, float4* aovD, float4* aovS, uint32_t mode,
+                                                    uint32_t subframe)
 {
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P.nPixPadded; p += gridDim.x * blockDim.x)
-        accumulate_pixel(P, Q, S, direct, mode, subframe, p);
+        accumulate_pixel(P, Q, S, direct, aovD, aovS, mode, subframe, p);
 }
 
 // format: SB_FORMAT_* of the output buffer
@@ -528,10 +529,11 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
     SB_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_accumulate(const LaunchCfg& cfg, const FrameParams& P, const Queues& Q, float4* S, float4* direct, uint32_t mode, uint32_t subframe)
+void launch_accumulate(const LaunchCfg& cfg, const FrameParams& P, const Queues& Q, float4* S, float4* direct, float4* aovD, float4* aovS,
+                       uint32_t mode, uint32_t subframe)
 {
     ScopedStage sc(cfg, kStageAccumulate);
-    k_accumulate<<<grid_for(cfg, 4), 256, 0, cfg.stream>>>(P, Q, S, direct, mode, subframe);
+    k_accumulate<<<grid_for(cfg, 4), 256, 0, cfg.stream>>>(P, Q, S, direct, aovD, aovS, mode, subframe);
     SB_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -47,7 +47,8 @@ struct LaunchCfg
 uint32_t* upload_sobol_table(cudaStream_t stream); // also returns the device copy of the byte-sliced tables
 // one wavefront batch: raygen, then per bounce extend -> shade -> shadow
 void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const SceneDev& S, const Queues& Q, bool stats);
-void launch_accumulate(const LaunchCfg& cfg, const FrameParams& P, const Queues& Q, float4* S, float4* direct, uint32_t mode, uint32_t subframe);
+void launch_accumulate(const LaunchCfg& cfg, const FrameParams& P, const Queues& Q, float4* S, float4* direct, float4* aovD, float4* aovS,
+                       uint32_t mode, uint32_t subframe);
 void launch_resolve(const LaunchCfg& cfg, const float4* S, void* out, uint32_t npix, uint32_t n, const float exposure[3], uint32_t tonemapper,
                     float gamma, uint32_t format);
 void launch_copy_image(const LaunchCfg& cfg, const float4* src, void* out, uint32_t npix, uint32_t format, const float exposure[3],

@@ -65,6 +65,8 @@ struct sb_ctx
     uint32_t width = 0, height = 0, tilesX = 0, nPixPadded = 0, batchPaths = 0;
     float4* S = nullptr; // accumulation: sum of T(L)
     float4* direct = nullptr; // non-accumulated launch result
+    float4* aovD = nullptr; // diffuse / specular AOVs (debug views 2 / 3): count * A in xyz, count in w
+    float4* aovS = nullptr;
     Queues Q = {};
     StatCounters* stats = nullptr;
     uint32_t* sobolTab = nullptr;
@@ -124,6 +126,8 @@ void free_frame(sb_ctx* c)
 {
     dev_free(c->S);
     dev_free(c->direct);
+    dev_free(c->aovD);
+    dev_free(c->aovS);
     for (int i = 0; i < 2; ++i)
     {
         dev_free(c->Q.rayO[i]);
@@ -165,6 +169,8 @@ void ensure_frame(sb_ctx* c, uint32_t w, uint32_t h)
     const size_t np = c->batchPaths;
     c->S = dev_alloc<float4>(size_t(w) * h);
     c->direct = dev_alloc<float4>(size_t(w) * h);
+    c->aovD = dev_alloc<float4>(size_t(w) * h);
+    c->aovS = dev_alloc<float4>(size_t(w) * h);
     for (int i = 0; i < 2; ++i)
     {
         c->Q.rayO[i] = dev_alloc<float4>(np);
@@ -182,6 +188,8 @@ void ensure_frame(sb_ctx* c, uint32_t w, uint32_t h)
     c->Q.sobolTab = c->sobolTab;
     SB_CUDA_CHECK(cudaMemsetAsync(c->S, 0, sizeof(float4) * size_t(w) * h, c->stream));
     SB_CUDA_CHECK(cudaMemsetAsync(c->direct, 0, sizeof(float4) * size_t(w) * h, c->stream));
+    SB_CUDA_CHECK(cudaMemsetAsync(c->aovD, 0, sizeof(float4) * size_t(w) * h, c->stream));
+    SB_CUDA_CHECK(cudaMemsetAsync(c->aovS, 0, sizeof(float4) * size_t(w) * h, c->stream));
     c->subframe = 0; // new dimensions reset rendering (OptixRender.cpp:834)
 }
 
@@ -205,6 +213,19 @@ uint32_t local_sample_budget(const sb_settings& st)
     if (st.sample_offset >= st.spp_total)
         return 0u;
     return (st.spp_total - st.sample_offset + stride - 1u) / stride;
+}
+
+// SharedContext::mSubframeIndex = 0: the next launch restarts the beauty and AOV accumulations
+void reset_accum(sb_ctx* c)
+{
+    c->subframe = 0;
+    if (c->S)
+    {
+        const size_t bytes = sizeof(float4) * size_t(c->width) * c->height;
+        SB_CUDA_CHECK(cudaMemsetAsync(c->S, 0, bytes, c->stream));
+        SB_CUDA_CHECK(cudaMemsetAsync(c->aovD, 0, bytes, c->stream));
+        SB_CUDA_CHECK(cudaMemsetAsync(c->aovS, 0, bytes, c->stream));
+    }
 }
 
 void set_error(sb_ctx* c, const std::string& msg)
@@ -259,7 +280,7 @@ void render_samples(sb_ctx* c, uint32_t samples, uint32_t mode, bool debugNormal
     P.maxDepth = std::min<uint32_t>(st.depth, kMaxDepth - 1);
     P.sppTotal = st.spp_total;
     P.rectMethod = st.rect_light_sampling_method;
-    P.debug = debugNormals ? 1u : 0u;
+    P.debug = debugNormals ? 1u : (st.debug == 2u || st.debug == 3u ? st.debug : 0u);
     P.shadowTmin = st.shadow_ray_tmin;
     P.materialTmin = st.material_ray_tmin;
     fill_camera(c, float(c->width) / float(c->height), P);
@@ -278,7 +299,7 @@ void render_samples(sb_ctx* c, uint32_t samples, uint32_t mode, bool debugNormal
         P.chunk = chunk;
         P.sampleBase = st.sample_offset + (c->subframe + done) * P.sampleStride;
         launch_wavefront_batch(cfg, P, c->scene, c->Q, c->trackStats);
-        launch_accumulate(cfg, P, c->Q, c->S, c->direct, mode, c->subframe + done);
+        launch_accumulate(cfg, P, c->Q, c->S, c->direct, c->aovD, c->aovS, mode, c->subframe + done);
         done += chunk;
     }
 }
@@ -289,13 +310,15 @@ void write_output(sb_ctx* c, sb_buffer* out, bool fromDirect, bool post, uint32_
     const uint32_t npix = c->width * c->height;
     float e[3];
     compute_exposure(c->settings, e);
-    if (fromDirect)
+    const uint32_t dbg = c->settings.debug;
+    if (fromDirect && dbg != 2u && dbg != 3u)
     {
         launch_copy_image(cfg, c->direct, out->dev, npix, out->format, e, post ? c->settings.tonemapper_type : 0u, post ? c->settings.gamma : 0.0f);
         return;
     }
-    launch_resolve(cfg, c->S, out->dev, npix, totalSamples, e, post ? c->settings.tonemapper_type : 0u, post ? c->settings.gamma : 0.0f,
-                   out->format);
+    const float4* src = dbg == 2u ? c->aovD : (dbg == 3u ? c->aovS : c->S);
+    launch_resolve(cfg, src, out->dev, npix, (dbg == 2u || dbg == 3u) ? 0xffffffffu : totalSamples, e, post ? c->settings.tonemapper_type : 0u,
+                   post ? c->settings.gamma : 0.0f, out->format);
 }
 
 // OptiXRender::render (OptixRender.cpp:874-1057) for `iterations` consecutive calls
@@ -537,9 +560,7 @@ sb_result sb_set_scene(sb_ctx* c, const sb_scene_view* v)
     SB_CUDA_CHECK(cudaStreamSynchronize(st));
     ex.release();
     c->haveScene = true;
-    c->subframe = 0;
-    if (c->S)
-        SB_CUDA_CHECK(cudaMemsetAsync(c->S, 0, sizeof(float4) * size_t(c->width) * c->height, st));
+    reset_accum(c);
     c->buildMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     SB_API_END
 }
@@ -549,9 +570,7 @@ sb_result sb_reset_accumulation(sb_ctx* c)
     if (!c)
         return SB_FAIL;
     SB_API_BEGIN(c)
-    c->subframe = 0;
-    if (c->S)
-        SB_CUDA_CHECK(cudaMemsetAsync(c->S, 0, sizeof(float4) * size_t(c->width) * c->height, c->stream));
+    reset_accum(c);
     SB_API_END
 }
 
@@ -569,9 +588,7 @@ sb_result sb_set_camera(sb_ctx* c, const float view[16], float fovY)
         c->fovY = fovY;
         c->rawMatrices = false;
         // a changed view/projection resets accumulation (OptixRender.cpp:903-908)
-        c->subframe = 0;
-        if (c->S)
-            SB_CUDA_CHECK(cudaMemsetAsync(c->S, 0, sizeof(float4) * size_t(c->width) * c->height, c->stream));
+        reset_accum(c);
     }
     SB_API_END
 }
@@ -584,9 +601,7 @@ sb_result sb_set_camera_matrices(sb_ctx* c, const float clipToView[16], const fl
     std::memcpy(c->clipToViewRaw, clipToView, sizeof(c->clipToViewRaw));
     std::memcpy(c->viewToWorld, viewToWorld, sizeof(c->viewToWorld));
     c->rawMatrices = true;
-    c->subframe = 0;
-    if (c->S)
-        SB_CUDA_CHECK(cudaMemsetAsync(c->S, 0, sizeof(float4) * size_t(c->width) * c->height, c->stream));
+    reset_accum(c);
     SB_API_END
 }
 
@@ -610,9 +625,7 @@ sb_result sb_set_settings(sb_ctx* c, const sb_settings* s)
     c->haveSettings = true;
     if (reset)
     {
-        c->subframe = 0;
-        if (c->S)
-            SB_CUDA_CHECK(cudaMemsetAsync(c->S, 0, sizeof(float4) * size_t(c->width) * c->height, c->stream));
+        reset_accum(c);
     }
     SB_API_END
 }

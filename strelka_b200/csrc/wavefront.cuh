@@ -223,7 +223,8 @@ SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, u
     corners.x = corners.y = corners.z = corners.w = 0u;
     if (kind == 1u)
         corners = S.triShade[f2u(ha.w)];
-    float3 Lpath = mk3(Q.Lacc[pathId]);
+    const float4 Lacc4 = Q.Lacc[pathId];
+    float3 Lpath = mk3(Lacc4);
 
     if (I.type == SB_INSTANCE_LIGHT)
     {
@@ -246,7 +247,7 @@ SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, u
                     const float w = mis_balance(lastBsdfPdf, lightPdf);
                     Lpath += throughput * color * -dot(rayD, ln) * w;
                 }
-                Q.Lacc[pathId] = mk4(Lpath, 0.0f);
+                Q.Lacc[pathId] = mk4(Lpath, Lacc4.w);
             }
         }
         return; // throughput = 0: the path ends
@@ -271,7 +272,7 @@ SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, u
     const BsdfSample bs = bsdf_sample(mat, sf.normal, sf.geomNormal, k1, mk4(rn.v[0], rn.v[1], rn.v[2], rn.v[3]));
     if (bs.event == EV_ABSORB)
     {
-        return; // throughput = 0 (firstEventType = eAbsorb only matters for the AOVs)
+        return; // throughput = 0 (firstEventType = eAbsorb: counted by neither AOV)
     }
     const bool specularBounce = (bs.event & EV_SPECULAR) != 0;
     if (depth == 0u)
@@ -282,6 +283,10 @@ SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, u
         if (bs.event & EV_GLOSSY)
             ev = 3u;
         flags = (flags & ~(3u << kFlagEventShift)) | (ev << kFlagEventShift);
+        // AOV views (debug 2 / 3): remember the first event of this sample next to its radiance; nothing has
+        // been added to Lacc yet at depth 0 (NEE contributions arrive with the shadow stage)
+        if (P.debug >= 2u)
+            Q.Lacc[pathId] = mk4(0.0f, 0.0f, 0.0f, u2f(ev));
     }
     if (bs.event & (EV_DIFFUSE | EV_GLOSSY))
     {
@@ -416,7 +421,7 @@ SB_HD void shadow_one(const SceneDev& S, const Queues& Q, uint32_t j, TravStats*
     {
         const uint32_t pathId = f2u(sc.w);
         const float4 L = Q.Lacc[pathId];
-        Q.Lacc[pathId] = mk4(L.x + sc.x, L.y + sc.y, L.z + sc.z, 0.0f);
+        Q.Lacc[pathId] = mk4(L.x + sc.x, L.y + sc.y, L.z + sc.z, L.w);
     }
 }
 
@@ -435,7 +440,8 @@ SB_HD float3 inverse_tonemap3(const float3& c, const float3& e)
 //  mode 0: S += sum_k T(L_k)                      (spp == 1 per launch: the reference's running mean of T)
 //  mode 1: reference lerp for a launch of `chunk` samples (quirk Q1: weight 1/(subframe+1))
 //  mode 2: no accumulation: `direct` receives the linear mean of the launch
-SB_HD void accumulate_pixel(const FrameParams& P, const Queues& Q, float4* S, float4* direct, uint32_t mode, uint32_t subframe, uint32_t p)
+SB_HD void accumulate_pixel(const FrameParams& P, const Queues& Q, float4* S, float4* direct, float4* aovD, float4* aovS, uint32_t mode,
+                            uint32_t subframe, uint32_t p)
 {
     const uint32_t tile = p >> 5, within = p & 31u;
     const uint32_t x = (tile % P.tilesX) * 8u + (within & 7u), y = (tile / P.tilesX) * 4u + (within >> 3);
@@ -443,6 +449,60 @@ SB_HD void accumulate_pixel(const FrameParams& P, const Queues& Q, float4* S, fl
         return;
     const uint32_t lin = y * P.width + x;
     const float3 e = mk3(P.exposure[0], P.exposure[1], P.exposure[2]);
+    if (P.debug >= 2u)
+    {
+        // diffuse / specular AOVs, OptixRender.cu:157-221: samples whose FIRST bsdf event was diffuse / glossy,
+        // accumulated like the beauty buffer but with their own (uint16, quirk Q20) sample counters.  Stored as
+        // (count * A) in xyz and the count in w, A being the tone-mapped running value.  The beauty buffer is
+        // not updated in these views (the reference returns early, OptixRender.cu:212-221).
+        for (int which = 0; which < 2; ++which)
+        {
+            float4* buf = which == 0 ? aovD : aovS;
+            const uint32_t wantEv = which == 0 ? 2u : 3u;
+            float4 acc = buf[lin];
+            uint32_t cnt = uint32_t(acc.w);
+            if (mode == 0u)
+            {
+                for (uint32_t k = 0; k < P.chunk; ++k)
+                {
+                    const float4 L = Q.Lacc[k * P.nPixPadded + p];
+                    if (f2u(L.w) != wantEv)
+                        continue;
+                    const uint32_t prev = (subframe + k > 0u) ? cnt : 0u;
+                    const float3 t = tonemap3(mk3(L), e);
+                    const float3 sum = prev > 0u ? mk3(acc) + t : t;
+                    cnt = (prev + 1u) & 0xffffu;
+                    acc = mk4(sum, float(cnt));
+                }
+            }
+            else
+            {
+                float3 mean = mk3(0.0f);
+                uint32_t n = 0;
+                for (uint32_t k = 0; k < P.chunk; ++k)
+                {
+                    const float4 L = Q.Lacc[k * P.nPixPadded + p];
+                    if (f2u(L.w) == wantEv)
+                    {
+                        mean += mk3(L);
+                        ++n;
+                    }
+                }
+                if (n > 0u)
+                {
+                    mean = mean / float(n);
+                    const uint32_t prev = subframe > 0u ? cnt : 0u;
+                    float3 A = tonemap3(mean, e);
+                    if (prev > 0u)
+                        A = lerp(mk3(acc) / float(prev), A, 1.0f / float(prev + 1u));
+                    cnt = (prev + n) & 0xffffu;
+                    acc = mk4(A * float(cnt), float(cnt));
+                }
+            }
+            buf[lin] = acc;
+        }
+        return;
+    }
     if (mode == 0u)
     {
         float3 s = mk3(S[lin]);
@@ -474,9 +534,11 @@ SB_HD void accumulate_pixel(const FrameParams& P, const Queues& Q, float4* S, fl
 // the optional post-process of OptixRender.cpp:1045-1049: tone curve (Tonemappers.cu:17-109), then gamma
 SB_HD float4 postprocess_pixel(float3 c, const float3& e, uint32_t tonemapper, float gamma);
 
-// image = T^-1(S / n), then the post-process
+// image = T^-1(S / n), then the post-process.  n == 0xffffffff: the count is per pixel, in s.w (AOV buffers)
 SB_HD float4 resolve_pixel(const float4& s, uint32_t n, const float3& e, uint32_t tonemapper, float gamma)
 {
+    if (n == 0xffffffffu)
+        n = uint32_t(s.w);
     float3 c = mk3(0.0f);
     if (n > 0u)
         c = inverse_tonemap3(mk3(s) / float(n), e);

@@ -192,7 +192,7 @@ void emul_render(const emul_scene* e, const sb_settings* st, const float* view, 
     P.maxDepth = st->depth;
     P.sppTotal = st->spp_total;
     P.rectMethod = st->rect_light_sampling_method;
-    P.debug = st->debug == 1 ? 1u : 0u;
+    P.debug = (st->debug >= 1 && st->debug <= 3) ? st->debug : 0u;
     P.shadowTmin = st->shadow_ray_tmin;
     P.materialTmin = st->material_ray_tmin;
     clip_to_view_from_fov(fovY, float(width) / float(height), P.clipToView);
@@ -235,7 +235,7 @@ void emul_render(const emul_scene* e, const sb_settings* st, const float* view, 
     for (uint32_t i = 0; i < kUnpackLutSize; ++i)
         unpackLut[i] = unpack_component(i);
     float4* Sacc = reinterpret_cast<float4*>(Sbuf);
-    std::vector<float4> direct(size_t(width) * height);
+    std::vector<float4> direct(size_t(width) * height), aovD(size_t(width) * height, mk4(0, 0, 0, 0)), aovS(size_t(width) * height, mk4(0, 0, 0, 0));
     const bool debugNormals = P.debug == 1u;
     const uint32_t mode = debugNormals ? 2u : 0u;
     uint32_t done = 0;
@@ -265,13 +265,20 @@ void emul_render(const emul_scene* e, const sb_settings* st, const float* view, 
                 shadow_one<false>(S, Q, i, &ts);
         }
         for (uint32_t p = 0; p < P.nPixPadded; ++p)
-            accumulate_pixel(P, Q, Sacc, direct.data(), mode, subframe + done, p);
+            accumulate_pixel(P, Q, Sacc, direct.data(), aovD.data(), aovS.data(), mode, subframe + done, p);
         done += chunk;
     }
     const float3 ex = mk3(P.exposure[0], P.exposure[1], P.exposure[2]);
     float4* img = reinterpret_cast<float4*>(image);
     for (size_t i = 0; i < size_t(width) * height; ++i)
-        img[i] = debugNormals ? direct[i] : resolve_pixel(Sacc[i], subframe + samples, ex, st->tonemapper_type, st->gamma);
+    {
+        if (debugNormals)
+            img[i] = direct[i];
+        else if (P.debug >= 2u)
+            img[i] = resolve_pixel(P.debug == 2u ? aovD[i] : aovS[i], 0xffffffffu, ex, st->tonemapper_type, st->gamma);
+        else
+            img[i] = resolve_pixel(Sacc[i], subframe + samples, ex, st->tonemapper_type, st->gamma);
+    }
 }
 
 void emul_sampler(uint32_t n, const uint32_t* x, const uint32_t* y, const uint32_t* sample, const uint32_t* maxs, const uint32_t* depth,

@@ -136,6 +136,24 @@ def test_debug_normals_exact():
     assert np.array_equal(img_o[..., :3], img_e[..., :3])
 
 
+@pytest.mark.parametrize("debug", [2, 3])
+def test_aov_views_match_oracle(debug):
+    # diffuse / specular AOVs (OptixRender.cu:157-221): per-AOV sample counters, image = that AOV
+    s, st = random_scene(seed=5)
+    st.setAs("render/pt/sppTotal", 6)
+    st.setAs("render/pt/debug", debug)
+    o, e = pyoracle.OracleScene(s), pyemul.EmulScene(s)
+    aov = np.zeros((30, 40, 10), dtype=np.float32)
+    img_o, _, sub, _ = o.render(st, 40, 30, 6, aov=aov)
+    img_e, _, _ = e.render(st, 40, 30, 6, chunk_max=4)
+    assert sub == 6
+    assert img_o[..., :3].max() > 0.0
+    counts = aov[..., 8 if debug == 2 else 9]
+    assert counts.max() > 0 and counts.min() == 0  # some pixels never saw this event: they stay black
+    assert np.all(img_e[counts == 0][..., :3] == 0.0)
+    assert rel_rmse(img_e, img_o) < 1e-5
+
+
 def test_progressive_equals_batched():
     # 6 launches one by one == one call with 6 samples in chunks of 4 (sum form is order independent)
     s, st, _ = make_cornell(32, 32, 6)

@@ -212,3 +212,19 @@ def test_non_float4_output_formats(gpu_render):
             np.testing.assert_allclose(img[..., :3], np.clip(ref[..., :3], 0, 1) * 255.0, atol=0.51)
         b.destroy()
     f4.destroy()
+
+
+@pytest.mark.parametrize("debug,spp", [(2, 1), (3, 1), (3, 3)])
+def test_aov_views_match_oracle_on_device(gpu_render, debug, spp):
+    # diffuse / specular AOV views (OptixRender.cu:157-221) with their own per-pixel sample counters
+    s, st = random_scene(seed=5)
+    st.setAs("render/pt/sppTotal", 9)
+    st.setAs("render/pt/spp", spp)
+    st.setAs("render/pt/debug", debug)
+    launches = 9 // spp
+    img_g = _render(gpu_render, s, st, 40, 30, launches, batched=(spp == 1))
+    assert gpu_render.getSharedContext().mSubframeIndex == 9
+    img_o, _, sub, _ = pyoracle.OracleScene(s).render(st, 40, 30, launches)
+    assert sub == 9
+    assert img_o[..., :3].max() > 0.0
+    assert rel_rmse(img_g, img_o) <= 1e-5
