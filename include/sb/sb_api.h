@@ -212,7 +212,10 @@ typedef struct sb_device_cfg
 enum
 {
     SB_CFG_TRAVERSAL_STATS = 1u, /* run the instrumented traversal kernels (counts nodes/prims per ray) */
-    SB_CFG_STAGE_TIMERS = 2u     /* bracket every kernel launch with CUDA events (per-stage device time) */
+    SB_CFG_STAGE_TIMERS = 2u,    /* bracket every kernel launch with CUDA events (per-stage device time) */
+    SB_CFG_FUSED_SMALL = 4u      /* scenes of a few BVH nodes run whole paths in one kernel (path state in registers,
+                                    path regeneration) instead of the wavefront queues.  Same images bit for bit;
+                                    measured slower on B200, kept for A/B measurements */
 };
 
 /* RenderFactory::createRender(RenderType::eCompute) + Render::init()
@@ -329,9 +332,9 @@ typedef struct sb_counters
     double render_ms;        /* device time of the last render call (CUDA events) */
     uint64_t kernel_launches; /* kernels launched by render/resolve calls since the last reset */
     /* SB_CFG_STAGE_TIMERS only: device milliseconds and launch counts per stage since the last reset,
-     * order: raygen, extend, shade, shadow, accumulate, resolve */
-    double stage_ms[6];
-    uint64_t stage_launches[6];
+     * order: raygen, extend, shade, shadow, accumulate, resolve, fused path kernel, (reserved) */
+    double stage_ms[8];
+    uint64_t stage_launches[8];
 } sb_counters;
 
 sb_result sb_get_counters(sb_ctx* ctx, sb_counters* out); /* synchronizes */

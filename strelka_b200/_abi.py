@@ -82,6 +82,7 @@ SB_MATERIAL_DIFFUSE, SB_MATERIAL_USD_PREVIEW_SURFACE, SB_MATERIAL_HAIR = 0, 1, 2
 SB_FORMAT_UNSIGNED_BYTE4, SB_FORMAT_FLOAT4, SB_FORMAT_FLOAT3 = 0, 1, 2
 SB_CFG_TRAVERSAL_STATS = 1
 SB_CFG_STAGE_TIMERS = 2
+SB_CFG_FUSED_SMALL = 4
 
 
 class sb_scene_view(C.Structure):
@@ -125,10 +126,10 @@ class sb_counters(C.Structure):
         ("bvh_nodes_tri", C.c_uint64), ("bvh_nodes_curve", C.c_uint64),
         ("build_ms", C.c_double), ("render_ms", C.c_double),
         ("kernel_launches", C.c_uint64),
-        ("stage_ms", C.c_double * 6), ("stage_launches", C.c_uint64 * 6),
+        ("stage_ms", C.c_double * 8), ("stage_launches", C.c_uint64 * 8),
     ]
 
-    STAGES = ("raygen", "extend", "shade", "shadow", "accumulate", "resolve")
+    STAGES = ("raygen", "extend", "shade", "shadow", "accumulate", "resolve", "path_fused", "reserved")
 
     def as_dict(self):
         d = {}

@@ -31,13 +31,81 @@ uint32_t* upload_sobol_table(cudaStream_t stream)
 }
 
 constexpr int kBlock = 128;
+constexpr int kBlockWarps = kBlock / 32;
 constexpr uint32_t kTinyBvhNodes = 64; // at or below this many wide nodes traversal is a few steps: no dynamic fetch
+
+// Block-aggregated queue allocation.  The first ncu source view of k_shade had a third of its stall samples
+// on the two warp-aggregated atomicAdds of the queue cursors: every warp of the chip hits the same two L2
+// addresses once per iteration and same-address atomics serialise in the L2 slice.  Here all threads of a block
+// reach the allocation point together (the callers loop block-uniformly), count with ballots, and ONE thread per
+// queue issues the atomic for the whole block: 4x fewer atomics, and the survivors of a block land in
+// consecutive slots.  `buf` alternates between consecutive calls so that one __syncthreads pair per call suffices.
+struct BlockAlloc
+{
+    uint32_t warpCount[2][2][kBlockWarps]; // [buf][queue][warp]
+    uint32_t base[2][2]; // [buf][queue]
+};
+// wantA / wantB: this thread needs a slot in queue A / B.  Returns the slots through slotA / slotB.
+__device__ __forceinline__ void block_alloc2(BlockAlloc& sh, uint32_t buf, uint32_t* counterA, uint32_t* counterB, bool wantA, bool wantB,
+                                             uint32_t& slotA, uint32_t& slotB)
+{
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned maskA = __ballot_sync(0xffffffffu, wantA), maskB = __ballot_sync(0xffffffffu, wantB);
+    if (lane == 0u)
+    {
+        sh.warpCount[buf][0][warp] = __popc(maskA);
+        sh.warpCount[buf][1][warp] = __popc(maskB);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2u)
+    {
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < kBlockWarps; ++w)
+            total += sh.warpCount[buf][threadIdx.x][w];
+        uint32_t* counter = threadIdx.x == 0u ? counterA : counterB;
+        sh.base[buf][threadIdx.x] = (total != 0u && counter != nullptr) ? atomicAdd(counter, total) : 0u;
+    }
+    __syncthreads();
+    uint32_t offA = sh.base[buf][0], offB = sh.base[buf][1];
+#pragma unroll
+    for (int w = 0; w < kBlockWarps; ++w)
+    {
+        if (w < int(warp))
+        {
+            offA += sh.warpCount[buf][0][w];
+            offB += sh.warpCount[buf][1][w];
+        }
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    slotA = offA + __popc(maskA & lt);
+    slotB = offB + __popc(maskB & lt);
+}
 
 __global__ void __launch_bounds__(kBlock) k_raygen(FrameParams P, Queues Q)
 {
+    __shared__ BlockAlloc s_alloc;
     const uint32_t n = P.nPixPadded * P.chunk;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        raygen_one(P, Q, i);
+    uint32_t buf = 0;
+    for (uint32_t base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock, buf ^= 1u)
+    {
+        const uint32_t i = base + threadIdx.x;
+        PathState ps;
+        bool valid = false;
+        if (i < n)
+        {
+            Q.Lacc[i] = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+            valid = raygen_state(P, i, ps);
+        }
+        uint32_t slot, unused;
+        block_alloc2(s_alloc, buf, &Q.counts[0], nullptr, valid, false, slot, unused);
+        if (valid)
+        {
+            Q.rayO[0][slot] = mk4(ps.o, u2f(i));
+            Q.rayD[0][slot] = mk4(ps.d, 0.0f);
+            Q.thr[0][slot] = mk4(1.0f, 1.0f, 1.0f, u2f(0u));
+        }
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(&Q.stats->paths, (unsigned long long)(P.width) * P.height * P.chunk);
 }
@@ -258,7 +326,7 @@ __global__ void __launch_bounds__(kBlock) k_shadow(SceneDev S, Queues Q, uint32_
                             const float4 sc = Q.shC[slot];
                             const uint32_t pathId = f2u(sc.w);
                             const float4 L = Q.Lacc[pathId];
-                            Q.Lacc[pathId] = mk4(L.x + sc.x, L.y + sc.y, L.z + sc.z, 0.0f);
+                            Q.Lacc[pathId] = mk4(L.x + sc.x, L.y + sc.y, L.z + sc.z, L.w);
                         }
                         active = false;
                     }
@@ -275,6 +343,25 @@ __global__ void __launch_bounds__(kBlock) k_shadow(SceneDev S, Queues Q, uint32_
         atomicAdd(&Q.stats->shadowRays, (unsigned long long)n);
 }
 
+// shade_bounce sink of k_shade: radiance goes straight to Lacc, the shadow ray is parked in shared memory
+struct StagedSink
+{
+    const Queues& Q;
+    float4 *o, *d, *c;
+    bool shadow;
+    __device__ __forceinline__ void radiance_changed(const PathState& ps) const
+    {
+        Q.Lacc[ps.pathId] = ps.L;
+    }
+    __device__ __forceinline__ void shadow_ray(const PathState& ps, const float4& so, const float4& sd, const float3& contrib)
+    {
+        *o = so;
+        *d = sd;
+        *c = mk4(contrib, u2f(ps.pathId));
+        shadow = true;
+    }
+};
+
 #ifndef SB_SHADE_MIN_BLOCKS
 #define SB_SHADE_MIN_BLOCKS 8 // measured: 64 registers + a few L1 spills beat 111 registers at 25 % occupancy (latency-bound kernel)
 #endif
@@ -289,9 +376,160 @@ __global__ void __launch_bounds__(kBlock, SB_SHADE_MIN_BLOCKS) k_shade(FramePara
     for (uint32_t i = threadIdx.x; i < kUnpackLutSize; i += blockDim.x)
         s_unpack[i] = unpack_component(i);
     __syncthreads();
+    // shadow rays wait in shared memory (not in registers: the kernel is register-bound) until the block
+    // allocates its queue slots at the end of the iteration
+    __shared__ float4 s_shO[kBlock], s_shD[kBlock], s_shC[kBlock];
+    __shared__ BlockAlloc s_alloc;
+    const int qi = int(depth & 1u), qo = qi ^ 1;
     const uint32_t n = Q.counts[depth];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        shade_one(P, S, Q, depth, i, s_tab, s_unpack);
+    uint32_t buf = 0;
+    for (uint32_t base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock, buf ^= 1u)
+    {
+        const uint32_t slot = base + threadIdx.x;
+        StagedSink sink = { Q, &s_shO[threadIdx.x], &s_shD[threadIdx.x], &s_shC[threadIdx.x], false };
+        PathState ps;
+        bool next = false;
+        if (slot < n)
+        {
+            const uint32_t hb = Q.hitB[slot];
+            if ((hb >> 30) != 0u) // else __miss__ms: the path ends
+            {
+                const float4 ro = Q.rayO[qi][slot], rd = Q.rayD[qi][slot], th = Q.thr[qi][slot];
+                const float4 ha = Q.hitA[slot];
+                ps.o = mk3(ro);
+                ps.d = mk3(rd);
+                ps.lastBsdfPdf = rd.w;
+                ps.throughput = mk3(th);
+                ps.flags = f2u(th.w);
+                ps.pathId = f2u(ro.w);
+                ps.L = Q.Lacc[ps.pathId];
+                next = shade_bounce(P, S, ps, ha, hb, depth, s_tab, s_unpack, sink);
+            }
+        }
+        uint32_t sslot, nslot;
+        block_alloc2(s_alloc, buf, &Q.counts[kCountShadowBase + depth], &Q.counts[depth + 1u], sink.shadow, next, sslot, nslot);
+        if (sink.shadow)
+        {
+            Q.shO[sslot] = s_shO[threadIdx.x];
+            Q.shD[sslot] = s_shD[threadIdx.x];
+            Q.shC[sslot] = s_shC[threadIdx.x];
+        }
+        if (next)
+        {
+            Q.rayO[qo][nslot] = mk4(ps.o, u2f(ps.pathId));
+            Q.rayD[qo][nslot] = mk4(ps.d, ps.lastBsdfPdf);
+            Q.thr[qo][nslot] = mk4(ps.throughput, u2f(ps.flags));
+        }
+    }
+}
+
+// ---- single-kernel path tracer for small scenes (opt-in: SB_CFG_FUSED_SMALL) -------------------------------
+// An experiment kept for A/B runs.  When the BVH is a handful of nodes (the Cornell box of the headline
+// benchmark: 3 nodes, 36 triangles) nothing of the scene comes from DRAM and the wavefront form streams ~300 B of
+// queue records per ray through HBM, so one would expect a register-resident megakernel to win.  Here the path
+// state stays in registers for the whole path and a lane whose path has ended takes the next (pixel, sample)
+// immediately (path regeneration).  Path ids are handed out in runs of kFusedGrab per warp (one L2 atomic per
+// run).  Per path the arithmetic is that of the wavefront kernels, operation for operation: bit-identical images.
+// MEASURED on B200, C2 at 64 spp: 42.5 ms (80 registers, 6 blocks/SM; 46.7 ms at 128 registers, 44.4 ms at 64)
+// against 30.9 ms for the wavefront form.  Regeneration keeps the lanes occupied but not useful: only ~45 % of
+// the bounces cast a shadow ray and ~10 % of the rays miss, so most lanes idle through the shadow traversal and
+// the tail of shading, which the wavefront queues compact away; and with 6 warps per scheduler the chains of
+// dependent L1 loads are not hidden.  The wavefront form stays the default for every scene size.
+#ifndef SB_FUSED_MIN_BLOCKS
+#define SB_FUSED_MIN_BLOCKS 6
+#endif
+constexpr uint32_t kFusedGrab = 256;
+template <bool STATS>
+__global__ void __launch_bounds__(kBlock, SB_FUSED_MIN_BLOCKS) k_path_fused(FrameParams P, SceneDev S, Queues Q)
+{
+    __shared__ __align__(16) uint32_t s_tab[kSobolTabWords];
+    for (uint32_t i = threadIdx.x; i < kSobolTabWords / 4; i += blockDim.x)
+        reinterpret_cast<uint4*>(s_tab)[i] = __ldg(reinterpret_cast<const uint4*>(Q.sobolTab) + i);
+    __shared__ float s_unpack[kUnpackLutSize];
+    for (uint32_t i = threadIdx.x; i < kUnpackLutSize; i += blockDim.x)
+        s_unpack[i] = unpack_component(i);
+    __syncthreads();
+    const uint32_t nPaths = P.nPixPadded * P.chunk;
+    uint32_t* head = &Q.counts[kHeadFused];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned laneLt = (1u << lane) - 1u;
+    uint32_t runNext = 0, runEnd = 0; // warp-uniform: the run of path ids this warp still owns
+    bool exhausted = false; // warp-uniform
+    bool alive = false;
+    uint32_t depth = 0;
+    PathState ps;
+    uint32_t nRadiance = 0, nShadow = 0;
+    TravStats stE = { 0, 0, 0, 0 }, stS = { 0, 0, 0, 0 };
+    for (;;)
+    {
+        // ---- regeneration: hand the next path ids to the idle lanes
+        unsigned want = __ballot_sync(0xffffffffu, !alive);
+        while (want != 0u)
+        {
+            if (runNext == runEnd)
+            {
+                if (exhausted)
+                    break;
+                uint32_t base = 0;
+                if (lane == 0u)
+                    base = atomicAdd(head, kFusedGrab);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= nPaths)
+                {
+                    exhausted = true;
+                    break;
+                }
+                runNext = base;
+                runEnd = min(base + kFusedGrab, nPaths);
+            }
+            const uint32_t avail = runEnd - runNext;
+            const uint32_t rank = __popc(want & laneLt);
+            if (!alive && rank < avail)
+            {
+                const uint32_t pathId = runNext + rank;
+                alive = raygen_state(P, pathId, ps);
+                depth = 0u;
+                if (!alive)
+                    Q.Lacc[pathId] = mk4(0.0f, 0.0f, 0.0f, 0.0f); // padding pixel of an edge tile
+            }
+            runNext += min(avail, uint32_t(__popc(want)));
+            want = __ballot_sync(0xffffffffu, !alive);
+        }
+        if (__ballot_sync(0xffffffffu, alive) == 0u)
+            break;
+        // ---- one bounce for every lane that holds a path
+        if (alive)
+        {
+            ++nRadiance;
+            const bool next = path_bounce<STATS>(P, S, ps, depth, s_tab, s_unpack, nShadow, &stE, &stS);
+            if (next)
+            {
+                ++depth;
+            }
+            else
+            {
+                Q.Lacc[ps.pathId] = ps.L;
+                alive = false;
+            }
+        }
+    }
+    if (STATS)
+    {
+        flush_stats(Q.stats, stE, false);
+        flush_stats(Q.stats, stS, true);
+    }
+    for (int off = 16; off > 0; off >>= 1)
+    {
+        nRadiance += __shfl_xor_sync(0xffffffffu, nRadiance, off);
+        nShadow += __shfl_xor_sync(0xffffffffu, nShadow, off);
+    }
+    if (lane == 0u)
+    {
+        atomicAdd(&Q.stats->radianceRays, (unsigned long long)nRadiance);
+        atomicAdd(&Q.stats->shadowRays, (unsigned long long)nShadow);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&Q.stats->paths, (unsigned long long)(P.width) * P.height * P.chunk);
 }
 
 // ---- one-ray-per-thread variants -------------------------------------------------------------------------
@@ -479,6 +717,16 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
     cudaStream_t st = cfg.stream;
     const bool tiny = (S.numTriNodes + S.numSegNodes) <= kTinyBvhNodes;
     SB_CUDA_CHECK(cudaMemsetAsync(Q.counts, 0, sizeof(uint32_t) * kNumCounts, st));
+    if (tiny && cfg.fusedSmall)
+    {
+        ScopedStage sc(cfg, kStagePathFused);
+        if (stats)
+            k_path_fused<true><<<grid_for(cfg, SB_FUSED_MIN_BLOCKS), kBlock, 0, st>>>(P, S, Q);
+        else
+            k_path_fused<false><<<grid_for(cfg, SB_FUSED_MIN_BLOCKS), kBlock, 0, st>>>(P, S, Q);
+        SB_CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     {
         ScopedStage sc(cfg, kStageRaygen);
         k_raygen<<<grid_for(cfg, 8), kBlock, 0, st>>>(P, Q);

@@ -14,6 +14,7 @@ enum Stage
     kStageShadow,
     kStageAccumulate,
     kStageResolve,
+    kStagePathFused, // whole paths in one kernel (small scenes)
     kNumStages
 };
 
@@ -28,8 +29,8 @@ struct StageTimer
     };
     std::vector<cudaEvent_t> pool;
     std::vector<Pending> pending;
-    double ms[kNumStages] = { 0, 0, 0, 0, 0, 0 };
-    uint64_t launches[kNumStages] = { 0, 0, 0, 0, 0, 0 };
+    double ms[kNumStages] = {};
+    uint64_t launches[kNumStages] = {};
     cudaEvent_t get();
     void collect();
     void reset();
@@ -42,6 +43,7 @@ struct LaunchCfg
     int numSms;
     StageTimer* timer; // may be null
     uint64_t* launchCount; // may be null
+    bool fusedSmall; // scenes of a few BVH nodes run the single-kernel path tracer
 };
 
 uint32_t* upload_sobol_table(cudaStream_t stream); // also returns the device copy of the byte-sliced tables

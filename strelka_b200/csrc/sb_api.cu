@@ -42,6 +42,7 @@ struct sb_ctx
     uint64_t launchCount = 0;
     std::string error;
     bool trackStats = false;
+    bool fusedSmall = false;
     uint32_t maxBatchPaths = 4u << 20;
     uint32_t curveSplit = 8;
 
@@ -263,6 +264,7 @@ LaunchCfg launch_cfg(const sb_ctx* c)
     l.numSms = c->numSms;
     l.timer = c->stageTimers ? const_cast<StageTimer*>(&c->timer) : nullptr;
     l.launchCount = const_cast<uint64_t*>(&c->launchCount);
+    l.fusedSmall = c->fusedSmall;
     return l;
 }
 
@@ -441,6 +443,7 @@ sb_result sb_create(const sb_device_cfg* cfg, sb_ctx** out)
         SB_CUDA_CHECK(cudaEventCreate(&c->evStart));
         SB_CUDA_CHECK(cudaEventCreate(&c->evStop));
         c->trackStats = cfg && (cfg->flags & SB_CFG_TRAVERSAL_STATS);
+        c->fusedSmall = cfg && (cfg->flags & SB_CFG_FUSED_SMALL);
         if (cfg && cfg->max_batch_paths)
             c->maxBatchPaths = cfg->max_batch_paths;
         if (cfg && cfg->curve_split)

@@ -24,6 +24,7 @@ constexpr uint32_t kMaxDepth = 32;
 constexpr uint32_t kCountShadowBase = 32; // counts[0..31] path queues per depth, counts[32..63] shadow queues
 constexpr uint32_t kHeadExtendBase = 64; // counts[64..95] / [96..127]: dynamic-fetch cursors of k_extend / k_shadow
 constexpr uint32_t kHeadShadowBase = 96;
+constexpr uint32_t kHeadFused = 127; // path-id dispenser of the fused small-scene kernel
 constexpr uint32_t kNumCounts = 128;
 
 // per-path flag bits (stored in thr.w)
@@ -95,13 +96,25 @@ SB_HD float4 mat4_mul(const float* m, const float4& v)
                m[8] * v.x + m[9] * v.y + m[10] * v.z + m[11] * v.w, m[12] * v.x + m[13] * v.y + m[14] * v.z + m[15] * v.w);
 }
 
-SB_HD void raygen_one(const FrameParams& P, const Queues& Q, uint32_t pathId)
+// The state one path carries from bounce to bounce (PerRayData, OptixRender.cu:85-153): queue records in the
+// wavefront kernels, registers in the fused path kernel.
+struct PathState
+{
+    float3 o, d; // current path segment
+    float lastBsdfPdf;
+    float3 throughput;
+    uint32_t flags;
+    uint32_t pathId;
+    float4 L; // radiance collected so far; w = bits(first bsdf event) for the AOV views
+};
+
+// Primary path segment of one (pixel, sample): false for the padding pixels of an edge tile.
+SB_HD bool raygen_state(const FrameParams& P, uint32_t pathId, PathState& ps)
 {
     uint32_t x, y, k;
     path_pixel(P, pathId, x, y, k);
-    Q.Lacc[pathId] = mk4(0.0f, 0.0f, 0.0f, 0.0f);
     if (x >= P.width || y >= P.height)
-        return;
+        return false;
     const uint32_t sidx = sampler_index(x, y, P.sampleBase + k * P.sampleStride, P.sppTotal);
     const uint32_t s0 = fmix32(52u);
     const uint32_t index = owen_scramble(sidx, s0);
@@ -113,11 +126,25 @@ SB_HD void raygen_one(const FrameParams& P, const Queues& Q, uint32_t pathId)
     const float ndcy = (posy / float(P.height)) * 2.0f - 1.0f;
     const float4 vs = mat4_mul(P.clipToView, mk4(ndcx, ndcy, 1.0f, 1.0f));
     const float4 wdir = mat4_mul(P.viewToWorld, mk4(vs.x, vs.y, vs.z, 0.0f));
-    const float3 origin = mk3(mat4_mul(P.viewToWorld, mk4(0.0f, 0.0f, 0.0f, 1.0f)));
-    const float3 dir = normalize(mk3(wdir));
+    ps.o = mk3(mat4_mul(P.viewToWorld, mk4(0.0f, 0.0f, 0.0f, 1.0f)));
+    ps.d = normalize(mk3(wdir));
+    ps.lastBsdfPdf = 0.0f;
+    ps.throughput = mk3(1.0f, 1.0f, 1.0f);
+    ps.flags = 0u;
+    ps.pathId = pathId;
+    ps.L = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+    return true;
+}
+
+SB_HD void raygen_one(const FrameParams& P, const Queues& Q, uint32_t pathId)
+{
+    Q.Lacc[pathId] = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+    PathState ps;
+    if (!raygen_state(P, pathId, ps))
+        return;
     const uint32_t slot = queue_alloc(&Q.counts[0]);
-    Q.rayO[0][slot] = mk4(origin, u2f(pathId));
-    Q.rayD[0][slot] = mk4(dir, 0.0f);
+    Q.rayO[0][slot] = mk4(ps.o, u2f(pathId));
+    Q.rayD[0][slot] = mk4(ps.d, 0.0f);
     Q.thr[0][slot] = mk4(1.0f, 1.0f, 1.0f, u2f(0u));
 }
 
@@ -201,30 +228,30 @@ SB_HD Surface curve_surface(const SceneDev& S, const InstDev& I, uint32_t segInd
     return s;
 }
 
-// One bounce of one path after its closest-hit query.  `depth` == prd.depth == sampler.depth.
-SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, uint32_t depth, uint32_t slot, const uint32_t* sobolTab,
-                     const float* unpackLut)
+// One bounce of one path after its closest-hit query (ha = t,u,v,bits(prim); hb = instance | kind << 30).
+// `depth` == prd.depth == sampler.depth.  Returns true when the path continues with the updated PathState.
+// Side effects go through `sink` at the point they arise (keeps the live ranges short):
+//   sink.radiance_changed(ps)                      ps.L changed (emitter hit, debug view, NaN guard, AOV tag)
+//   sink.shadow_ray(ps, shO, shD, contrib)         trace (origin.xyz + tmin, dir.xyz + tmax); add contrib to L if unoccluded
+template <class Sink>
+SB_HD bool shade_bounce(const FrameParams& P, const SceneDev& S, PathState& ps, const float4& ha, uint32_t hb, uint32_t depth, const uint32_t* sobolTab,
+                        const float* unpackLut, Sink& sink)
 {
-    const int qi = int(depth & 1u), qo = qi ^ 1;
-    const float4 ro = Q.rayO[qi][slot], rd = Q.rayD[qi][slot], th = Q.thr[qi][slot];
-    const float4 ha = Q.hitA[slot];
-    const uint32_t hb = Q.hitB[slot];
-    const uint32_t pathId = f2u(ro.w);
-    const float3 rayO = mk3(ro), rayD = mk3(rd);
-    float3 throughput = mk3(th);
-    uint32_t flags = f2u(th.w);
-    const float lastBsdfPdf = rd.w;
+    const uint32_t pathId = ps.pathId;
+    const float3 rayO = ps.o, rayD = ps.d;
+    float3 throughput = ps.throughput;
+    uint32_t flags = ps.flags;
+    const float lastBsdfPdf = ps.lastBsdfPdf;
     const uint32_t kind = hb >> 30;
     if (kind == 0u)
-        return; // __miss__ms: radiance += throughput * bg_color(0); path ends
-    // independent loads issued together: instance record, corner indices (triangles), path radiance
+        return false; // __miss__ms: radiance += throughput * bg_color(0); path ends
+    // independent loads issued together: instance record, corner indices (triangles)
     const InstDev I = S.instances[hb & 0x0fffffffu];
     uint4 corners;
     corners.x = corners.y = corners.z = corners.w = 0u;
     if (kind == 1u)
         corners = S.triShade[f2u(ha.w)];
-    const float4 Lacc4 = Q.Lacc[pathId];
-    float3 Lpath = mk3(Lacc4);
+    float3 Lpath = mk3(ps.L);
 
     if (I.type == SB_INSTANCE_LIGHT)
     {
@@ -247,10 +274,11 @@ SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, u
                     const float w = mis_balance(lastBsdfPdf, lightPdf);
                     Lpath += throughput * color * -dot(rayD, ln) * w;
                 }
-                Q.Lacc[pathId] = mk4(Lpath, Lacc4.w);
+                ps.L = mk4(Lpath, ps.L.w);
+                sink.radiance_changed(ps);
             }
         }
-        return; // throughput = 0: the path ends
+        return false; // throughput = 0: the path ends
     }
 
     // ---- __closesthit__radiance, closest_hit.cu:456-606 --------------------------------------------
@@ -258,8 +286,9 @@ SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, u
     const Surface sf = (kind == 1u) ? tri_surface(S, I, corners, ha.y, ha.z, isInside, unpackLut) : curve_surface(S, I, f2u(ha.w), ha.y, ha.x, rayO, rayD, isInside);
     if (P.debug == 1u)
     {
-        Q.Lacc[pathId] = mk4((sf.normal + mk3(1.0f)) * 0.5f, 0.0f); // closest_hit.cu:504-508
-        return;
+        ps.L = mk4((sf.normal + mk3(1.0f)) * 0.5f, 0.0f); // closest_hit.cu:504-508
+        sink.radiance_changed(ps);
+        return false;
     }
     const sb_material mat = S.materials[I.material];
     uint32_t px, py, pk;
@@ -272,7 +301,7 @@ SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, u
     const BsdfSample bs = bsdf_sample(mat, sf.normal, sf.geomNormal, k1, mk4(rn.v[0], rn.v[1], rn.v[2], rn.v[3]));
     if (bs.event == EV_ABSORB)
     {
-        return; // throughput = 0 (firstEventType = eAbsorb: counted by neither AOV)
+        return false; // throughput = 0 (firstEventType = eAbsorb: counted by neither AOV)
     }
     const bool specularBounce = (bs.event & EV_SPECULAR) != 0;
     if (depth == 0u)
@@ -284,9 +313,12 @@ SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, u
             ev = 3u;
         flags = (flags & ~(3u << kFlagEventShift)) | (ev << kFlagEventShift);
         // AOV views (debug 2 / 3): remember the first event of this sample next to its radiance; nothing has
-        // been added to Lacc yet at depth 0 (NEE contributions arrive with the shadow stage)
+        // been added to L yet at depth 0 (NEE contributions arrive with the shadow ray)
         if (P.debug >= 2u)
-            Q.Lacc[pathId] = mk4(0.0f, 0.0f, 0.0f, u2f(ev));
+        {
+            ps.L = mk4(0.0f, 0.0f, 0.0f, u2f(ev));
+            sink.radiance_changed(ps);
+        }
     }
     if (bs.event & (EV_DIFFUSE | EV_GLOSSY))
     {
@@ -303,11 +335,12 @@ SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, u
             if (dot(sf.normal, ls.L) > 0.0f && -dot(ls.L, ls.normal) > 0.0 && all_nonzero(Li))
             {
                 const float lightPdf = ls.pdf * lightSelectionPdf;
-                const float3 radiance = Li * saturate(dot(sf.normal, ls.L)); // visibility applied by the shadow stage
+                const float3 radiance = Li * saturate(dot(sf.normal, ls.L)); // visibility applied by the shadow ray
                 if (isnan3(radiance) || isnanf_(lightPdf))
                 {
-                    Q.Lacc[pathId] = mk4(10000.0f, 0.0f, 0.0f, 0.0f); // quirk Q17
-                    return;
+                    ps.L = mk4(10000.0f, 0.0f, 0.0f, 0.0f); // quirk Q17
+                    sink.radiance_changed(ps);
+                    return false;
                 }
                 const bool nextEventValid = ((dot(ls.L, sf.normal) > 0.0f) != isInside) && lightPdf != 0.0f;
                 if (nextEventValid)
@@ -315,8 +348,9 @@ SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, u
                     const BsdfEval ev = bsdf_evaluate(mat, sf.normal, sf.geomNormal, k1, ls.L);
                     if (isnan3(ev.diffuse) || isnan3(ev.glossy))
                     {
-                        Q.Lacc[pathId] = mk4(10000.0f, 0.0f, 0.0f, 0.0f);
-                        return;
+                        ps.L = mk4(10000.0f, 0.0f, 0.0f, 0.0f);
+                        sink.radiance_changed(ps);
+                        return false;
                     }
                     if (ev.pdf > 0.0f)
                     {
@@ -325,10 +359,7 @@ SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, u
                         const float3 contrib = throughput * radianceOverPdf * w * (ev.diffuse + ev.glossy);
                         if (contrib.x != 0.0f || contrib.y != 0.0f || contrib.z != 0.0f)
                         {
-                            const uint32_t sslot = queue_alloc(&Q.counts[kCountShadowBase + depth]);
-                            Q.shO[sslot] = mk4(offset_ray(sf.position, sf.geomNormal), P.shadowTmin);
-                            Q.shD[sslot] = mk4(ls.L, ls.distToLight);
-                            Q.shC[sslot] = mk4(contrib, u2f(pathId));
+                            sink.shadow_ray(ps, mk4(offset_ray(sf.position, sf.geomNormal), P.shadowTmin), mk4(ls.L, ls.distToLight), contrib);
                         }
                     }
                 }
@@ -354,29 +385,74 @@ SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, u
     {
         const float p = maxcomp(throughput);
         if (rn.v[4] > p)
-            return;
+            return false;
         throughput *= 1.0f / (p + 1e-5f);
     }
     if (dot(throughput, throughput) < 1e-5f)
-        return;
+        return false;
     if (depth + 1u >= P.maxDepth)
-        return;
-    const uint32_t nslot = queue_alloc(&Q.counts[depth + 1u]);
-    Q.rayO[qo][nslot] = mk4(newOrigin, u2f(pathId));
-    Q.rayD[qo][nslot] = mk4(bs.k2, newPdf);
-    Q.thr[qo][nslot] = mk4(throughput, u2f(flags));
+        return false;
+    ps.o = newOrigin;
+    ps.d = bs.k2;
+    ps.lastBsdfPdf = newPdf;
+    ps.throughput = throughput;
+    ps.flags = flags;
+    return true;
 }
 
-// closest hit of one queued ray: triangles first, then curves (strictly closer only)
-template <bool STATS>
-SB_HD void extend_one(const FrameParams& P, const SceneDev& S, const Queues& Q, uint32_t depth, uint32_t slot, TravStats* st)
+// Wavefront form of one bounce: path state in, shadow-ray and next-segment queue records out.
+struct QueueSink
 {
-    const int qi = int(depth & 1u);
-    const float4 ro = Q.rayO[qi][slot], rd = Q.rayD[qi][slot];
+    const Queues& Q;
+    uint32_t depth;
+    SB_HD void radiance_changed(const PathState& ps) const
+    {
+        Q.Lacc[ps.pathId] = ps.L;
+    }
+    SB_HD void shadow_ray(const PathState& ps, const float4& o, const float4& d, const float3& contrib) const
+    {
+        const uint32_t sslot = queue_alloc(&Q.counts[kCountShadowBase + depth]);
+        Q.shO[sslot] = o;
+        Q.shD[sslot] = d;
+        Q.shC[sslot] = mk4(contrib, u2f(ps.pathId));
+    }
+};
+SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, uint32_t depth, uint32_t slot, const uint32_t* sobolTab,
+                     const float* unpackLut)
+{
+    const int qi = int(depth & 1u), qo = qi ^ 1;
+    const float4 ro = Q.rayO[qi][slot], rd = Q.rayD[qi][slot], th = Q.thr[qi][slot];
+    const float4 ha = Q.hitA[slot];
+    const uint32_t hb = Q.hitB[slot];
+    if ((hb >> 30) == 0u)
+        return; // miss
+    PathState ps;
+    ps.o = mk3(ro);
+    ps.d = mk3(rd);
+    ps.lastBsdfPdf = rd.w;
+    ps.throughput = mk3(th);
+    ps.flags = f2u(th.w);
+    ps.pathId = f2u(ro.w);
+    ps.L = Q.Lacc[ps.pathId];
+    QueueSink sink = { Q, depth };
+    if (shade_bounce(P, S, ps, ha, hb, depth, sobolTab, unpackLut, sink))
+    {
+        const uint32_t nslot = queue_alloc(&Q.counts[depth + 1u]);
+        Q.rayO[qo][nslot] = mk4(ps.o, u2f(ps.pathId));
+        Q.rayD[qo][nslot] = mk4(ps.d, ps.lastBsdfPdf);
+        Q.thr[qo][nslot] = mk4(ps.throughput, u2f(ps.flags));
+    }
+}
+
+// closest hit of one ray: triangles first, then curves (strictly closer only).
+// ha = t, u, v, bits(global triangle id | curve SegInfo index); hb = instance | kind << 30 (kind 0 = miss)
+template <bool STATS>
+SB_HD void trace_closest(const SceneDev& S, const float3& o, const float3& d, float tmin, float4& ha, uint32_t& hb, TravStats* st)
+{
     Ray ray;
-    ray.o = mk3(ro);
-    ray.d = mk3(rd);
-    ray.tmin = P.materialTmin;
+    ray.o = o;
+    ray.d = d;
+    ray.tmin = tmin;
     ray.tmax = 1e16f;
     const RayPrep rp = prepare_ray(ray.d);
     HitRec hit;
@@ -395,14 +471,14 @@ SB_HD void extend_one(const FrameParams& P, const SceneDev& S, const Queues& Q, 
             hit.u = span_to_segment_u(si.span, hit.u);
         }
     }
-    Q.hitA[slot] = mk4(hit.t, hit.u, hit.v, u2f(hit.kind == 1u ? hit.gid : hit.prim)); // triangles: global id; curves: SegInfo index
-    Q.hitB[slot] = hit.inst | (hit.kind << 30);
+    ha = mk4(hit.t, hit.u, hit.v, u2f(hit.kind == 1u ? hit.gid : hit.prim));
+    hb = hit.inst | (hit.kind << 30);
 }
 
+// any hit along a shadow ray (so = origin.xyz, tmin; sd = dir.xyz, tmax)
 template <bool STATS>
-SB_HD void shadow_one(const SceneDev& S, const Queues& Q, uint32_t j, TravStats* st)
+SB_HD bool trace_occluded(const SceneDev& S, const float4& so, const float4& sd, TravStats* st)
 {
-    const float4 so = Q.shO[j], sd = Q.shD[j], sc = Q.shC[j];
     Ray ray;
     ray.o = mk3(so);
     ray.tmin = so.w;
@@ -417,12 +493,72 @@ SB_HD void shadow_one(const SceneDev& S, const Queues& Q, uint32_t j, TravStats*
         occluded = traverse_bvh<1, true, STATS>(S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, st);
     if (!occluded && S.numSegNodes)
         occluded = traverse_bvh<2, true, STATS>(S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, st);
-    if (!occluded)
+    return occluded;
+}
+
+template <bool STATS>
+SB_HD void extend_one(const FrameParams& P, const SceneDev& S, const Queues& Q, uint32_t depth, uint32_t slot, TravStats* st)
+{
+    const int qi = int(depth & 1u);
+    const float4 ro = Q.rayO[qi][slot], rd = Q.rayD[qi][slot];
+    float4 ha;
+    uint32_t hb;
+    trace_closest<STATS>(S, mk3(ro), mk3(rd), P.materialTmin, ha, hb, st);
+    Q.hitA[slot] = ha;
+    Q.hitB[slot] = hb;
+}
+
+template <bool STATS>
+SB_HD void shadow_one(const SceneDev& S, const Queues& Q, uint32_t j, TravStats* st)
+{
+    const float4 so = Q.shO[j], sd = Q.shD[j], sc = Q.shC[j];
+    if (!trace_occluded<STATS>(S, so, sd, st))
     {
         const uint32_t pathId = f2u(sc.w);
         const float4 L = Q.Lacc[pathId];
         Q.Lacc[pathId] = mk4(L.x + sc.x, L.y + sc.y, L.z + sc.z, L.w);
     }
+}
+
+// ---- fused form: one whole bounce (closest hit, shading, shadow ray) with the path state in registers ------
+// Used by the single-kernel path tracer that small scenes run (kernels.cu: k_path_fused): when the whole BVH is a
+// handful of nodes, the queue traffic of the wavefront form costs more than the divergence it removes.  Same
+// functions, same order of floating-point operations per path as the wavefront form: identical images.
+struct RegisterSink
+{
+    bool shadow;
+    float4 o, d;
+    float3 contrib;
+    SB_HD void radiance_changed(const PathState&) const
+    {
+    }
+    SB_HD void shadow_ray(const PathState&, const float4& so, const float4& sd, const float3& c)
+    {
+        shadow = true;
+        o = so;
+        d = sd;
+        contrib = c;
+    }
+};
+
+// returns true when the path continues at depth + 1
+template <bool STATS>
+SB_HD bool path_bounce(const FrameParams& P, const SceneDev& S, PathState& ps, uint32_t depth, const uint32_t* sobolTab, const float* unpackLut,
+                       uint32_t& shadowRays, TravStats* stExtend, TravStats* stShadow)
+{
+    float4 ha;
+    uint32_t hb;
+    trace_closest<STATS>(S, ps.o, ps.d, P.materialTmin, ha, hb, stExtend);
+    RegisterSink sink;
+    sink.shadow = false;
+    const bool next = shade_bounce(P, S, ps, ha, hb, depth, sobolTab, unpackLut, sink);
+    if (sink.shadow)
+    {
+        ++shadowRays;
+        if (!trace_occluded<STATS>(S, sink.o, sink.d, stShadow))
+            ps.L = mk4(ps.L.x + sink.contrib.x, ps.L.y + sink.contrib.y, ps.L.z + sink.contrib.z, ps.L.w);
+    }
+    return next;
 }
 
 // tonemap / inverseTonemap, postprocessing/Utils.h:5-15

@@ -120,11 +120,12 @@ class Render:
     """oka::Render (render.h:19-56) implemented by the B200 backend (RenderType::eCompute)."""
 
     def __init__(self, device: int = 0, traversal_stats: bool = False, max_batch_paths: int = 0, stage_timers: bool = False,
-                 curve_split: int = 0):
+                 curve_split: int = 0, fused_small: bool = False):
         self._lib = _abi.load_library()
         self._ctx = None
         self._device = device
-        self._flags = (_abi.SB_CFG_TRAVERSAL_STATS if traversal_stats else 0) | (_abi.SB_CFG_STAGE_TIMERS if stage_timers else 0)
+        self._flags = ((_abi.SB_CFG_TRAVERSAL_STATS if traversal_stats else 0) | (_abi.SB_CFG_STAGE_TIMERS if stage_timers else 0)
+                       | (_abi.SB_CFG_FUSED_SMALL if fused_small else 0))
         self._max_batch = max_batch_paths
         self._curve_split = curve_split
         self.mSharedCtx: SharedContext | None = None  # noqa: N815

@@ -180,7 +180,7 @@ void emul_trace(const emul_scene* e, uint32_t n, const float* rays, uint32_t mod
 // samples [subframe, subframe + samples) into S (float4 per pixel, caller-zeroed for subframe 0) and
 // resolves `image`.  counters: [paths, radiance rays, shadow rays].
 void emul_render(const emul_scene* e, const sb_settings* st, const float* view, float fovY, uint32_t width, uint32_t height,
-                 uint32_t subframe, uint32_t samples, uint32_t chunkMax, float* Sbuf, float* image, uint64_t* counters)
+                 uint32_t subframe, uint32_t samples, uint32_t chunkMax, float* Sbuf, float* image, uint64_t* counters, uint32_t fused)
 {
     const SceneDev& S = e->S;
     FrameParams P;
@@ -245,10 +245,36 @@ void emul_render(const emul_scene* e, const sb_settings* st, const float* view, 
         P.chunk = chunk;
         P.sampleBase = st->sample_offset + (subframe + done) * P.sampleStride;
         std::fill(counts.begin(), counts.end(), 0u);
-        for (uint32_t i = 0; i < P.nPixPadded * chunk; ++i)
-            raygen_one(P, Q, i);
         counters[0] += uint64_t(width) * height * chunk;
-        for (uint32_t depth = 0; depth < P.maxDepth; ++depth)
+        if (fused)
+        {
+            // the per-lane body of k_path_fused: whole paths, state in "registers"
+            for (uint32_t i = 0; i < P.nPixPadded * chunk; ++i)
+            {
+                PathState ps;
+                if (!raygen_state(P, i, ps))
+                {
+                    Q.Lacc[i] = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+                    continue;
+                }
+                TravStats te = { 0, 0, 0, 0 }, tsh = { 0, 0, 0, 0 };
+                uint32_t depth = 0, nShadow = 0;
+                for (;;)
+                {
+                    ++counters[1];
+                    const bool next = path_bounce<false>(P, S, ps, depth, Q.sobolTab, unpackLut.data(), nShadow, &te, &tsh);
+                    if (!next)
+                        break;
+                    ++depth;
+                }
+                counters[2] += nShadow;
+                Q.Lacc[i] = ps.L;
+            }
+        }
+        if (!fused)
+            for (uint32_t i = 0; i < P.nPixPadded * chunk; ++i)
+                raygen_one(P, Q, i);
+        for (uint32_t depth = 0; depth < (fused ? 0u : P.maxDepth); ++depth)
         {
             TravStats ts = { 0, 0, 0, 0 };
             const uint32_t n = counts[depth];

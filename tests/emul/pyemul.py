@@ -26,7 +26,7 @@ def lib():
         _lib.emul_scene_info.argtypes = [C.c_void_p, C.c_void_p]
         _lib.emul_trace.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib.emul_render.argtypes = [C.c_void_p, C.POINTER(_abi.sb_settings), C.c_void_p, C.c_float, C.c_uint32, C.c_uint32,
-                                     C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+                                     C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         _lib.emul_sampler.argtypes = [C.c_uint32] + [C.c_void_p] * 7
         _lib.emul_light_sample.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         _lib.emul_curve_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -55,7 +55,7 @@ class EmulScene:
         lib().emul_trace(self._h, len(rays), rays.ctypes.data, mode, hits.ctypes.data, stats.ctypes.data)
         return (hits, stats) if with_stats else hits
 
-    def render(self, settings, width, height, samples, subframe=0, chunk_max=1, S=None):
+    def render(self, settings, width, height, samples, subframe=0, chunk_max=1, S=None, fused=False):
         st = settings.to_sb_settings() if hasattr(settings, "to_sb_settings") else settings
         cam = self._scene.getCamera(0)
         cam.updateViewMatrix()
@@ -65,7 +65,7 @@ class EmulScene:
         image = np.zeros((height, width, 4), dtype=np.float32)
         counters = np.zeros(3, dtype=np.uint64)
         lib().emul_render(self._h, C.byref(st), view.ctypes.data, C.c_float(cam.fov), width, height, subframe, samples, chunk_max,
-                          S.ctypes.data, image.ctypes.data, counters.ctypes.data)
+                          S.ctypes.data, image.ctypes.data, counters.ctypes.data, 1 if fused else 0)
         return image, S, {"paths": int(counters[0]), "radiance_rays": int(counters[1]), "shadow_rays": int(counters[2])}
 
     def close(self):

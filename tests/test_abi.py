@@ -31,7 +31,7 @@ def test_struct_sizes_match_header():
     # sizes implied by the header (checked against the ctypes/numpy mirrors)
     assert C.sizeof(_abi.sb_settings) == 16 * 4 + 16
     assert C.sizeof(_abi.sb_device_cfg) == 16
-    assert C.sizeof(_abi.sb_counters) == 14 * 8 + 16 + 8 + 6 * 8 + 6 * 8
+    assert C.sizeof(_abi.sb_counters) == 14 * 8 + 16 + 8 + 8 * 8 + 8 * 8
     assert _abi.VERTEX_DTYPE.itemsize == 32 and _abi.LIGHT_DTYPE.itemsize == 112
     assert _abi.INSTANCE_DTYPE.itemsize == 80 and _abi.MATERIAL_DTYPE.itemsize == 96
 

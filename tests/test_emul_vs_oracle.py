@@ -154,6 +154,22 @@ def test_aov_views_match_oracle(debug):
     assert rel_rmse(img_e, img_o) < 1e-5
 
 
+@pytest.mark.parametrize("debug", [0, 1, 3])
+def test_fused_path_form_equals_wavefront_form(debug):
+    # k_path_fused (small scenes) runs whole paths with the state in registers: bit-identical to the queue form
+    s, st = random_scene(seed=9)
+    st.setAs("render/pt/sppTotal", 5)
+    st.setAs("render/pt/depth", 6)
+    st.setAs("render/pt/debug", debug)
+    e = pyemul.EmulScene(s)
+    n = 1 if debug == 1 else 5
+    a, Sa, ca = e.render(st, 37, 26, n, chunk_max=2)
+    b, Sb, cb = e.render(st, 37, 26, n, chunk_max=2, fused=True)
+    assert np.array_equal(a, b) and np.array_equal(Sa, Sb)
+    if debug != 1:
+        assert ca == cb
+
+
 def test_progressive_equals_batched():
     # 6 launches one by one == one call with 6 samples in chunks of 4 (sum form is order independent)
     s, st, _ = make_cornell(32, 32, 6)

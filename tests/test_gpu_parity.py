@@ -228,3 +228,23 @@ def test_aov_views_match_oracle_on_device(gpu_render, debug, spp):
     assert sub == 9
     assert img_o[..., :3].max() > 0.0
     assert rel_rmse(img_g, img_o) <= 1e-5
+
+
+def test_fused_small_scene_kernel_is_bit_identical_to_wavefront(gpu_render):
+    # SB_CFG_FUSED_SMALL: whole paths in one kernel, state in registers (kernels.cu: k_path_fused)
+    from strelka_b200 import RenderFactory, RenderType
+
+    s, st, _ = make_cornell(50, 38, 6)
+    st.setAs("render/pt/depth", 5)
+    img_w = _render(gpu_render, s, st, 50, 38, 6)
+    cw = gpu_render.counters()
+    fused = RenderFactory.createRender(RenderType.eCompute, fused_small=True)
+    fused.init()
+    try:
+        img_f = _render(fused, s, st, 50, 38, 6)
+        cf = fused.counters()
+    finally:
+        fused.destroy()
+    assert cf["bvh_nodes_tri"] <= 64  # small enough to take the fused path
+    assert np.array_equal(img_w, img_f)
+    assert (cw["radiance_rays"], cw["shadow_rays"]) == (cf["radiance_rays"], cf["shadow_rays"])
