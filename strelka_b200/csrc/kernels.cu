@@ -172,12 +172,14 @@ __device__ __forceinline__ uint32_t fetch_slots(uint32_t* head, uint32_t n, bool
     return (need && idx < n) ? idx : 0xffffffffu;
 }
 
+#ifndef SB_EXTEND_MIN_BLOCKS
+#define SB_EXTEND_MIN_BLOCKS 8
+#endif
 template <bool STATS>
-__global__ void __launch_bounds__(kBlock) k_extend(FrameParams P, SceneDev S, Queues Q, uint32_t depth)
+__global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FrameParams P, SceneDev S, Queues Q, uint32_t depth)
 {
     const uint32_t n = Q.counts[depth];
     uint32_t* head = &Q.counts[kHeadExtendBase + depth];
-    const int qi = int(depth & 1u);
     const bool haveTris = S.numTriNodes != 0u, haveSegs = S.numSegNodes != 0u;
     TravStats st = { 0, 0, 0, 0 };
     bool active = false, exhausted = false;
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(kBlock) k_extend(FrameParams P, SceneDev S, Qu
         if (got != 0xffffffffu)
         {
             slot = got;
-            const float4 ro = Q.rayO[qi][slot], rd = Q.rayD[qi][slot];
+            const float4 ro = Q.rayO[0][slot], rd = Q.rayD[0][slot];
             ray.o = mk3(ro);
             ray.d = mk3(rd);
             ray.tmin = P.materialTmin;
@@ -259,8 +261,11 @@ __global__ void __launch_bounds__(kBlock) k_extend(FrameParams P, SceneDev S, Qu
         atomicAdd(&Q.stats->radianceRays, (unsigned long long)n);
 }
 
+#ifndef SB_SHADOW_MIN_BLOCKS
+#define SB_SHADOW_MIN_BLOCKS 8
+#endif
 template <bool STATS>
-__global__ void __launch_bounds__(kBlock) k_shadow(SceneDev S, Queues Q, uint32_t depth)
+__global__ void __launch_bounds__(kBlock, SB_SHADOW_MIN_BLOCKS) k_shadow(SceneDev S, Queues Q, uint32_t depth)
 {
     const uint32_t n = Q.counts[kCountShadowBase + depth];
     uint32_t* head = &Q.counts[kHeadShadowBase + depth];
@@ -380,7 +385,6 @@ __global__ void __launch_bounds__(kBlock, SB_SHADE_MIN_BLOCKS) k_shade(FramePara
     // allocates its queue slots at the end of the iteration
     __shared__ float4 s_shO[kBlock], s_shD[kBlock], s_shC[kBlock];
     __shared__ BlockAlloc s_alloc;
-    const int qi = int(depth & 1u), qo = qi ^ 1;
     const uint32_t n = Q.counts[depth];
     uint32_t buf = 0;
     for (uint32_t base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock, buf ^= 1u)
@@ -394,7 +398,7 @@ __global__ void __launch_bounds__(kBlock, SB_SHADE_MIN_BLOCKS) k_shade(FramePara
             const uint32_t hb = Q.hitB[slot];
             if ((hb >> 30) != 0u) // else __miss__ms: the path ends
             {
-                const float4 ro = Q.rayO[qi][slot], rd = Q.rayD[qi][slot], th = Q.thr[qi][slot];
+                const float4 ro = Q.rayO[0][slot], rd = Q.rayD[0][slot], th = Q.thr[0][slot];
                 const float4 ha = Q.hitA[slot];
                 ps.o = mk3(ro);
                 ps.d = mk3(rd);
@@ -416,9 +420,9 @@ __global__ void __launch_bounds__(kBlock, SB_SHADE_MIN_BLOCKS) k_shade(FramePara
         }
         if (next)
         {
-            Q.rayO[qo][nslot] = mk4(ps.o, u2f(ps.pathId));
-            Q.rayD[qo][nslot] = mk4(ps.d, ps.lastBsdfPdf);
-            Q.thr[qo][nslot] = mk4(ps.throughput, u2f(ps.flags));
+            Q.rayO[1][nslot] = mk4(ps.o, u2f(ps.pathId));
+            Q.rayD[1][nslot] = mk4(ps.d, ps.lastBsdfPdf);
+            Q.thr[1][nslot] = mk4(ps.throughput, u2f(ps.flags));
         }
     }
 }
@@ -535,13 +539,16 @@ __global__ void __launch_bounds__(kBlock, SB_FUSED_MIN_BLOCKS) k_path_fused(Fram
 // ---- one-ray-per-thread variants -------------------------------------------------------------------------
 // Coherent or very short traversals (primary rays; scenes whose whole BVH is a handful of nodes) finish within a
 // few steps of each other: there the dynamic-fetch machinery only adds ballots and an L2 atomic per refill.
+#ifndef SB_SIMPLE_MIN_BLOCKS
+#define SB_SIMPLE_MIN_BLOCKS 8
+#endif
 template <bool STATS>
-__global__ void __launch_bounds__(kBlock) k_extend_simple(FrameParams P, SceneDev S, Queues Q, uint32_t depth)
+__global__ void __launch_bounds__(kBlock, SB_SIMPLE_MIN_BLOCKS) k_extend_simple(FrameParams P, SceneDev S, Queues Q, uint32_t depth)
 {
     const uint32_t n = Q.counts[depth];
     TravStats st = { 0, 0, 0, 0 };
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        extend_one<STATS>(P, S, Q, depth, i, &st);
+        extend_one<STATS>(P, S, Q, 0, i, &st);
     if (STATS)
         flush_stats(Q.stats, st, false);
     if (blockIdx.x == 0 && threadIdx.x == 0)
@@ -549,7 +556,7 @@ __global__ void __launch_bounds__(kBlock) k_extend_simple(FrameParams P, SceneDe
 }
 
 template <bool STATS>
-__global__ void __launch_bounds__(kBlock) k_shadow_simple(SceneDev S, Queues Q, uint32_t depth)
+__global__ void __launch_bounds__(kBlock, SB_SIMPLE_MIN_BLOCKS) k_shadow_simple(SceneDev S, Queues Q, uint32_t depth)
 {
     const uint32_t n = Q.counts[kCountShadowBase + depth];
     TravStats st = { 0, 0, 0, 0 };
@@ -712,8 +719,9 @@ static inline unsigned grid_for(const LaunchCfg& cfg, int blocksPerSm)
     return unsigned(cfg.numSms * blocksPerSm);
 }
 
-void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const SceneDev& S, const Queues& Q, bool stats)
+void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const SceneDev& S, const Queues& Qbase, bool stats)
 {
+    const Queues& Q = Qbase;
     cudaStream_t st = cfg.stream;
     const bool tiny = (S.numTriNodes + S.numSegNodes) <= kTinyBvhNodes;
     SB_CUDA_CHECK(cudaMemsetAsync(Q.counts, 0, sizeof(uint32_t) * kNumCounts, st));
@@ -733,6 +741,14 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
     }
     for (uint32_t depth = 0; depth < P.maxDepth; ++depth)
     {
+        // the kernels read path queue 0 and write path queue 1: swap the ping-pong pointers per bounce
+        Queues Q = Qbase;
+        if (depth & 1u)
+        {
+            std::swap(Q.rayO[0], Q.rayO[1]);
+            std::swap(Q.rayD[0], Q.rayD[1]);
+            std::swap(Q.thr[0], Q.thr[1]);
+        }
         {
             ScopedStage sc(cfg, kStageExtend);
             // primary rays are coherent, and a scene of a few nodes is traversed in a few steps: one ray per thread
@@ -740,9 +756,9 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
             if (persistent)
             {
                 if (stats)
-                    k_extend<true><<<grid_for(cfg, 8), kBlock, 0, st>>>(P, S, Q, depth);
+                    k_extend<true><<<grid_for(cfg, SB_EXTEND_MIN_BLOCKS), kBlock, 0, st>>>(P, S, Q, depth);
                 else
-                    k_extend<false><<<grid_for(cfg, 8), kBlock, 0, st>>>(P, S, Q, depth);
+                    k_extend<false><<<grid_for(cfg, SB_EXTEND_MIN_BLOCKS), kBlock, 0, st>>>(P, S, Q, depth);
             }
             else
             {
@@ -762,9 +778,9 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
         if (!tiny)
         {
             if (stats)
-                k_shadow<true><<<grid_for(cfg, 8), kBlock, 0, st>>>(S, Q, depth);
+                k_shadow<true><<<grid_for(cfg, SB_SHADOW_MIN_BLOCKS), kBlock, 0, st>>>(S, Q, depth);
             else
-                k_shadow<false><<<grid_for(cfg, 8), kBlock, 0, st>>>(S, Q, depth);
+                k_shadow<false><<<grid_for(cfg, SB_SHADOW_MIN_BLOCKS), kBlock, 0, st>>>(S, Q, depth);
         }
         else
         {

@@ -62,6 +62,15 @@ struct Queues
     const uint32_t* sobolTab; // kSobolTabWords, byte-sliced Sobol tables (global memory copy)
 };
 
+// The ping-pong path queue `i` (bounce & 1 on the host).  The kernels always read queue 0 and write queue 1: the
+// launcher swaps the pointers per bounce.  Never index Q.rayO[] with a run-time value in a kernel: the compiler
+// then copies the whole parameter struct to local memory and every queue pointer costs a local load (seen in
+// the SASS of k_shade: LDC/STL prologue, LDL before each queue access).
+SB_HD float4* qsel(float4* const (&q)[2], int i)
+{
+    return i ? q[1] : q[0];
+}
+
 // Warp-aggregated slot allocation: one atomicAdd per warp instead of one per surviving lane.
 SB_HD uint32_t queue_alloc(uint32_t* counter)
 {
@@ -417,11 +426,11 @@ struct QueueSink
         Q.shC[sslot] = mk4(contrib, u2f(ps.pathId));
     }
 };
-SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, uint32_t depth, uint32_t slot, const uint32_t* sobolTab,
+SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, uint32_t depth, int qi, uint32_t slot, const uint32_t* sobolTab,
                      const float* unpackLut)
 {
-    const int qi = int(depth & 1u), qo = qi ^ 1;
-    const float4 ro = Q.rayO[qi][slot], rd = Q.rayD[qi][slot], th = Q.thr[qi][slot];
+    const int qo = qi ^ 1;
+    const float4 ro = qsel(Q.rayO, qi)[slot], rd = qsel(Q.rayD, qi)[slot], th = qsel(Q.thr, qi)[slot];
     const float4 ha = Q.hitA[slot];
     const uint32_t hb = Q.hitB[slot];
     if ((hb >> 30) == 0u)
@@ -438,9 +447,9 @@ SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, u
     if (shade_bounce(P, S, ps, ha, hb, depth, sobolTab, unpackLut, sink))
     {
         const uint32_t nslot = queue_alloc(&Q.counts[depth + 1u]);
-        Q.rayO[qo][nslot] = mk4(ps.o, u2f(ps.pathId));
-        Q.rayD[qo][nslot] = mk4(ps.d, ps.lastBsdfPdf);
-        Q.thr[qo][nslot] = mk4(ps.throughput, u2f(ps.flags));
+        qsel(Q.rayO, qo)[nslot] = mk4(ps.o, u2f(ps.pathId));
+        qsel(Q.rayD, qo)[nslot] = mk4(ps.d, ps.lastBsdfPdf);
+        qsel(Q.thr, qo)[nslot] = mk4(ps.throughput, u2f(ps.flags));
     }
 }
 
@@ -497,10 +506,9 @@ SB_HD bool trace_occluded(const SceneDev& S, const float4& so, const float4& sd,
 }
 
 template <bool STATS>
-SB_HD void extend_one(const FrameParams& P, const SceneDev& S, const Queues& Q, uint32_t depth, uint32_t slot, TravStats* st)
+SB_HD void extend_one(const FrameParams& P, const SceneDev& S, const Queues& Q, int qi, uint32_t slot, TravStats* st)
 {
-    const int qi = int(depth & 1u);
-    const float4 ro = Q.rayO[qi][slot], rd = Q.rayD[qi][slot];
+    const float4 ro = qsel(Q.rayO, qi)[slot], rd = qsel(Q.rayD, qi)[slot];
     float4 ha;
     uint32_t hb;
     trace_closest<STATS>(S, mk3(ro), mk3(rd), P.materialTmin, ha, hb, st);

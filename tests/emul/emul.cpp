@@ -280,9 +280,9 @@ void emul_render(const emul_scene* e, const sb_settings* st, const float* view, 
             const uint32_t n = counts[depth];
             counters[1] += n;
             for (uint32_t i = 0; i < n; ++i)
-                extend_one<false>(P, S, Q, depth, i, &ts);
+                extend_one<false>(P, S, Q, int(depth & 1u), i, &ts);
             for (uint32_t i = 0; i < n; ++i)
-                shade_one(P, S, Q, depth, i, (depth & 1u) ? Q.sobolTab : nullptr, (depth & 1u) ? unpackLut.data() : nullptr); // both code paths, same bits
+                shade_one(P, S, Q, depth, int(depth & 1u), i, (depth & 1u) ? Q.sobolTab : nullptr, (depth & 1u) ? unpackLut.data() : nullptr); // both code paths, same bits
             if (debugNormals)
                 break;
             const uint32_t ns = counts[kCountShadowBase + depth];
