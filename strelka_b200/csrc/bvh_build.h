@@ -31,6 +31,16 @@ struct InstDev // 128 B
     uint32_t pad2[3];
 };
 
+// Per-triangle shading record (64 B, one per global triangle id).
+struct alignas(16) TriShade
+{
+    float pos[9]; // object-space positions of the three corners
+    uint32_t normal[3]; // 10-10-10 packed, as in sb_vertex
+    uint32_t tangent[3];
+    uint32_t material; // of the owning instance
+};
+static_assert(sizeof(TriShade) == 64, "TriShade is fetched as four 16-byte loads");
+
 struct SceneDev
 {
     // uploaded scene arrays (same layouts as the host structs)
@@ -48,7 +58,7 @@ struct SceneDev
     uint64_t numCurvePoints = 0, numCurveRadii = 0;
     // world-space geometry + BVHs
     TriRec* tris = nullptr;
-    uint4* triShade = nullptr; // per GLOBAL triangle id: absolute vertex indices of its 3 corners + instance
+    TriShade* triShade = nullptr; // per GLOBAL triangle id: everything fillTriangleGeomData reads, in one 64-byte record
     SegRec* segs = nullptr;
     SegInfo* segInfo = nullptr; // per SegRec (leaf order)
     WideNode* triNodes = nullptr;
@@ -330,9 +340,10 @@ inline void build_scene_bvhs(Exec& ex, SceneDev& S, const uint32_t* instTriFirst
     {
         TriRec* unsorted = ex.alloc<TriRec>(numTris);
         Aabb* boxes = ex.alloc<Aabb>(numTris);
-        // shading-side record: one 16-byte load replaces the mesh -> index-buffer chain of the reference's
-        // fillTriangleGeomData (closest_hit.cu:369-377) so that the three vertex fetches can start at once
-        uint4* shade = ex.alloc<uint4>(numTris);
+        // shading-side record: ONE 64-byte fetch replaces the mesh -> index buffer -> 3 x vertex chain of the
+        // reference's fillTriangleGeomData (closest_hit.cu:365-421): object-space corner positions, packed
+        // normals and tangents, bit-for-bit the values the vertex buffer holds
+        TriShade* shade = ex.alloc<TriShade>(numTris);
         ex.pfor(numTris, SB_LAMBDA(size_t g) {
             const uint32_t inst = upper_owner(instTriFirst, numInst + 1, uint32_t(g));
             const InstDev& I = Sv.instances[inst];
@@ -346,11 +357,17 @@ inline void build_scene_bvhs(Exec& ex, SceneDev& S, const uint32_t* instTriFirst
                 const sb_vertex& vx = Sv.vertices[vi[k]];
                 p[k] = xform_point(I.o2w, mk3(vx.pos[0], vx.pos[1], vx.pos[2]));
             }
-            uint4 sh;
-            sh.x = vi[0];
-            sh.y = vi[1];
-            sh.z = vi[2];
-            sh.w = inst;
+            TriShade sh;
+            for (int k = 0; k < 3; ++k)
+            {
+                const sb_vertex& vx = Sv.vertices[vi[k]];
+                sh.pos[3 * k] = vx.pos[0];
+                sh.pos[3 * k + 1] = vx.pos[1];
+                sh.pos[3 * k + 2] = vx.pos[2];
+                sh.normal[k] = vx.normal;
+                sh.tangent[k] = vx.tangent;
+            }
+            sh.material = I.material;
             shade[g] = sh;
             TriRec r;
             r.v0 = mk4(p[0], u2f(t));

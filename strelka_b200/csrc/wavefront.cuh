@@ -199,15 +199,30 @@ struct Surface
 };
 
 // fillTriangleGeomData, closest_hit.cu:365-421 (quirks Q11, Q12)
-SB_HD Surface tri_surface(const SceneDev& S, const InstDev& I, const uint4& corners, float bu, float bv, bool inside, const float* lut)
+// The four 16-byte quarters of a TriShade record.
+struct TriShadeRegs
 {
-    const sb_vertex v0 = S.vertices[corners.x], v1 = S.vertices[corners.y], v2 = S.vertices[corners.z];
-    const float3 p0 = mk3(v0.pos[0], v0.pos[1], v0.pos[2]), p1 = mk3(v1.pos[0], v1.pos[1], v1.pos[2]), p2 = mk3(v2.pos[0], v2.pos[1], v2.pos[2]);
+    float4 a, b, c, d;
+};
+SB_HD TriShadeRegs load_tri_shade(const TriShade* rec)
+{
+    const float4* q = reinterpret_cast<const float4*>(rec);
+    TriShadeRegs r;
+    r.a = q[0];
+    r.b = q[1];
+    r.c = q[2];
+    r.d = q[3];
+    return r;
+}
+SB_HD Surface tri_surface(const InstDev& I, const TriShadeRegs& r, float bu, float bv, bool inside, const float* lut)
+{
+    const float3 p0 = mk3(r.a.x, r.a.y, r.a.z), p1 = mk3(r.a.w, r.b.x, r.b.y), p2 = mk3(r.b.z, r.b.w, r.c.x);
+    const uint32_t n0 = f2u(r.c.y), n1 = f2u(r.c.z), n2 = f2u(r.c.w), t0 = f2u(r.d.x), t1 = f2u(r.d.y), t2 = f2u(r.d.z);
     Surface s;
     s.position = xform_point(I.o2w, interp3(p0, p1, p2, bu, bv));
-    s.normal = normalize(xform_normal(I.w2o, interp3(unpack_normal(v0.normal, lut), unpack_normal(v1.normal, lut), unpack_normal(v2.normal, lut), bu, bv)));
+    s.normal = normalize(xform_normal(I.w2o, interp3(unpack_normal(n0, lut), unpack_normal(n1, lut), unpack_normal(n2, lut), bu, bv)));
     s.geomNormal = normalize(xform_normal(I.w2o, cross(p1 - p0, p2 - p0)));
-    s.tangent = normalize(xform_normal(I.w2o, interp3(unpack_normal(v0.tangent, lut), unpack_normal(v1.tangent, lut), unpack_normal(v2.tangent, lut), bu, bv)));
+    s.tangent = normalize(xform_normal(I.w2o, interp3(unpack_normal(t0, lut), unpack_normal(t1, lut), unpack_normal(t2, lut), bu, bv)));
     const float flip = inside ? -1.0f : 1.0f;
     s.geomNormal *= flip;
     s.normal *= flip;
@@ -254,12 +269,12 @@ SB_HD bool shade_bounce(const FrameParams& P, const SceneDev& S, PathState& ps, 
     const uint32_t kind = hb >> 30;
     if (kind == 0u)
         return false; // __miss__ms: radiance += throughput * bg_color(0); path ends
-    // independent loads issued together: instance record, corner indices (triangles)
+    // independent loads issued together: instance record, shading record of the triangle
     const InstDev I = S.instances[hb & 0x0fffffffu];
-    uint4 corners;
-    corners.x = corners.y = corners.z = corners.w = 0u;
+    TriShadeRegs tri;
+    tri.a = tri.b = tri.c = tri.d = mk4(0.0f, 0.0f, 0.0f, 0.0f);
     if (kind == 1u)
-        corners = S.triShade[f2u(ha.w)];
+        tri = load_tri_shade(&S.triShade[f2u(ha.w)]);
     float3 Lpath = mk3(ps.L);
 
     if (I.type == SB_INSTANCE_LIGHT)
@@ -292,13 +307,15 @@ SB_HD bool shade_bounce(const FrameParams& P, const SceneDev& S, PathState& ps, 
 
     // ---- __closesthit__radiance, closest_hit.cu:456-606 --------------------------------------------
     const bool isInside = (flags & kFlagInside) != 0u;
-    const Surface sf = (kind == 1u) ? tri_surface(S, I, corners, ha.y, ha.z, isInside, unpackLut) : curve_surface(S, I, f2u(ha.w), ha.y, ha.x, rayO, rayD, isInside);
+    const Surface sf = (kind == 1u) ? tri_surface(I, tri, ha.y, ha.z, isInside, unpackLut) : curve_surface(S, I, f2u(ha.w), ha.y, ha.x, rayO, rayD, isInside);
     if (P.debug == 1u)
     {
         ps.L = mk4((sf.normal + mk3(1.0f)) * 0.5f, 0.0f); // closest_hit.cu:504-508
         sink.radiance_changed(ps);
         return false;
     }
+    // (measured: fetching the material or computing the Sobol values earlier, to overlap them with the fetches
+    // above, lengthens live ranges in this register-bound kernel and costs 3-8 %)
     const sb_material mat = S.materials[I.material];
     uint32_t px, py, pk;
     path_pixel(P, pathId, px, py, pk);
