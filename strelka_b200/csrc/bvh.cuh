@@ -137,10 +137,91 @@ struct CollapseItem
     uint32_t wideIndex; // where the wide node goes
 };
 
-// Greedy surface-area collapse of the subtree under `root` into at most 8 slots, followed by the
-// octant-aware slot assignment.  `count[]` = primitives under each BVH2 node.  Returns the number of
-// inner children; nPrims = primitives referenced directly by this node's leaf slots.
-SB_HD uint32_t collapse_select(const Bvh2Node* nodes, const uint32_t* count, uint32_t numLeaves, uint32_t root,
+// Optimal BVH2 -> BVH8 cut by dynamic programming (Ylitie, Karras, Laine 2017, section 3.1).  For every BVH2
+// node m and every i in 1..7, cost[i-1] is the SAH cost of the cheapest way to represent the subtree of m by a
+// forest of at most i wide-node children (leaf slots or whole wide nodes):
+//   C(m,1) = min( A(m) * P(m) * cPrim  if P(m) <= maxLeaf,      one leaf slot
+//                 A(m) * cNode + min_k C(l,k) + C(r,8-k) )       a wide node of its own, split k : 8-k
+//   C(m,i) = min( C(m,i-1), min_k C(l,k) + C(r,i-k) )           i >= 2
+// A greedy "open the largest child" cut leaves the bottom of the tree badly filled: a balanced 32-triangle
+// subtree becomes 8 wide nodes of 4 triangles each, where 7 leaf slots of 3 + one wide node of 11 do (the first
+// build of the 2 M-triangle scene held 7 triangles per 80-byte node, and node tests are ~90 % of the traversal
+// instructions).  The table is filled bottom-up along the PLOC merge rounds (children are always older nodes).
+struct CollapseDp
+{
+    float cost[7];
+    uint8_t split[8]; // [i-1], i = 2..7: k of the best split, 0 = "same as i-1"; [7]: k of the split as a wide node
+};
+
+SB_HD float collapse_cost(const Bvh2Node* nodes, const CollapseDp* dp, uint32_t numLeaves, float cPrim, uint32_t m, int i)
+{
+    if (m < numLeaves)
+        return aabb_half_area(node_box(nodes[m])) * cPrim; // one primitive: one leaf slot, whatever the budget
+    return dp[m - numLeaves].cost[i - 1];
+}
+
+// dp entry of inner BVH2 node m (both children already done)
+SB_HD void collapse_dp_node(const Bvh2Node* nodes, const uint32_t* count, CollapseDp* dp, uint32_t numLeaves, uint32_t maxLeaf, float cNode,
+                            float cPrim, uint32_t m)
+{
+    const uint32_t l = nodes[m].left, r = nodes[m].right;
+    float cl[7], cr[7];
+    for (int i = 1; i <= 7; ++i)
+    {
+        cl[i - 1] = collapse_cost(nodes, dp, numLeaves, cPrim, l, i);
+        cr[i - 1] = collapse_cost(nodes, dp, numLeaves, cPrim, r, i);
+    }
+    const float area = aabb_half_area(node_box(nodes[m]));
+    CollapseDp e;
+    // as a wide node: 8 children to distribute
+    float best = 3.0e38f;
+    int bestK = 1;
+    for (int k = 1; k <= 7; ++k)
+    {
+        const float c = cl[k - 1] + cr[8 - k - 1];
+        if (c < best)
+        {
+            best = c;
+            bestK = k;
+        }
+    }
+    e.split[7] = uint8_t(bestK);
+    const float cInternal = area * cNode + best;
+    const float cLeaf = (count[m] <= maxLeaf) ? area * float(count[m]) * cPrim : 3.0e38f;
+    e.cost[0] = fminf(cLeaf, cInternal);
+    e.split[0] = 0;
+    for (int i = 2; i <= 7; ++i)
+    {
+        float bd = 3.0e38f;
+        int bk = 1;
+        for (int k = 1; k < i; ++k)
+        {
+            const float c = cl[k - 1] + cr[i - k - 1];
+            if (c < bd)
+            {
+                bd = c;
+                bk = k;
+            }
+        }
+        if (bd < e.cost[i - 2])
+        {
+            e.cost[i - 1] = bd;
+            e.split[i - 1] = uint8_t(bk);
+        }
+        else
+        {
+            e.cost[i - 1] = e.cost[i - 2];
+            e.split[i - 1] = 0;
+        }
+    }
+    dp[m - numLeaves] = e;
+}
+
+// The (at most 8) children of the wide node rooted at BVH2 node `root`, following the dp decisions, then the
+// octant-aware slot assignment.  `count[]` = primitives under each BVH2 node.  A child with more than maxLeaf
+// primitives becomes a wide node of its own, any other a leaf slot.  Returns the number of inner children;
+// nPrims = primitives referenced directly by this node's leaf slots.
+SB_HD uint32_t collapse_select(const Bvh2Node* nodes, const uint32_t* count, const CollapseDp* dp, uint32_t numLeaves, uint32_t root,
                                uint32_t maxLeaf, uint32_t slots[8], uint32_t& nPrims)
 {
     uint32_t cand[8];
@@ -151,37 +232,33 @@ SB_HD uint32_t collapse_select(const Bvh2Node* nodes, const uint32_t* count, uin
     }
     else
     {
-        cand[n++] = nodes[root].left;
-        cand[n++] = nodes[root].right;
-    }
-    // pass 0: open the largest node that MUST be opened (more primitives than a leaf slot holds);
-    // pass 1: with slots to spare, also split small groups so that every primitive gets its own box
-    for (int pass = 0; pass < 2; ++pass)
-    {
-        while (n < 8)
+        uint32_t stackNode[8];
+        int stackBudget[8];
+        int sp = 0;
+        const int k8 = dp[root - numLeaves].split[7];
+        stackNode[sp] = nodes[root].right;
+        stackBudget[sp++] = 8 - k8;
+        stackNode[sp] = nodes[root].left;
+        stackBudget[sp++] = k8;
+        while (sp > 0)
         {
-            int best = -1;
-            float bestArea = -1.0f;
-            for (int k = 0; k < n; ++k)
+            const uint32_t m = stackNode[--sp];
+            int budget = stackBudget[sp];
+            int k = 0;
+            if (m >= numLeaves)
             {
-                const uint32_t c = cand[k];
-                if (c < numLeaves)
-                    continue;
-                const bool big = count[c] > maxLeaf;
-                if ((pass == 0) != big)
-                    continue;
-                const float a = aabb_half_area(node_box(nodes[c]));
-                if (a > bestArea)
-                {
-                    bestArea = a;
-                    best = k;
-                }
+                while (budget > 1 && (k = dp[m - numLeaves].split[budget - 1]) == 0)
+                    --budget;
             }
-            if (best < 0)
-                break;
-            const uint32_t c = cand[best];
-            cand[best] = nodes[c].left;
-            cand[n++] = nodes[c].right;
+            if (m < numLeaves || budget == 1)
+            {
+                cand[n++] = m; // at most 8 by construction of the budgets
+                continue;
+            }
+            stackNode[sp] = nodes[m].right;
+            stackBudget[sp++] = budget - k;
+            stackNode[sp] = nodes[m].left;
+            stackBudget[sp++] = k;
         }
     }
     // octant-aware assignment: greedily give the (child, slot) pair with the largest
@@ -272,8 +349,8 @@ SB_HD uint32_t quant_exponent(float extent)
     uint32_t e = (f2u(cell) + 0x7fffffu) >> 23; // round the magnitude up to a power of two
     if (e < 1u)
         e = 1u;
-    if (e > 253u)
-        e = 253u;
+    if (e > 238u)
+        e = 238u; // wide_node_hits scales the cell size by 2^15: stay clear of the float exponent range
     // keep one cell of head-room so that ceil() of the far face can never reach 256
     if (extent * (1.0f / u2f(e << 23)) > 254.0f)
         e += 1u;

@@ -17,6 +17,8 @@
 #include "traverse.cuh"
 #include "../../include/sb/sb_api.h"
 #include <algorithm>
+#include <utility>
+#include <vector>
 
 namespace sb
 {
@@ -65,6 +67,14 @@ struct SceneDev
     WideNode* segNodes = nullptr;
     uint32_t numTris = 0, numSegs = 0, numTriNodes = 0, numSegNodes = 0;
 };
+
+// SAH constants of the BVH2 -> BVH8 cut (collapse_dp_node).  Ylitie 2017 uses node : triangle = 1 : 0.3; measured
+// here on the 2 M- and 10 M-triangle scenes 0.8-1.2 is best (a triangle test is fewer instructions than a node
+// test, but it runs with few lanes of the warp active).  With one segment per leaf slot the curve constant is moot.
+#ifndef SB_COST_TRI
+#define SB_COST_TRI 1.0f
+#endif
+constexpr float kCostNode = 1.0f, kCostTri = SB_COST_TRI, kCostSeg = 1.0f;
 
 struct WideBvh
 {
@@ -127,7 +137,7 @@ SB_HD uint32_t upper_owner(const uint32_t* a, uint32_t n, uint32_t v)
 }
 
 // Build a wide BVH over `n` boxes.  boxes are consumed (device memory, Aabb per primitive).
-inline WideBvh build_wide_bvh(Exec& ex, const Aabb* boxes, uint32_t n, uint32_t maxLeaf)
+inline WideBvh build_wide_bvh(Exec& ex, const Aabb* boxes, uint32_t n, uint32_t maxLeaf, float cNode, float cPrim)
 {
     WideBvh out;
     out.numPrims = n;
@@ -189,6 +199,7 @@ inline WideBvh build_wide_bvh(Exec& ex, const Aabb* boxes, uint32_t n, uint32_t 
         clusterA[i] = uint32_t(i);
     });
     uint32_t active = n, nextNode = n;
+    std::vector<std::pair<uint32_t, uint32_t>> rounds; // (first node, nodes) created by each PLOC round
     uint32_t* cur = clusterA;
     uint32_t* nxt = clusterB;
     while (active > 1)
@@ -237,6 +248,7 @@ inline WideBvh build_wide_bvh(Exec& ex, const Aabb* boxes, uint32_t n, uint32_t 
         const uint64_t totals = ex.read(scan + na);
         const uint32_t merges = uint32_t(totals >> 32);
         active = uint32_t(totals & 0xffffffffull);
+        rounds.emplace_back(nextNode, merges);
         nextNode += merges;
         std::swap(cur, nxt);
         if (merges == 0)
@@ -246,6 +258,14 @@ inline WideBvh build_wide_bvh(Exec& ex, const Aabb* boxes, uint32_t n, uint32_t 
     ex.free(clusterA);
     ex.free(clusterB);
     ex.free(nearest);
+
+    // ---- optimal cut table, bottom-up along the merge rounds ------------------------------------------
+    CollapseDp* dp = ex.alloc<CollapseDp>(n > 1 ? n - 1 : 1);
+    for (const auto& rd : rounds)
+    {
+        const uint32_t first = rd.first;
+        ex.pfor(rd.second, SB_LAMBDA(size_t i) { collapse_dp_node(nodes, count, dp, n, maxLeaf, cNode, cPrim, first + uint32_t(i)); });
+    }
 
     // ---- collapse to 8-wide, level by level --------------------------------------------------------
     // upper bound on wide nodes: every wide node except a degenerate root has >= 2 children and every
@@ -275,7 +295,7 @@ inline WideBvh build_wide_bvh(Exec& ex, const Aabb* boxes, uint32_t n, uint32_t 
             }
             uint32_t slots[8];
             uint32_t nPrims = 0;
-            const uint32_t nInner = collapse_select(nodes, count, n, items[i].bvh2Node, maxLeaf, slots, nPrims);
+            const uint32_t nInner = collapse_select(nodes, count, dp, n, items[i].bvh2Node, maxLeaf, slots, nPrims);
             for (int s = 0; s < 8; ++s)
                 slotBuf[i * 8 + s] = slots[s];
             flags[i] = (uint64_t(nInner) << 32) | uint64_t(nPrims);
@@ -313,6 +333,7 @@ inline WideBvh build_wide_bvh(Exec& ex, const Aabb* boxes, uint32_t n, uint32_t 
     ex.free(slotBuf);
     ex.free(flags);
     ex.free(scan);
+    ex.free(dp);
     ex.free(nodes);
     ex.free(count);
     ex.free(sorted);
@@ -380,7 +401,7 @@ inline void build_scene_bvhs(Exec& ex, SceneDev& S, const uint32_t* instTriFirst
             aabb_grow(b, p[2]);
             boxes[g] = b;
         });
-        WideBvh bvh = build_wide_bvh(ex, boxes, numTris, 3u);
+        WideBvh bvh = build_wide_bvh(ex, boxes, numTris, 3u, kCostNode, kCostTri);
         TriRec* ordered = ex.alloc<TriRec>(numTris);
         const uint32_t* order = bvh.primOrder;
         ex.pfor(numTris, SB_LAMBDA(size_t i) { ordered[i] = unsorted[order[i]]; });
@@ -417,7 +438,7 @@ inline void build_scene_bvhs(Exec& ex, SceneDev& S, const uint32_t* instTriFirst
             unsorted[g] = r;
             boxes[g] = b;
         });
-        WideBvh bvh = build_wide_bvh(ex, boxes, numSegs, 1u);
+        WideBvh bvh = build_wide_bvh(ex, boxes, numSegs, 1u, kCostNode, kCostSeg);
         SegRec* ordered = ex.alloc<SegRec>(numSegs);
         SegInfo* info = ex.alloc<SegInfo>(numSegs);
         const uint32_t* order = bvh.primOrder;
