@@ -10,6 +10,10 @@
 #include "bvh.cuh"
 #include "curve.cuh"
 
+#ifndef SB_SIMPLE_WW
+#define SB_SIMPLE_WW 1
+#endif
+
 namespace sb
 {
 
@@ -340,6 +344,25 @@ SB_HD bool trav_step_unit(Traversal& T, const WideNode* __restrict__ nodes, cons
     return trav_node<STATS>(T, nodes, ray, rp, st);
 }
 
+// "While-while" step: ONE node visit, then ALL the primitives it queued.  The lanes of a warp meet again at every
+// node test (the expensive half of the work) instead of drifting apart.
+template <int KIND, bool ANY, bool STATS>
+SB_HD bool trav_step_ww(Traversal& T, const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask, Ray& ray,
+                        const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st)
+{
+    if (T.tgroup.y == 0u && !trav_node<STATS>(T, nodes, ray, rp, st))
+        return false;
+    while (T.tgroup.y != 0u)
+    {
+        if (trav_prim<KIND, ANY, STATS>(T, prims, rayMask, ray, hit, st))
+        {
+            anyHit = true;
+            return false;
+        }
+    }
+    return true;
+}
+
 // Whole traversal of one BVH for one ray (test hooks, host emulation).  Returns true if a hit was found
 // (closest: hit updated and ray.tmax shrunk; any: first accepted hit).
 template <int KIND, bool ANY, bool STATS>
@@ -351,9 +374,29 @@ SB_HD bool traverse_bvh(const WideNode* __restrict__ nodes, const void* __restri
     const uint32_t kindBefore = hit.kind;
     const float tBefore = ray.tmax;
     bool anyHit = false;
+#if SB_SIMPLE_WW
+    // "while-while": a lane drains the primitives of the node it just visited before the warp moves on, so the
+    // lanes of a warp meet again at every node test (the expensive half) instead of drifting apart
+    for (;;)
+    {
+        if (T.tgroup.y == 0u && !trav_node<STATS>(T, nodes, ray, rp, st))
+            break;
+        while (T.tgroup.y != 0u)
+        {
+            if (trav_prim<KIND, ANY, STATS>(T, prims, rayMask, ray, hit, st))
+            {
+                anyHit = true;
+                break;
+            }
+        }
+        if (ANY && anyHit)
+            break;
+    }
+#else
     while (trav_step<KIND, ANY, STATS>(T, nodes, prims, rayMask, ray, rp, hit, anyHit, st))
     {
     }
+#endif
     if (ANY)
         return anyHit;
     return hit.kind == uint32_t(KIND) && (kindBefore != uint32_t(KIND) || ray.tmax < tBefore);
