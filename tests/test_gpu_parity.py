@@ -236,6 +236,7 @@ def test_fused_small_scene_kernel_is_bit_identical_to_wavefront(gpu_render):
 
     s, st, _ = make_cornell(50, 38, 6)
     st.setAs("render/pt/depth", 5)
+    gpu_render.reset_counters()  # the session-wide renderer has counted the earlier tests' rays
     img_w = _render(gpu_render, s, st, 50, 38, 6)
     cw = gpu_render.counters()
     fused = RenderFactory.createRender(RenderType.eCompute, fused_small=True)
