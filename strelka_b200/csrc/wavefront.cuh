@@ -21,11 +21,21 @@ namespace sb
 {
 
 constexpr uint32_t kMaxDepth = 32;
-constexpr uint32_t kCountShadowBase = 32; // counts[0..31] path queues per depth, counts[32..63] shadow queues
-constexpr uint32_t kHeadExtendBase = 64; // counts[64..95] / [96..127]: dynamic-fetch cursors of k_extend / k_shadow
-constexpr uint32_t kHeadShadowBase = 96;
-constexpr uint32_t kHeadFused = 127; // path-id dispenser of the fused small-scene kernel
-constexpr uint32_t kNumCounts = 128;
+// Device-resident queue counters (Queues::counts).  The path-queue count of bounce d+1 and the shadow-queue count
+// of bounce d share one aligned 64-bit word, so that the shade kernel reserves both with ONE atomic per warp:
+//   counts[2d] = rays queued for bounce d,  counts[2d + 3] = shadow rays cast at bounce d
+SB_HD constexpr uint32_t count_path(uint32_t depth)
+{
+    return 2u * depth;
+}
+SB_HD constexpr uint32_t count_shadow(uint32_t depth)
+{
+    return 2u * depth + 3u;
+}
+constexpr uint32_t kHeadExtendBase = 72; // dynamic-fetch cursors of k_extend / k_shadow, one per bounce
+constexpr uint32_t kHeadShadowBase = 104;
+constexpr uint32_t kHeadFused = 136; // path-id dispenser of the fused small-scene kernel
+constexpr uint32_t kNumCounts = 144;
 
 // per-path flag bits (stored in thr.w)
 constexpr uint32_t kFlagInside = 1u, kFlagSpecular = 2u;
@@ -437,7 +447,7 @@ struct QueueSink
     }
     SB_HD void shadow_ray(const PathState& ps, const float4& o, const float4& d, const float3& contrib) const
     {
-        const uint32_t sslot = queue_alloc(&Q.counts[kCountShadowBase + depth]);
+        const uint32_t sslot = queue_alloc(&Q.counts[count_shadow(depth)]);
         Q.shO[sslot] = o;
         Q.shD[sslot] = d;
         Q.shC[sslot] = mk4(contrib, u2f(ps.pathId));
@@ -463,7 +473,7 @@ SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, u
     QueueSink sink = { Q, depth };
     if (shade_bounce(P, S, ps, ha, hb, depth, sobolTab, unpackLut, sink))
     {
-        const uint32_t nslot = queue_alloc(&Q.counts[depth + 1u]);
+        const uint32_t nslot = queue_alloc(&Q.counts[count_path(depth + 1u)]);
         qsel(Q.rayO, qo)[nslot] = mk4(ps.o, u2f(ps.pathId));
         qsel(Q.rayD, qo)[nslot] = mk4(ps.d, ps.lastBsdfPdf);
         qsel(Q.thr, qo)[nslot] = mk4(ps.throughput, u2f(ps.flags));

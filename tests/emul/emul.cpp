@@ -277,7 +277,7 @@ void emul_render(const emul_scene* e, const sb_settings* st, const float* view, 
         for (uint32_t depth = 0; depth < (fused ? 0u : P.maxDepth); ++depth)
         {
             TravStats ts = { 0, 0, 0, 0 };
-            const uint32_t n = counts[depth];
+            const uint32_t n = counts[count_path(depth)];
             counters[1] += n;
             for (uint32_t i = 0; i < n; ++i)
                 extend_one<false>(P, S, Q, int(depth & 1u), i, &ts);
@@ -285,7 +285,7 @@ void emul_render(const emul_scene* e, const sb_settings* st, const float* view, 
                 shade_one(P, S, Q, depth, int(depth & 1u), i, (depth & 1u) ? Q.sobolTab : nullptr, (depth & 1u) ? unpackLut.data() : nullptr); // both code paths, same bits
             if (debugNormals)
                 break;
-            const uint32_t ns = counts[kCountShadowBase + depth];
+            const uint32_t ns = counts[count_shadow(depth)];
             counters[2] += ns;
             for (uint32_t i = 0; i < ns; ++i)
                 shadow_one<false>(S, Q, i, &ts);
