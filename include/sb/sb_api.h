@@ -204,7 +204,7 @@ typedef struct sb_buffer sb_buffer;
 typedef struct sb_device_cfg
 {
     int32_t device;          /* CUDA device ordinal (reference: cudaFree(0), OptixRender.cpp:166) */
-    uint32_t max_batch_paths; /* wavefront batch size cap, 0 = default (4 Mi paths)            */
+    uint32_t max_batch_paths; /* wavefront batch size cap, 0 = default (32 Mi paths)           */
     uint32_t flags;          /* SB_CFG_* */
     uint32_t curve_split;    /* BVH spans per cubic curve segment (tighter boxes for hair), 0 = default (8) */
 } sb_device_cfg;

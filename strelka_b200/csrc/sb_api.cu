@@ -43,7 +43,7 @@ struct sb_ctx
     std::string error;
     bool trackStats = false;
     bool fusedSmall = false;
-    uint32_t maxBatchPaths = 4u << 20;
+    uint32_t maxBatchPaths = 32u << 20;
     uint32_t curveSplit = 8;
 
     SceneDev scene;
@@ -64,6 +64,7 @@ struct sb_ctx
 
     // per-resolution state
     uint32_t width = 0, height = 0, tilesX = 0, nPixPadded = 0, batchPaths = 0;
+    size_t queuePaths = 0; // paths the queues are currently allocated for (grows on demand up to batchPaths)
     float4* S = nullptr; // accumulation: sum of T(L)
     float4* direct = nullptr; // non-accumulated launch result
     float4* aovD = nullptr; // diffuse / specular AOVs (debug views 2 / 3): count * A in xyz, count in w
@@ -123,12 +124,8 @@ void free_scene(sb_ctx* c)
     c->haveScene = false;
 }
 
-void free_frame(sb_ctx* c)
+void free_queues(sb_ctx* c)
 {
-    dev_free(c->S);
-    dev_free(c->direct);
-    dev_free(c->aovD);
-    dev_free(c->aovS);
     for (int i = 0; i < 2; ++i)
     {
         dev_free(c->Q.rayO[i]);
@@ -141,6 +138,16 @@ void free_frame(sb_ctx* c)
     dev_free(c->Q.shO);
     dev_free(c->Q.shD);
     dev_free(c->Q.shC);
+    c->queuePaths = 0;
+}
+
+void free_frame(sb_ctx* c)
+{
+    dev_free(c->S);
+    dev_free(c->direct);
+    dev_free(c->aovD);
+    dev_free(c->aovS);
+    free_queues(c);
     dev_free(c->Q.counts);
     c->width = c->height = 0;
 }
@@ -167,11 +174,28 @@ void ensure_frame(sb_ctx* c, uint32_t w, uint32_t h)
     c->nPixPadded = c->tilesX * tilesY * 32u;
     const uint32_t chunkMax = std::max<uint32_t>(1u, c->maxBatchPaths / c->nPixPadded);
     c->batchPaths = c->nPixPadded * chunkMax;
-    const size_t np = c->batchPaths;
     c->S = dev_alloc<float4>(size_t(w) * h);
     c->direct = dev_alloc<float4>(size_t(w) * h);
     c->aovD = dev_alloc<float4>(size_t(w) * h);
     c->aovS = dev_alloc<float4>(size_t(w) * h);
+    c->Q.counts = dev_alloc<uint32_t>(kNumCounts);
+    c->Q.stats = c->stats;
+    c->Q.sobolTab = c->sobolTab;
+    SB_CUDA_CHECK(cudaMemsetAsync(c->S, 0, sizeof(float4) * size_t(w) * h, c->stream));
+    SB_CUDA_CHECK(cudaMemsetAsync(c->direct, 0, sizeof(float4) * size_t(w) * h, c->stream));
+    SB_CUDA_CHECK(cudaMemsetAsync(c->aovD, 0, sizeof(float4) * size_t(w) * h, c->stream));
+    SB_CUDA_CHECK(cudaMemsetAsync(c->aovS, 0, sizeof(float4) * size_t(w) * h, c->stream));
+    c->subframe = 0; // new dimensions reset rendering (OptixRender.cpp:834)
+}
+
+// Path-state queues for `np` paths in flight: 180 bytes per path, allocated for the largest batch actually
+// rendered so far (one sample per render() call needs W*H paths; a batched render up to maxBatchPaths).
+void ensure_queues(sb_ctx* c, size_t np)
+{
+    if (np <= c->queuePaths)
+        return;
+    SB_CUDA_CHECK(cudaStreamSynchronize(c->stream)); // nothing may still be using the old queues
+    free_queues(c);
     for (int i = 0; i < 2; ++i)
     {
         c->Q.rayO[i] = dev_alloc<float4>(np);
@@ -184,14 +208,7 @@ void ensure_frame(sb_ctx* c, uint32_t w, uint32_t h)
     c->Q.shO = dev_alloc<float4>(np);
     c->Q.shD = dev_alloc<float4>(np);
     c->Q.shC = dev_alloc<float4>(np);
-    c->Q.counts = dev_alloc<uint32_t>(kNumCounts);
-    c->Q.stats = c->stats;
-    c->Q.sobolTab = c->sobolTab;
-    SB_CUDA_CHECK(cudaMemsetAsync(c->S, 0, sizeof(float4) * size_t(w) * h, c->stream));
-    SB_CUDA_CHECK(cudaMemsetAsync(c->direct, 0, sizeof(float4) * size_t(w) * h, c->stream));
-    SB_CUDA_CHECK(cudaMemsetAsync(c->aovD, 0, sizeof(float4) * size_t(w) * h, c->stream));
-    SB_CUDA_CHECK(cudaMemsetAsync(c->aovS, 0, sizeof(float4) * size_t(w) * h, c->stream));
-    c->subframe = 0; // new dimensions reset rendering (OptixRender.cpp:834)
+    c->queuePaths = np;
 }
 
 void fill_camera(const sb_ctx* c, float aspect, FrameParams& P)
@@ -299,6 +316,7 @@ void render_samples(sb_ctx* c, uint32_t samples, uint32_t mode, bool debugNormal
         if (chunk > chunkMax)
             throw std::runtime_error("render/pt/spp larger than the wavefront batch allows; raise sb_device_cfg.max_batch_paths");
         P.chunk = chunk;
+        ensure_queues(c, size_t(c->nPixPadded) * chunk);
         P.sampleBase = st.sample_offset + (c->subframe + done) * P.sampleStride;
         launch_wavefront_batch(cfg, P, c->scene, c->Q, c->trackStats);
         launch_accumulate(cfg, P, c->Q, c->S, c->direct, c->aovD, c->aovS, mode, c->subframe + done);
