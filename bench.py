@@ -318,7 +318,7 @@ def run_b200(args) -> None:
             "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "width": W, "height": H, "spp_per_gpu": SPP, "spp_total": spp_total, "depth": DEPTH,
                        "parallelism": f"sample-stride x{world} + NCCL all-reduce of S" if world > 1 else "single GPU",
-                       "l2": "explicit 256 MiB flush between timed steps; per-batch path state (~750 MB) also exceeds L2"},
+                       "l2": "explicit 256 MiB flush between timed steps; per-batch path state (32 spp x 1 Mpix x 180 B = 5.8 GB) also exceeds L2"},
             "spp_mpix_per_s": W * H * spp_total / (dev_ms * 1e-3) / 1e6,
             "rays_per_step": rays_total, "wall_ms_per_step": 1e3 * t_wall / args.steps, "bvh_build_ms": build_ms,
             "e2e": {"value": rays_total / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

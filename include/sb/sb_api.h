@@ -278,6 +278,13 @@ sb_result sb_buffer_resize(sb_buffer* buf, uint32_t width, uint32_t height);
  * getHostPointer()), the host pointer is returned through *host_ptr when non-NULL. */
 sb_result sb_buffer_map(sb_buffer* buf, void** host_ptr);
 sb_result sb_buffer_unmap(sb_buffer* buf);
+/* Non-blocking form for progressive display (the reference's map() blocks the app loop,
+ * OptixBuffer.cpp:37-43, hdRunner/main.cpp:698-708): sb_buffer_map_async enqueues the device->host copy of
+ * the buffer's current contents behind the rendering already issued and returns at once, so the next
+ * sb_render() can be issued while the copy runs; sb_buffer_map_wait blocks until THAT copy has landed in
+ * the pinned mirror (not until later work finishes) and returns the host pointer. */
+sb_result sb_buffer_map_async(sb_buffer* buf);
+sb_result sb_buffer_map_wait(sb_buffer* buf, void** host_ptr);
 void* sb_buffer_host_ptr(sb_buffer* buf);   /* Buffer::getHostPointer, buffer.h:42-45 */
 size_t sb_buffer_host_size(sb_buffer* buf); /* Buffer::getHostDataSize, buffer.h:46-49 */
 void* sb_buffer_device_ptr(sb_buffer* buf); /* OptixBuffer::getNativePtr / Render::getNativeDevicePtr */

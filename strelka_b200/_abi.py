@@ -143,7 +143,7 @@ class sb_counters(C.Structure):
 ABI_SYMBOLS = [
     "sb_settings_default", "sb_create", "sb_set_stream", "sb_destroy", "sb_last_error", "sb_set_scene", "sb_set_camera",
     "sb_set_camera_matrices", "sb_set_settings", "sb_reset_accumulation", "sb_subframe_index",
-    "sb_buffer_create", "sb_buffer_destroy", "sb_buffer_resize", "sb_buffer_map", "sb_buffer_unmap",
+    "sb_buffer_create", "sb_buffer_destroy", "sb_buffer_resize", "sb_buffer_map", "sb_buffer_unmap", "sb_buffer_map_async", "sb_buffer_map_wait",
     "sb_buffer_host_ptr", "sb_buffer_host_size", "sb_buffer_device_ptr", "sb_buffer_width", "sb_buffer_height",
     "sb_render", "sb_render_iterations", "sb_synchronize", "sb_accum_device_ptr", "sb_resolve",
     "sb_get_counters", "sb_reset_counters", "sb_test_sampler", "sb_test_light_sample", "sb_test_trace",
@@ -182,6 +182,8 @@ def load_library() -> C.CDLL:
         "sb_buffer_destroy": (None, [vp]),
         "sb_buffer_resize": (C.c_int, [vp, u32, u32]),
         "sb_buffer_map": (C.c_int, [vp, P(vp)]),
+        "sb_buffer_map_async": (C.c_int, [vp]),
+        "sb_buffer_map_wait": (C.c_int, [vp, P(vp)]),
         "sb_buffer_unmap": (C.c_int, [vp]),
         "sb_buffer_host_ptr": (vp, [vp]),
         "sb_buffer_host_size": (C.c_size_t, [vp]),

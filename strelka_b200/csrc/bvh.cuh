@@ -105,7 +105,10 @@ SB_HD uint64_t morton63(const float3& p, const float3& lo, const float3& invExte
 }
 
 // ---- PLOC (Meister & Bittner 2018): nearest neighbour inside a window of the Morton-ordered clusters
-constexpr int kPlocRadius = 16;
+#ifndef SB_PLOC_RADIUS
+#define SB_PLOC_RADIUS 16
+#endif
+constexpr int kPlocRadius = SB_PLOC_RADIUS;
 
 SB_HD uint32_t ploc_nearest(const Bvh2Node* nodes, const uint32_t* cluster, uint32_t n, uint32_t i)
 {

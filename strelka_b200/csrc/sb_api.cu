@@ -28,6 +28,8 @@ struct sb_buffer
     void* host = nullptr; // pinned mirror
     uint32_t width = 0, height = 0, format = SB_FORMAT_FLOAT4;
     size_t bytes = 0;
+    cudaEvent_t copied = nullptr; // sb_buffer_map_async: the copy into `host` has completed
+    bool copyPending = false;
 };
 
 struct sb_ctx
@@ -715,6 +717,8 @@ void sb_buffer_destroy(sb_buffer* b)
         cudaFree(b->dev);
     if (b->host)
         cudaFreeHost(b->host);
+    if (b->copied)
+        cudaEventDestroy(b->copied);
     delete b;
 }
 
@@ -727,6 +731,37 @@ sb_result sb_buffer_map(sb_buffer* b, void** hostPtr)
     {
         SB_CUDA_CHECK(cudaMemcpyAsync(b->host, b->dev, b->bytes, cudaMemcpyDeviceToHost, b->ctx->stream));
         SB_CUDA_CHECK(cudaStreamSynchronize(b->ctx->stream));
+    }
+    if (hostPtr)
+        *hostPtr = b->host;
+    SB_API_END
+}
+
+sb_result sb_buffer_map_async(sb_buffer* b)
+{
+    if (!b)
+        return SB_FAIL;
+    SB_API_BEGIN(b->ctx)
+    if (b->bytes)
+    {
+        if (!b->copied)
+            SB_CUDA_CHECK(cudaEventCreateWithFlags(&b->copied, cudaEventDisableTiming));
+        SB_CUDA_CHECK(cudaMemcpyAsync(b->host, b->dev, b->bytes, cudaMemcpyDeviceToHost, b->ctx->stream));
+        SB_CUDA_CHECK(cudaEventRecord(b->copied, b->ctx->stream));
+        b->copyPending = true;
+    }
+    SB_API_END
+}
+
+sb_result sb_buffer_map_wait(sb_buffer* b, void** hostPtr)
+{
+    if (!b)
+        return SB_FAIL;
+    SB_API_BEGIN(b->ctx)
+    if (b->copyPending)
+    {
+        SB_CUDA_CHECK(cudaEventSynchronize(b->copied));
+        b->copyPending = false;
     }
     if (hostPtr)
         *hostPtr = b->host;

@@ -79,6 +79,16 @@ class Buffer:
         _check(self._lib, self._render._ctx, self._lib.sb_buffer_map(self._h, C.byref(p)), "sb_buffer_map")
         return self.getHostPointer()
 
+    def map_async(self) -> None:
+        """Enqueue the device->host copy behind the rendering issued so far and return at once (sb_buffer_map_async)."""
+        _check(self._lib, self._render._ctx, self._lib.sb_buffer_map_async(self._h), "sb_buffer_map_async")
+
+    def map_wait(self):
+        """Wait for the copy of the last map_async() only; later render calls may still be running."""
+        p = C.c_void_p()
+        _check(self._lib, self._render._ctx, self._lib.sb_buffer_map_wait(self._h, C.byref(p)), "sb_buffer_map_wait")
+        return self.getHostPointer()
+
     def unmap(self) -> None:
         _check(self._lib, self._render._ctx, self._lib.sb_buffer_unmap(self._h), "sb_buffer_unmap")
 

@@ -249,3 +249,27 @@ def test_fused_small_scene_kernel_is_bit_identical_to_wavefront(gpu_render):
     assert cf["bvh_nodes_tri"] <= 64  # small enough to take the fused path
     assert np.array_equal(img_w, img_f)
     assert (cw["radiance_rays"], cw["shadow_rays"]) == (cf["radiance_rays"], cf["shadow_rays"])
+
+
+def test_async_map_returns_the_frame_it_was_issued_for(gpu_render):
+    # progressive display: copy of frame k overlaps the rendering of frame k+1
+    s, st, _ = make_cornell(64, 64, 8)
+    r = gpu_render
+    r.setScene(s)
+    r.setSharedContext(SharedContext(mSettingsManager=st))
+    r._last_settings = None
+    r.reset_accumulation()
+    bufs = [r.createBuffer(BufferDesc(64, 64, BufferFormat.FLOAT4)) for _ in range(2)]  # round-robin like hdRunner
+    r.render(bufs[0])
+    bufs[0].map_async()
+    r.render(bufs[1])  # issued while the copy of frame 0 may still be in flight
+    frame0 = bufs[0].map_wait().copy()
+    frame1 = bufs[1].map().copy()
+    o = pyoracle.OracleScene(s)
+    img1, acc, sub, _ = o.render(st, 64, 64, 1)
+    img2, _, _, _ = o.render(st, 64, 64, 1, subframe=sub, accum=acc)
+    assert rel_rmse(frame0, img1) <= 1e-5
+    assert rel_rmse(frame1, img2) <= 1e-5
+    assert not np.array_equal(frame0, frame1)
+    for b in bufs:
+        b.destroy()
