@@ -17,6 +17,7 @@ uint32_t h_sobol[5][32];
 
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 using namespace sb;
@@ -114,6 +115,65 @@ void emul_scene_info(const emul_scene* e, uint64_t* out /* [4] tris, segs, triNo
     out[1] = e->S.numSegs;
     out[2] = e->S.numTriNodes;
     out[3] = e->S.numSegNodes;
+}
+
+// Structure of the triangle BVH: walks every wide node from the root.
+// out[0] nodes reached, [1] inner children, [2] leaf slots, [3] primitive references, [4] primitives referenced
+// more than once or never (must be 0), [5] deepest level, [6] empty child slots
+void emul_bvh_stats(const emul_scene* e, uint64_t* out)
+{
+    for (int i = 0; i < 7; ++i)
+        out[i] = 0;
+    const SceneDev& S = e->S;
+    if (!S.numTriNodes)
+        return;
+    std::vector<uint32_t> seen(S.numTris, 0u);
+    std::vector<std::pair<uint32_t, uint32_t>> stack; // node, level
+    stack.emplace_back(0u, 1u);
+    while (!stack.empty())
+    {
+        const auto [ni, level] = stack.back();
+        stack.pop_back();
+        const WideNode& n = S.triNodes[ni];
+        out[0]++;
+        out[5] = std::max<uint64_t>(out[5], level);
+        const uint32_t imask = n.n0.w >> 24, childBase = n.n1.x, primBase = n.n1.y;
+        uint32_t innerSeen = 0;
+        for (int j = 0; j < 8; ++j)
+        {
+            const uint32_t meta = ((j < 4 ? n.n1.z : n.n1.w) >> (8 * (j & 3))) & 0xffu;
+            if (meta == 0u)
+            {
+                out[6]++;
+                continue;
+            }
+            const uint32_t bitIndex = meta & 31u, childBits = meta >> 5;
+            if (bitIndex >= 24u)
+            {
+                out[1]++;
+                // inner children are stored in slot order: rank among the inner slots below this one
+                const uint32_t rel = uint32_t(__builtin_popcount(imask & ((1u << j) - 1u)));
+                stack.emplace_back(childBase + rel, level + 1u);
+                innerSeen |= 1u << j;
+            }
+            else
+            {
+                out[2]++;
+                for (uint32_t b = 0; b < 3; ++b)
+                    if (childBits & (1u << b))
+                    {
+                        out[3]++;
+                        const uint32_t gid = f2u(S.tris[primBase + bitIndex + b].e2.w);
+                        seen[gid]++;
+                    }
+            }
+        }
+        if (innerSeen != imask)
+            out[4] += 1u << 20; // inner mask and meta bytes disagree
+    }
+    for (uint32_t c : seen)
+        if (c != 1u)
+            out[4]++;
 }
 
 // same contract as sb_test_trace; stats (optional) [nodes, tris, segs, overflow] summed over rays

@@ -25,6 +25,7 @@ def lib():
         _lib.emul_scene_destroy.argtypes = [C.c_void_p]
         _lib.emul_scene_info.argtypes = [C.c_void_p, C.c_void_p]
         _lib.emul_trace.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        _lib.emul_bvh_stats.argtypes = [C.c_void_p, C.c_void_p]
         _lib.emul_render.argtypes = [C.c_void_p, C.POINTER(_abi.sb_settings), C.c_void_p, C.c_float, C.c_uint32, C.c_uint32,
                                      C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         _lib.emul_sampler.argtypes = [C.c_uint32] + [C.c_void_p] * 7
@@ -47,6 +48,12 @@ class EmulScene:
         out = np.zeros(4, dtype=np.uint64)
         lib().emul_scene_info(self._h, out.ctypes.data)
         return {"triangles": int(out[0]), "segments": int(out[1]), "tri_nodes": int(out[2]), "seg_nodes": int(out[3])}
+
+    def bvh_stats(self):
+        out = np.zeros(7, dtype=np.uint64)
+        lib().emul_bvh_stats(self._h, out.ctypes.data)
+        keys = ("nodes", "inner_children", "leaf_slots", "prim_refs", "errors", "depth", "empty_slots")
+        return dict(zip(keys, (int(v) for v in out)))
 
     def trace(self, rays, mode=0, with_stats=False):
         rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)

@@ -66,6 +66,22 @@ def test_traversal_hits_bit_exact(scene_kind):
     assert np.array_equal(o.trace(rays, 1)["kind"], e.trace(rays, 1)["kind"])
 
 
+def test_wide_bvh_structure_and_fill():
+    # every triangle referenced exactly once, inner mask == meta bytes, and the dynamic-programming cut
+    # (bvh.cuh: collapse_dp_node) fills the 8-wide nodes: a greedy cut left this scene below 5 children per node
+    s, _ = random_scene(seed=3, n_meshes=8, n_instances=40)
+    e = pyemul.EmulScene(s)
+    info, st = e.info(), e.bvh_stats()
+    assert st["errors"] == 0
+    assert st["nodes"] == info["tri_nodes"] and st["prim_refs"] == info["triangles"]
+    assert st["inner_children"] == st["nodes"] - 1
+    assert (st["inner_children"] + st["leaf_slots"]) / st["nodes"] >= 6.0
+    assert st["inner_children"] + st["leaf_slots"] + st["empty_slots"] == 8 * st["nodes"]
+    s, _, _ = make_cornell(16, 16, 1)
+    st = pyemul.EmulScene(s).bvh_stats()
+    assert st["errors"] == 0 and st["prim_refs"] == 36 and st["nodes"] == 3
+
+
 def test_empty_and_tiny_scenes():
     from strelka_b200.scene import Scene
     from strelka_b200.scenes.common import make_quad_mesh
