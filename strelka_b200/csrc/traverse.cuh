@@ -10,6 +10,9 @@
 #include "bvh.cuh"
 #include "curve.cuh"
 
+#ifndef SB_F32X2
+#define SB_F32X2 1
+#endif
 #ifndef SB_SIMPLE_WW
 #define SB_SIMPLE_WW 1
 #endif
@@ -94,6 +97,39 @@ SB_HD float byte_to_float(uint32_t w, int j)
 #endif
 }
 
+#if defined(__CUDA_ARCH__)
+// Packed fp32 arithmetic of sm_100 (FADD2 / FFMA2: two IEEE fp32 operations per issued instruction, each
+// component rounded exactly like the scalar instruction).  The traversal kernels are bound by instruction issue,
+// and the slab tests come in natural pairs (x|y near, x|y far, z near|far).
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// bit pattern of 2^23 + byte j of w (see byte_to_float)
+__device__ __forceinline__ float byte_magic(uint32_t w, int j)
+{
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + uint32_t(j)));
+}
+#endif
+
 // Ray/child-box tests of one wide node -> 32-bit hit mask: bits 24..31 inner children in traversal
 // priority (highest first), bits 0..23 leaf primitives relative to primBase.
 SB_HD uint32_t wide_node_hits(const uint4& n0, const uint4& n1, const uint4& n2, const uint4& n3, const uint4& n4, const float3& o,
@@ -108,6 +144,10 @@ SB_HD uint32_t wide_node_hits(const uint4& n0, const uint4& n1, const uint4& n2,
     const float by = (p.y - o.y) * idir.y;
     const float bz = (p.z - o.z) * idir.z;
     uint32_t hitmask = 0;
+#if defined(__CUDA_ARCH__) && SB_F32X2
+    const unsigned long long Axy = f2_pack(ax, ay), Bxy = f2_pack(bx, by), Azz = f2_pack(az, az), Bzz = f2_pack(bz, bz);
+    const unsigned long long kMagic = f2_pack(-8388608.0f, -8388608.0f);
+#endif
 #pragma unroll
     for (int half = 0; half < 2; ++half)
     {
@@ -124,12 +164,19 @@ SB_HD uint32_t wide_node_hits(const uint4& n0, const uint4& n1, const uint4& n2,
 #pragma unroll
         for (int j = 0; j < 4; ++j)
         {
+#if defined(__CUDA_ARCH__) && SB_F32X2
+            float t0x, t0y, t0z, t1x, t1y, t1z;
+            f2_unpack(f2_fma(f2_add(f2_pack(byte_magic(nearx, j), byte_magic(neary, j)), kMagic), Axy, Bxy), t0x, t0y);
+            f2_unpack(f2_fma(f2_add(f2_pack(byte_magic(farx, j), byte_magic(fary, j)), kMagic), Axy, Bxy), t1x, t1y);
+            f2_unpack(f2_fma(f2_add(f2_pack(byte_magic(nearz, j), byte_magic(farz, j)), kMagic), Azz, Bzz), t0z, t1z);
+#else
             const float t0x = fmaf(byte_to_float(nearx, j), ax, bx);
             const float t0y = fmaf(byte_to_float(neary, j), ay, by);
             const float t0z = fmaf(byte_to_float(nearz, j), az, bz);
             const float t1x = fmaf(byte_to_float(farx, j), ax, bx);
             const float t1y = fmaf(byte_to_float(fary, j), ay, by);
             const float t1z = fmaf(byte_to_float(farz, j), az, bz);
+#endif
             const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
             // conservative far plane: the 1 + 2*gamma(3) factor of Ize 2013 (the CPU oracle's slab test uses it
             // too).  It must scale the RESULT: pre-scaled plane coefficients lose it to cancellation.
