@@ -87,7 +87,9 @@ SB_HD uint32_t byte_of(uint32_t w, int j)
 // one FFMA per plane and no FADD.  The folded constant is only accurate to 2^-9 of a quantisation cell, so the
 // planes need that much slack; rays leaving an axis-aligned wall then enter the flat boxes of its co-planar
 // neighbours: +38 % triangle tests on the Cornell box (-3 % Mrays/s), for -4 % traversal time on the 2 M-triangle
-// scene.  Kept exact.)
+// scene.  Kept exact.  Also measured: uncompressed float child boxes (224-byte nodes) for scenes of <= 64 nodes --
+// no conversions at all, but the 9 extra vector loads and the pointer selects cost as much ALU work as the 48 PRMTs
+// they remove: +2 % on the Cornell box.)
 SB_HD float byte_to_float(uint32_t w, int j)
 {
 #if defined(__CUDA_ARCH__)
