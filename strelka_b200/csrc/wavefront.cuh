@@ -294,7 +294,7 @@ SB_HD bool shade_bounce(const FrameParams& P, const SceneDev& S, PathState& ps, 
         // __closesthit__light, OptixRender.cu:315-341 (quirks Q5, Q19)
         if (I.light < S.numLights)
         {
-            const sb_light l = S.lights[I.light];
+            const sb_light& l = S.lights[I.light];
             const float3 hitPoint = rayO + ha.x * rayD;
             const float3 ln = light_normal(l, hitPoint);
             const float3 color = mk3(l.color[0], l.color[1], l.color[2]);
