@@ -44,6 +44,7 @@ def run(name, spp):
         c = r.counters()
         if mode == "timed":
             rays = c["radiance_rays"] + c["shadow_rays"]
+            wall = max(sum(c["stage_ms"]) * 1e-3, 1e-9)  # device time of the kernels (the host wall clock also sees queue growth)
             out.update(build_ms=round(c0["build_ms"], 1), tris=c["num_triangles"], segs=c["num_segments"], nodes_tri=c["bvh_nodes_tri"],
                        nodes_seg=c["bvh_nodes_curve"], mrays_s=round(rays / wall / 1e6, 1), spp_mpix_s=round(w * h * spp / wall / 1e6, 2),
                        wall_s=round(wall, 3), rays_per_path=round(rays / c["paths"], 2),
