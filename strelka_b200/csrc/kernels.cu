@@ -555,6 +555,20 @@ __global__ void __launch_bounds__(kBlock, SB_FUSED_MIN_BLOCKS) k_path_fused(Fram
 // ---- one-ray-per-thread variants -------------------------------------------------------------------------
 // Coherent or very short traversals (primary rays; scenes whose whole BVH is a handful of nodes) finish within a
 // few steps of each other: there the dynamic-fetch machinery only adds ballots and an L2 atomic per refill.
+// Grid sizes in CTAs per SM.  The grid-stride kernels assign slots to CTAs statically, so with exactly one resident
+// wave (8 CTAs/SM) the slowest CTA sets the kernel time; more, smaller CTA workloads let the block scheduler balance
+// them.  Measured on C2: one-ray-per-thread traversal kernels 16 -> 256 CTAs/SM: -8 %; shade 8 -> 128: -4 % (each
+// shade CTA first fills 16 KB of shared-memory tables, so more than that costs again); 1024+: launch overhead shows.
+// The persistent kernels balance themselves through the dynamic ray fetch and stay at one wave.
+#ifndef SB_RAYGEN_GRID
+#define SB_RAYGEN_GRID 8
+#endif
+#ifndef SB_SHADE_GRID
+#define SB_SHADE_GRID 128
+#endif
+#ifndef SB_SIMPLE_GRID
+#define SB_SIMPLE_GRID 256
+#endif
 #ifndef SB_SIMPLE_MIN_BLOCKS
 #define SB_SIMPLE_MIN_BLOCKS 8
 #endif
@@ -753,7 +767,7 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
     }
     {
         ScopedStage sc(cfg, kStageRaygen);
-        k_raygen<<<grid_for(cfg, 8), kBlock, 0, st>>>(P, Q);
+        k_raygen<<<grid_for(cfg, SB_RAYGEN_GRID), kBlock, 0, st>>>(P, Q);
     }
     for (uint32_t depth = 0; depth < P.maxDepth; ++depth)
     {
@@ -779,14 +793,14 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
             else
             {
                 if (stats)
-                    k_extend_simple<true><<<grid_for(cfg, 16), kBlock, 0, st>>>(P, S, Q, depth);
+                    k_extend_simple<true><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
                 else
-                    k_extend_simple<false><<<grid_for(cfg, 16), kBlock, 0, st>>>(P, S, Q, depth);
+                    k_extend_simple<false><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
             }
         }
         {
             ScopedStage sc(cfg, kStageShade);
-            k_shade<<<grid_for(cfg, 8), kBlock, 0, st>>>(P, S, Q, depth);
+            k_shade<<<grid_for(cfg, SB_SHADE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
         }
         if (P.debug == 1u)
             break; // debug normals: only the first hit is shaded (OptixRender.cu:151-152)
@@ -801,9 +815,9 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
         else
         {
             if (stats)
-                k_shadow_simple<true><<<grid_for(cfg, 16), kBlock, 0, st>>>(S, Q, depth);
+                k_shadow_simple<true><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(S, Q, depth);
             else
-                k_shadow_simple<false><<<grid_for(cfg, 16), kBlock, 0, st>>>(S, Q, depth);
+                k_shadow_simple<false><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(S, Q, depth);
         }
     }
     SB_CUDA_CHECK(cudaGetLastError());
