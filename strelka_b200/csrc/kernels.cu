@@ -560,6 +560,9 @@ __global__ void __launch_bounds__(kBlock, SB_FUSED_MIN_BLOCKS) k_path_fused(Fram
 // them.  Measured on C2: one-ray-per-thread traversal kernels 16 -> 256 CTAs/SM: -8 %; shade 8 -> 128: -4 % (each
 // shade CTA first fills 16 KB of shared-memory tables, so more than that costs again); 1024+: launch overhead shows.
 // The persistent kernels balance themselves through the dynamic ray fetch and stay at one wave.
+#ifndef SB_ACC_GRID
+#define SB_ACC_GRID 32
+#endif
 #ifndef SB_RAYGEN_GRID
 #define SB_RAYGEN_GRID 8
 #endif
@@ -827,7 +830,7 @@ void launch_accumulate(const LaunchCfg& cfg, const FrameParams& P, const Queues&
                        uint32_t mode, uint32_t subframe)
 {
     ScopedStage sc(cfg, kStageAccumulate);
-    k_accumulate<<<grid_for(cfg, 4), 256, 0, cfg.stream>>>(P, Q, S, direct, aovD, aovS, mode, subframe);
+    k_accumulate<<<grid_for(cfg, SB_ACC_GRID), 256, 0, cfg.stream>>>(P, Q, S, direct, aovD, aovS, mode, subframe);
     SB_CUDA_CHECK(cudaGetLastError());
 }
 
