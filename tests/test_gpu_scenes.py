@@ -95,3 +95,32 @@ def test_full_size_c3_properties(gpu_render):
     b = _render(gpu_render, s, st, 480, 270, 4)
     st.setAs("render/b200/sampleOffset", 0)
     assert abs(a[..., :3].mean() / b[..., :3].mean() - 1.0) < 0.05
+
+
+def test_full_size_c3_closest_and_any_hit_agree(gpu_render):
+    """Size-independent traversal check on the full 2 M-triangle BVH: for every ray, the any-hit query must find
+    an occluder exactly when its range reaches the closest hit -- two different kernels walking the same tree."""
+    from strelka_b200 import _abi
+    from util import random_rays
+
+    s, st, _ = make_kitchen(64, 36, 1)
+    gpu_render.setScene(s)
+    rays = random_rays(200_000, seed=9, extent=3.0)
+    rays[:, 1] = np.abs(rays[:, 1]) * 0.8 + 0.05  # origins inside the room
+    closest = gpu_render.test_trace(rays, 0)
+    hit = closest["kind"] == 1
+    inst_type = np.array([i[1] for i in s.instances])
+    solid = hit & (inst_type[np.minimum(closest["instance"], len(inst_type) - 1)] != _abi.SB_INSTANCE_LIGHT)  # lights are invisible to shadow rays
+    assert solid.sum() > 50_000
+    t = closest["t"]
+    beyond, before = rays.copy(), rays.copy()
+    # margins: at grazing incidence the float t of the triangle test is off by up to ~1 % of the true distance
+    # (measured: 7 of 133 k rays at a 0.1 % margin, 2 at 1 %, none at 50 %), so the ranges keep clear of t
+    beyond[:, 7] = np.where(solid, t * np.float32(2.0), np.float32(1e16))
+    before[:, 7] = np.where(solid, t * np.float32(0.9), np.float32(1e-6))
+    occ_beyond = gpu_render.test_trace(beyond, 1)["kind"] != 0
+    occ_before = gpu_render.test_trace(before, 1)["kind"] != 0
+    assert occ_beyond[solid].all()
+    assert occ_before[solid].mean() < 1e-4
+    missed = closest["kind"] == 0
+    assert not occ_beyond[missed].any()
