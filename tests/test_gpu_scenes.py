@@ -124,3 +124,31 @@ def test_full_size_c3_closest_and_any_hit_agree(gpu_render):
     assert occ_before[solid].mean() < 1e-4
     missed = closest["kind"] == 0
     assert not occ_beyond[missed].any()
+
+
+def test_full_size_c2_batched_equals_progressive_and_sharded(gpu_render):
+    """BASELINE configs[1] at full resolution: 40 samples rendered as one call (wavefront batches of 32 + 8 samples,
+    queues grown on demand) == 40 render() calls bit for bit, and two sample-stride shards sum to the same S."""
+    from strelka_b200.scenes import make_cornell
+
+    s, st, (w, h) = make_cornell(1024, 1024, 40)
+    r = gpu_render
+    a = _render(r, s, st, w, h, 40)
+    assert r.getSharedContext().mSubframeIndex == 40
+    r.reset_accumulation()
+    buf = r.createBuffer(BufferDesc(w, h, BufferFormat.FLOAT4))
+    for _ in range(40):
+        r.render(buf)
+    b = buf.map().copy()
+    assert np.array_equal(a, b)
+    whole = r.accum_tensor().cpu().numpy().copy()
+    parts = []
+    for off in (0, 1):
+        st.setAs("render/b200/sampleOffset", off)
+        st.setAs("render/b200/sampleStride", 2)
+        _render(r, s, st, w, h, 20)
+        parts.append(r.accum_tensor().cpu().numpy().copy())
+    st.setAs("render/b200/sampleOffset", 0)
+    st.setAs("render/b200/sampleStride", 1)
+    np.testing.assert_allclose(parts[0] + parts[1], whole, rtol=2e-6, atol=1e-9)
+    buf.destroy()
