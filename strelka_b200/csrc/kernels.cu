@@ -1,9 +1,12 @@
 // Hand-written sm_100a kernels of the wavefront path tracer + their launchers.
 //
-// Launch geometry (B200: 148 SMs): every stage is a grid-stride kernel over a device-resident queue
-// count, launched with a fixed grid of 148 * kBlocksPerSm blocks so that (a) no host round-trip is
-// needed to size a launch, (b) the grid is always a whole number of waves.  Blocks are 128 threads:
-// traversal is latency-bound pointer chasing, so occupancy (registers) matters more than block size.
+// Launch geometry (B200: 148 SMs): every stage is a grid-stride kernel over a device-resident queue count,
+// launched with a fixed grid of 148 * k blocks so that (a) no host round-trip is needed to size a launch, (b) the
+// grid is always a whole number of SM-loads.  k = 8 (one resident wave at 64 registers) for the persistent
+// traversal kernels, which balance themselves through their dynamic ray fetch; k = 128-256 for the statically
+// partitioned kernels, where the block scheduler does the balancing (SB_*_GRID below).  Blocks are 128 threads:
+// traversal and shading are bound by instruction issue and latency, so registers (occupancy) matter more than
+// block size.
 #include <cstdint>
 namespace sb
 {

@@ -63,7 +63,7 @@ struct Queues
     float4* thr[2]; // throughput.xyz, bits(flags)
     float4* hitA; // t, u, v, bits(global triangle id | curve SegInfo index)
     uint32_t* hitB; // instance | kind << 30
-    float4* Lacc; // per pathId: radiance accumulated along the path (w unused)
+    float4* Lacc; // per pathId: radiance accumulated along the path; w = bits(first bsdf event), for the AOV views
     float4* shO; // origin.xyz, tmin
     float4* shD; // dir.xyz, tmax
     float4* shC; // contribution.xyz, bits(pathId)
