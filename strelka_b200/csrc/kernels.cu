@@ -178,12 +178,12 @@ __device__ __forceinline__ uint32_t fetch_slots(uint32_t* head, uint32_t n, bool
 #ifndef SB_EXTEND_MIN_BLOCKS
 #define SB_EXTEND_MIN_BLOCKS 8
 #endif
-template <bool STATS>
+template <bool STATS, bool CURVES>
 __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FrameParams P, SceneDev S, Queues Q, uint32_t depth)
 {
     const uint32_t n = Q.counts[count_path(depth)];
     uint32_t* head = &Q.counts[kHeadExtendBase + depth];
-    const bool haveTris = S.numTriNodes != 0u, haveSegs = S.numSegNodes != 0u;
+    const bool haveTris = S.numTriNodes != 0u, haveSegs = CURVES && S.numSegNodes != 0u; // CURVES = false: no curve code at all
     TravStats st = { 0, 0, 0, 0 };
     bool active = false, exhausted = false;
     uint32_t slot = 0;
@@ -227,17 +227,17 @@ __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FramePa
 #if SB_EXTEND_UNIT_STEP == 2
                 if (phase == 0)
                     more = trav_step_ww<1, false, STATS>(T, S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
-                else if (phase == 1)
+                else if (CURVES && phase == 1)
                     more = trav_step_ww<2, false, STATS>(T, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
 #elif SB_EXTEND_UNIT_STEP
                 if (phase == 0)
                     more = trav_step_unit<1, false, STATS>(T, S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
-                else if (phase == 1)
+                else if (CURVES && phase == 1)
                     more = trav_step_unit<2, false, STATS>(T, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
 #else
                 if (phase == 0)
                     more = trav_step<1, false, STATS>(T, S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
-                else if (phase == 1)
+                else if (CURVES && phase == 1)
                     more = trav_step<2, false, STATS>(T, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
 #endif
                 if (!more)
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FramePa
                     }
                     else
                     {
-                        if (hit.kind == 2u)
+                        if (CURVES && hit.kind == 2u)
                         {
                             const SegInfo si = S.segInfo[hit.prim];
                             hit.inst = si.inst;
@@ -275,12 +275,12 @@ __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FramePa
 #ifndef SB_SHADOW_MIN_BLOCKS
 #define SB_SHADOW_MIN_BLOCKS 8
 #endif
-template <bool STATS>
+template <bool STATS, bool CURVES>
 __global__ void __launch_bounds__(kBlock, SB_SHADOW_MIN_BLOCKS) k_shadow(SceneDev S, Queues Q, uint32_t depth)
 {
     const uint32_t n = Q.counts[count_shadow(depth)];
     uint32_t* head = &Q.counts[kHeadShadowBase + depth];
-    const bool haveTris = S.numTriNodes != 0u, haveSegs = S.numSegNodes != 0u;
+    const bool haveTris = S.numTriNodes != 0u, haveSegs = CURVES && S.numSegNodes != 0u; // CURVES = false: no curve code at all
     TravStats st = { 0, 0, 0, 0 };
     bool active = false, exhausted = false;
     uint32_t slot = 0;
@@ -320,17 +320,17 @@ __global__ void __launch_bounds__(kBlock, SB_SHADOW_MIN_BLOCKS) k_shadow(SceneDe
 #if SB_SHADOW_UNIT_STEP == 2
                 if (phase == 0)
                     more = trav_step_ww<1, true, STATS>(T, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st);
-                else if (phase == 1)
+                else if (CURVES && phase == 1)
                     more = trav_step_ww<2, true, STATS>(T, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st);
 #elif SB_SHADOW_UNIT_STEP
                 if (phase == 0)
                     more = trav_step_unit<1, true, STATS>(T, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st);
-                else if (phase == 1)
+                else if (CURVES && phase == 1)
                     more = trav_step_unit<2, true, STATS>(T, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st);
 #else
                 if (phase == 0)
                     more = trav_step<1, true, STATS>(T, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st);
-                else if (phase == 1)
+                else if (CURVES && phase == 1)
                     more = trav_step<2, true, STATS>(T, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st);
 #endif
                 if (!more)
@@ -578,26 +578,26 @@ __global__ void __launch_bounds__(kBlock, SB_FUSED_MIN_BLOCKS) k_path_fused(Fram
 #ifndef SB_SIMPLE_MIN_BLOCKS
 #define SB_SIMPLE_MIN_BLOCKS 8
 #endif
-template <bool STATS>
+template <bool STATS, bool CURVES>
 __global__ void __launch_bounds__(kBlock, SB_SIMPLE_MIN_BLOCKS) k_extend_simple(FrameParams P, SceneDev S, Queues Q, uint32_t depth)
 {
     const uint32_t n = Q.counts[count_path(depth)];
     TravStats st = { 0, 0, 0, 0 };
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        extend_one<STATS>(P, S, Q, 0, i, &st);
+        extend_one<STATS, CURVES>(P, S, Q, 0, i, &st);
     if (STATS)
         flush_stats(Q.stats, st, false);
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(&Q.stats->radianceRays, (unsigned long long)n);
 }
 
-template <bool STATS>
+template <bool STATS, bool CURVES>
 __global__ void __launch_bounds__(kBlock, SB_SIMPLE_MIN_BLOCKS) k_shadow_simple(SceneDev S, Queues Q, uint32_t depth)
 {
     const uint32_t n = Q.counts[count_shadow(depth)];
     TravStats st = { 0, 0, 0, 0 };
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        shadow_one<STATS>(S, Q, i, &st);
+        shadow_one<STATS, CURVES>(S, Q, i, &st);
     if (STATS)
         flush_stats(Q.stats, st, true);
     if (blockIdx.x == 0 && threadIdx.x == 0)
@@ -760,6 +760,7 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
     const Queues& Q = Qbase;
     cudaStream_t st = cfg.stream;
     const bool tiny = (S.numTriNodes + S.numSegNodes) <= kTinyBvhNodes;
+    const bool curves = S.numSegNodes != 0u;
     SB_CUDA_CHECK(cudaMemsetAsync(Q.counts, 0, sizeof(uint32_t) * kNumCounts, st));
     if (tiny && cfg.fusedSmall)
     {
@@ -791,17 +792,39 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
             const bool persistent = !tiny && depth > 0;
             if (persistent)
             {
-                if (stats)
-                    k_extend<true><<<grid_for(cfg, SB_EXTEND_MIN_BLOCKS), kBlock, 0, st>>>(P, S, Q, depth);
+                // scenes without curves run kernels compiled without the curve phase (the traversal loop is very
+                // sensitive to its size and shape)
+                if (curves)
+                {
+                    if (stats)
+                        k_extend<true, true><<<grid_for(cfg, SB_EXTEND_MIN_BLOCKS), kBlock, 0, st>>>(P, S, Q, depth);
+                    else
+                        k_extend<false, true><<<grid_for(cfg, SB_EXTEND_MIN_BLOCKS), kBlock, 0, st>>>(P, S, Q, depth);
+                }
                 else
-                    k_extend<false><<<grid_for(cfg, SB_EXTEND_MIN_BLOCKS), kBlock, 0, st>>>(P, S, Q, depth);
+                {
+                    if (stats)
+                        k_extend<true, false><<<grid_for(cfg, SB_EXTEND_MIN_BLOCKS), kBlock, 0, st>>>(P, S, Q, depth);
+                    else
+                        k_extend<false, false><<<grid_for(cfg, SB_EXTEND_MIN_BLOCKS), kBlock, 0, st>>>(P, S, Q, depth);
+                }
             }
             else
             {
-                if (stats)
-                    k_extend_simple<true><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
+                if (curves)
+                {
+                    if (stats)
+                        k_extend_simple<true, true><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
+                    else
+                        k_extend_simple<false, true><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
+                }
                 else
-                    k_extend_simple<false><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
+                {
+                    if (stats)
+                        k_extend_simple<true, false><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
+                    else
+                        k_extend_simple<false, false><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
+                }
             }
         }
         {
@@ -813,17 +836,37 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
         ScopedStage sc(cfg, kStageShadow);
         if (!tiny)
         {
-            if (stats)
-                k_shadow<true><<<grid_for(cfg, SB_SHADOW_MIN_BLOCKS), kBlock, 0, st>>>(S, Q, depth);
+            if (curves)
+            {
+                if (stats)
+                    k_shadow<true, true><<<grid_for(cfg, SB_SHADOW_MIN_BLOCKS), kBlock, 0, st>>>(S, Q, depth);
+                else
+                    k_shadow<false, true><<<grid_for(cfg, SB_SHADOW_MIN_BLOCKS), kBlock, 0, st>>>(S, Q, depth);
+            }
             else
-                k_shadow<false><<<grid_for(cfg, SB_SHADOW_MIN_BLOCKS), kBlock, 0, st>>>(S, Q, depth);
+            {
+                if (stats)
+                    k_shadow<true, false><<<grid_for(cfg, SB_SHADOW_MIN_BLOCKS), kBlock, 0, st>>>(S, Q, depth);
+                else
+                    k_shadow<false, false><<<grid_for(cfg, SB_SHADOW_MIN_BLOCKS), kBlock, 0, st>>>(S, Q, depth);
+            }
         }
         else
         {
-            if (stats)
-                k_shadow_simple<true><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(S, Q, depth);
+            if (curves)
+            {
+                if (stats)
+                    k_shadow_simple<true, true><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(S, Q, depth);
+                else
+                    k_shadow_simple<false, true><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(S, Q, depth);
+            }
             else
-                k_shadow_simple<false><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(S, Q, depth);
+            {
+                if (stats)
+                    k_shadow_simple<true, false><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(S, Q, depth);
+                else
+                    k_shadow_simple<false, false><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(S, Q, depth);
+            }
         }
     }
     SB_CUDA_CHECK(cudaGetLastError());

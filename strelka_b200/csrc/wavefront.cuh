@@ -484,7 +484,8 @@ SB_HD void shade_one(const FrameParams& P, const SceneDev& S, const Queues& Q, u
 
 // closest hit of one ray: triangles first, then curves (strictly closer only).
 // ha = t, u, v, bits(global triangle id | curve SegInfo index); hb = instance | kind << 30 (kind 0 = miss)
-template <bool STATS>
+// CURVES = false compiles the curve BVH out (scenes without curves: the traversal kernels are sensitive to code size)
+template <bool STATS, bool CURVES = true>
 SB_HD void trace_closest(const SceneDev& S, const float3& o, const float3& d, float tmin, float4& ha, uint32_t& hb, TravStats* st)
 {
     Ray ray;
@@ -500,7 +501,7 @@ SB_HD void trace_closest(const SceneDev& S, const float3& o, const float3& d, fl
     hit.gid = 0xffffffffu;
     if (S.numTriNodes)
         traverse_bvh<1, false, STATS>(S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, st);
-    if (S.numSegNodes)
+    if (CURVES && S.numSegNodes)
     {
         if (traverse_bvh<2, false, STATS>(S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, st))
         {
@@ -514,7 +515,7 @@ SB_HD void trace_closest(const SceneDev& S, const float3& o, const float3& d, fl
 }
 
 // any hit along a shadow ray (so = origin.xyz, tmin; sd = dir.xyz, tmax)
-template <bool STATS>
+template <bool STATS, bool CURVES = true>
 SB_HD bool trace_occluded(const SceneDev& S, const float4& so, const float4& sd, TravStats* st)
 {
     Ray ray;
@@ -529,27 +530,27 @@ SB_HD bool trace_occluded(const SceneDev& S, const float4& so, const float4& sd,
     bool occluded = false;
     if (S.numTriNodes)
         occluded = traverse_bvh<1, true, STATS>(S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, st);
-    if (!occluded && S.numSegNodes)
+    if (CURVES && !occluded && S.numSegNodes)
         occluded = traverse_bvh<2, true, STATS>(S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, st);
     return occluded;
 }
 
-template <bool STATS>
+template <bool STATS, bool CURVES = true>
 SB_HD void extend_one(const FrameParams& P, const SceneDev& S, const Queues& Q, int qi, uint32_t slot, TravStats* st)
 {
     const float4 ro = qsel(Q.rayO, qi)[slot], rd = qsel(Q.rayD, qi)[slot];
     float4 ha;
     uint32_t hb;
-    trace_closest<STATS>(S, mk3(ro), mk3(rd), P.materialTmin, ha, hb, st);
+    trace_closest<STATS, CURVES>(S, mk3(ro), mk3(rd), P.materialTmin, ha, hb, st);
     Q.hitA[slot] = ha;
     Q.hitB[slot] = hb;
 }
 
-template <bool STATS>
+template <bool STATS, bool CURVES = true>
 SB_HD void shadow_one(const SceneDev& S, const Queues& Q, uint32_t j, TravStats* st)
 {
     const float4 so = Q.shO[j], sd = Q.shD[j], sc = Q.shC[j];
-    if (!trace_occluded<STATS>(S, so, sd, st))
+    if (!trace_occluded<STATS, CURVES>(S, so, sd, st))
     {
         const uint32_t pathId = f2u(sc.w);
         const float4 L = Q.Lacc[pathId];
