@@ -203,6 +203,8 @@ SB_HD BsdfEval ups_eval_core(const UpsLobes& L, const UpsWeights& w, const float
 
 // mdlcode_evaluate stand-in.  n = shading normal, ng = geometric normal (both already flipped by
 // `inside`, closest_hit.cu:405-406), k1 = -ray_dir, k2 = direction to the light.
+// PREVIEW = false compiles the UsdPreviewSurface model out (scenes whose materials are all diffuse)
+template <bool PREVIEW = true>
 SB_HD BsdfEval bsdf_evaluate(const sb_material& m, const float3& n, const float3& ng, const float3& k1, const float3& k2)
 {
     BsdfEval e;
@@ -215,7 +217,7 @@ SB_HD BsdfEval bsdf_evaluate(const sb_material& m, const float3& n, const float3
     {
         return e;
     }
-    if (m.model == SB_MATERIAL_USD_PREVIEW_SURFACE)
+    if (PREVIEW && m.model == SB_MATERIAL_USD_PREVIEW_SURFACE)
     {
         const UpsLobes L = ups_init(m);
         const UpsWeights w = ups_weights(L, nk1);
@@ -231,6 +233,7 @@ SB_HD BsdfEval bsdf_evaluate(const sb_material& m, const float3& n, const float3
 }
 
 // mdlcode_sample stand-in.  xi = (z1..z4) of closest_hit.cu:510-519.
+template <bool PREVIEW = true>
 SB_HD BsdfSample bsdf_sample(const sb_material& m, const float3& n, const float3& ng, const float3& k1, const float4& xi)
 {
     BsdfSample s;
@@ -243,7 +246,7 @@ SB_HD BsdfSample bsdf_sample(const sb_material& m, const float3& n, const float3
     {
         return s; // seen from below: absorb (no facing test in the reference, quirk Q13)
     }
-    if (m.model == SB_MATERIAL_USD_PREVIEW_SURFACE)
+    if (PREVIEW && m.model == SB_MATERIAL_USD_PREVIEW_SURFACE)
     {
         const UpsLobes L = ups_init(m);
         const UpsWeights w = ups_weights(L, nk1);

@@ -66,6 +66,8 @@ struct SceneDev
     WideNode* triNodes = nullptr;
     WideNode* segNodes = nullptr;
     uint32_t numTris = 0, numSegs = 0, numTriNodes = 0, numSegNodes = 0;
+    bool onlyRectLights = false; // every light is a rect light (with rectLightSamplingMethod 0 the shade kernel keeps only that sampler)
+    bool anyPreviewMaterial = true; // false: every material is a diffuse one (the shade kernel drops the UsdPreviewSurface code)
 };
 
 // SAH constants of the BVH2 -> BVH8 cut (collapse_dp_node).  Ylitie 2017 uses node : triangle = 1 : 0.3; measured

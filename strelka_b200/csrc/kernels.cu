@@ -16,6 +16,7 @@ uint32_t h_sobol[5][32];
 
 #include "wavefront.cuh"
 #include "kernels.h"
+#include <type_traits>
 
 namespace sb
 {
@@ -386,6 +387,7 @@ struct StagedSink
 #ifndef SB_SHADE_MIN_BLOCKS
 #define SB_SHADE_MIN_BLOCKS 8 // measured: 64 registers + a few L1 spills beat 111 registers at 25 % occupancy (latency-bound kernel)
 #endif
+template <bool CURVES, bool PREVIEW, bool RECT_UNIFORM>
 __global__ void __launch_bounds__(kBlock, SB_SHADE_MIN_BLOCKS) k_shade(FrameParams P, SceneDev S, Queues Q, uint32_t depth)
 {
     // 12 KB of byte-sliced Sobol tables per CTA (L2-resident source; 6 x 128-bit loads per thread)
@@ -426,7 +428,7 @@ __global__ void __launch_bounds__(kBlock, SB_SHADE_MIN_BLOCKS) k_shade(FramePara
                 ps.flags = f2u(th.w);
                 ps.pathId = f2u(ro.w);
                 ps.L = Q.Lacc[ps.pathId];
-                next = shade_bounce(P, S, ps, ha, hb, depth, s_tab, s_unpack, sink);
+                next = shade_bounce<CURVES, PREVIEW, RECT_UNIFORM>(P, S, ps, ha, hb, depth, s_tab, s_unpack, sink);
             }
         }
         uint32_t sslot, nslot;
@@ -829,7 +831,14 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
         }
         {
             ScopedStage sc(cfg, kStageShade);
-            k_shade<<<grid_for(cfg, SB_SHADE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
+            // the variant without the code paths this scene cannot take
+            const bool preview = S.anyPreviewMaterial, rectUniform = S.onlyRectLights && P.rectMethod == 0u;
+            auto launch = [&](auto c, auto p, auto r) {
+                k_shade<decltype(c)::value, decltype(p)::value, decltype(r)::value><<<grid_for(cfg, SB_SHADE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
+            };
+            auto pick_r = [&](auto c, auto p) { rectUniform ? launch(c, p, std::true_type()) : launch(c, p, std::false_type()); };
+            auto pick_p = [&](auto c) { preview ? pick_r(c, std::true_type()) : pick_r(c, std::false_type()); };
+            curves ? pick_p(std::true_type()) : pick_p(std::false_type());
         }
         if (P.debug == 1u)
             break; // debug normals: only the first hit is shaded (OptixRender.cu:151-152)

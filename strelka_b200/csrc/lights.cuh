@@ -150,8 +150,11 @@ SB_HD float rect_light_pdf(const sb_light& l, const float3& lightHit, const floa
     return s.distToLight * s.distToLight / (dot(-s.L, s.normal) * s.area);
 }
 // getLightPdf(l, lightHitPoint, surfaceHitPoint), Lights.h:221-243
+template <bool RECT_UNIFORM = false>
 SB_HD float light_pdf(const sb_light& l, const float3& lightHit, const float3& surfaceHit)
 {
+    if (RECT_UNIFORM)
+        return rect_light_pdf(l, lightHit, surfaceHit);
     switch (l.type)
     {
     case 0:
@@ -258,8 +261,12 @@ SB_HD LightSample sample_sphere(const sb_light& l, float u, float v, const float
     return s;
 }
 // the switch of sampleLight(), closest_hit.cu:266-291
+// RECT_UNIFORM = true: the caller guarantees rect lights sampled uniformly only (compiles the other samplers out)
+template <bool RECT_UNIFORM = false>
 SB_HD LightSample sample_light(const sb_light& l, float u, float v, const float3& hitPoint, uint32_t rectMethod)
 {
+    if (RECT_UNIFORM)
+        return sample_rect_uniform(l, u, v, hitPoint);
     LightSample s;
     s.pointOnLight = mk3(0.0f);
     s.pdf = 0.0f;

@@ -559,6 +559,12 @@ sb_result sb_set_scene(sb_ctx* c, const sb_scene_view* v)
     s.numInstances = v->num_instances;
     s.numLights = v->num_lights;
     s.numMaterials = numMaterials;
+    s.onlyRectLights = v->num_lights > 0;
+    for (uint32_t i = 0; i < v->num_lights; ++i)
+        s.onlyRectLights = s.onlyRectLights && v->lights[i].type == 0;
+    s.anyPreviewMaterial = false;
+    for (uint32_t i = 0; i < v->num_materials; ++i)
+        s.anyPreviewMaterial = s.anyPreviewMaterial || v->materials[i].model == SB_MATERIAL_USD_PREVIEW_SURFACE;
     s.numMeshes = v->num_meshes;
     s.numCurves = v->num_curves;
     s.numCurvePoints = v->num_curve_points;

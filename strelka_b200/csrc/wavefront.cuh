@@ -267,7 +267,10 @@ SB_HD Surface curve_surface(const SceneDev& S, const InstDev& I, uint32_t segInd
 // Side effects go through `sink` at the point they arise (keeps the live ranges short):
 //   sink.radiance_changed(ps)                      ps.L changed (emitter hit, debug view, NaN guard, AOV tag)
 //   sink.shadow_ray(ps, shO, shD, contrib)         trace (origin.xyz + tmin, dir.xyz + tmax); add contrib to L if unoccluded
-template <class Sink>
+// CURVES / PREVIEW = false compile the curve attributes / the UsdPreviewSurface model out for scenes without them,
+// RECT_UNIFORM = true everything but the uniform rect-light sampler (all lights rect, rectLightSamplingMethod 0)
+// (the shade kernel is register-bound; the host picks the variant per scene)
+template <bool CURVES = true, bool PREVIEW = true, bool RECT_UNIFORM = false, class Sink>
 SB_HD bool shade_bounce(const FrameParams& P, const SceneDev& S, PathState& ps, const float4& ha, uint32_t hb, uint32_t depth, const uint32_t* sobolTab,
                         const float* unpackLut, Sink& sink)
 {
@@ -306,7 +309,7 @@ SB_HD bool shade_bounce(const FrameParams& P, const SceneDev& S, PathState& ps, 
                 }
                 else
                 {
-                    const float lightPdf = light_pdf(l, hitPoint, rayO) / float(S.numLights);
+                    const float lightPdf = light_pdf<RECT_UNIFORM>(l, hitPoint, rayO) / float(S.numLights);
                     const float w = mis_balance(lastBsdfPdf, lightPdf);
                     Lpath += throughput * color * -dot(rayD, ln) * w;
                 }
@@ -319,7 +322,7 @@ SB_HD bool shade_bounce(const FrameParams& P, const SceneDev& S, PathState& ps, 
 
     // ---- __closesthit__radiance, closest_hit.cu:456-606 --------------------------------------------
     const bool isInside = (flags & kFlagInside) != 0u;
-    const Surface sf = (kind == 1u) ? tri_surface(I, tri, ha.y, ha.z, isInside, unpackLut) : curve_surface(S, I, f2u(ha.w), ha.y, ha.x, rayO, rayD, isInside);
+    const Surface sf = (!CURVES || kind == 1u) ? tri_surface(I, tri, ha.y, ha.z, isInside, unpackLut) : curve_surface(S, I, f2u(ha.w), ha.y, ha.x, rayO, rayD, isInside);
     if (P.debug == 1u)
     {
         ps.L = mk4((sf.normal + mk3(1.0f)) * 0.5f, 0.0f); // closest_hit.cu:504-508
@@ -336,7 +339,7 @@ SB_HD bool shade_bounce(const FrameParams& P, const SceneDev& S, PathState& ps, 
     // lightPoint = (v[3], v[4]), russian roulette = v[4]
     const Sample5 rn = sampler_sample5(sidx, depth, sobolTab);
     const float3 k1 = -rayD;
-    const BsdfSample bs = bsdf_sample(mat, sf.normal, sf.geomNormal, k1, mk4(rn.v[0], rn.v[1], rn.v[2], rn.v[3]));
+    const BsdfSample bs = bsdf_sample<PREVIEW>(mat, sf.normal, sf.geomNormal, k1, mk4(rn.v[0], rn.v[1], rn.v[2], rn.v[3]));
     if (bs.event == EV_ABSORB)
     {
         return false; // throughput = 0 (firstEventType = eAbsorb: counted by neither AOV)
@@ -368,7 +371,7 @@ SB_HD bool shade_bounce(const FrameParams& P, const SceneDev& S, PathState& ps, 
                 lightId = S.numLights - 1u;
             const float lightSelectionPdf = 1.0f / float(S.numLights);
             const sb_light& l = S.lights[lightId];
-            const LightSample ls = sample_light(l, rn.v[3], rn.v[4], sf.position, P.rectMethod);
+            const LightSample ls = sample_light<RECT_UNIFORM>(l, rn.v[3], rn.v[4], sf.position, P.rectMethod);
             const float3 Li = mk3(l.color[0], l.color[1], l.color[2]);
             if (dot(sf.normal, ls.L) > 0.0f && -dot(ls.L, ls.normal) > 0.0 && all_nonzero(Li))
             {
@@ -383,7 +386,7 @@ SB_HD bool shade_bounce(const FrameParams& P, const SceneDev& S, PathState& ps, 
                 const bool nextEventValid = ((dot(ls.L, sf.normal) > 0.0f) != isInside) && lightPdf != 0.0f;
                 if (nextEventValid)
                 {
-                    const BsdfEval ev = bsdf_evaluate(mat, sf.normal, sf.geomNormal, k1, ls.L);
+                    const BsdfEval ev = bsdf_evaluate<PREVIEW>(mat, sf.normal, sf.geomNormal, k1, ls.L);
                     if (isnan3(ev.diffuse) || isnan3(ev.glossy))
                     {
                         ps.L = mk4(10000.0f, 0.0f, 0.0f, 0.0f);
