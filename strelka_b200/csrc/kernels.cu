@@ -757,6 +757,28 @@ static inline unsigned grid_for(const LaunchCfg& cfg, int blocksPerSm)
     return unsigned(cfg.numSms * blocksPerSm);
 }
 
+// run-time flags -> compile-time template arguments: calls f(std::bool_constant<a>, <b>, <c>)
+template <class F>
+static void launch_shade_variant(bool a, bool b, bool c, F f)
+{
+    auto with_c = [&](auto ta, auto tb) {
+        if (c)
+            f(ta, tb, std::true_type());
+        else
+            f(ta, tb, std::false_type());
+    };
+    auto with_b = [&](auto ta) {
+        if (b)
+            with_c(ta, std::true_type());
+        else
+            with_c(ta, std::false_type());
+    };
+    if (a)
+        with_b(std::true_type());
+    else
+        with_b(std::false_type());
+}
+
 void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const SceneDev& S, const Queues& Qbase, bool stats)
 {
     const Queues& Q = Qbase;
@@ -833,12 +855,9 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
             ScopedStage sc(cfg, kStageShade);
             // the variant without the code paths this scene cannot take
             const bool preview = S.anyPreviewMaterial, rectUniform = S.onlyRectLights && P.rectMethod == 0u;
-            auto launch = [&](auto c, auto p, auto r) {
+            launch_shade_variant(curves, preview, rectUniform, [&](auto c, auto p, auto r) {
                 k_shade<decltype(c)::value, decltype(p)::value, decltype(r)::value><<<grid_for(cfg, SB_SHADE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
-            };
-            auto pick_r = [&](auto c, auto p) { rectUniform ? launch(c, p, std::true_type()) : launch(c, p, std::false_type()); };
-            auto pick_p = [&](auto c) { preview ? pick_r(c, std::true_type()) : pick_r(c, std::false_type()); };
-            curves ? pick_p(std::true_type()) : pick_p(std::false_type());
+            });
         }
         if (P.debug == 1u)
             break; // debug normals: only the first hit is shaded (OptixRender.cu:151-152)
