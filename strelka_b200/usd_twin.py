@@ -19,9 +19,9 @@ and so that the flattening contract of the delegate is executable here (`ingest`
   * Camera.cpp:65-106      position = translation of the camera transform, orientation = conjugate of its rotation,
                            fov = vertical field of view in degrees
 Prims are visited in path order, as HdRenderIndex::GetRprimIds / GetSprimSubtree return them; the writer names prims
-so that this order is the original instance order.  OpenUSD itself (UsdImaging, HdMeshUtil triangulation of n-gons,
-Hd_SmoothNormals, instancers, MaterialX translation) is NOT restated: the twins only contain triangles with
-face-varying normals, direct transforms and UsdPreviewSurface constants.  Parity of this module against the real
+so that this order is the original instance order.  Of OpenUSD itself only the two published mesh utilities the delegate calls are restated (`triangulate` = HdMeshUtil's
+fan triangulation, `smooth_normals` = Hd_SmoothNormals); UsdImaging, instancers and the MaterialX translation are not:
+the twins only contain triangles with face-varying normals, direct transforms and UsdPreviewSurface constants.  Parity of this module against the real
 delegate is therefore unpinned; it documents the contract and keeps the twins honest.
 """
 from __future__ import annotations
@@ -275,6 +275,43 @@ def _compute_tangent(n: np.ndarray) -> np.ndarray:
     return (t / np.maximum(ln, _F(1e-30))).astype(_F)
 
 
+def triangulate(counts, indices, left_handed: bool = False):
+    """HdMeshUtil::ComputeTriangleIndices / ComputeTriangulatedFaceVaryingPrimvar (OpenUSD pxr/imaging/hd/meshUtil.cpp,
+    not in the reference tree): fan (0, i+1, i+2) per face, winding flipped for leftHanded orientation, faces with
+    fewer than 3 vertices dropped.  Returns (vertex indices [T,3], face-varying corner indices [T,3])."""
+    counts = np.asarray(counts, dtype=np.int64)
+    indices = np.asarray(indices, dtype=np.int64)
+    tri_v, tri_c = [], []
+    base = 0
+    for n in counts:
+        for i in range(max(int(n) - 2, 0)):
+            c = (base, base + i + 2, base + i + 1) if left_handed else (base, base + i + 1, base + i + 2)
+            tri_c.append(c)
+            tri_v.append(tuple(indices[list(c)]))
+        base += int(n)
+    return np.asarray(tri_v, dtype=np.int64).reshape(-1, 3), np.asarray(tri_c, dtype=np.int64).reshape(-1, 3)
+
+
+def smooth_normals(points, counts, indices, left_handed: bool = False) -> np.ndarray:
+    """Hd_SmoothNormals::ComputeSmoothNormals (pxr/imaging/hd/smoothNormals.cpp): per vertex, the normalised sum over
+    its incident face corners of cross(next - curr, prev - curr) -- area- and angle-weighted, float32 accumulation."""
+    points = np.asarray(points, dtype=_F).reshape(-1, 3)
+    counts = np.asarray(counts, dtype=np.int64)
+    indices = np.asarray(indices, dtype=np.int64)
+    n = np.zeros_like(points)
+    base = 0
+    for cnt in counts:
+        cnt = int(cnt)
+        for k in range(cnt):
+            cur, prv, nxt = indices[base + k], indices[base + (k - 1) % cnt], indices[base + (k + 1) % cnt]
+            if left_handed:
+                prv, nxt = nxt, prv
+            n[cur] += np.cross(points[nxt] - points[cur], points[prv] - points[cur]).astype(_F)
+        base += cnt
+    ln = np.sqrt((n * n).sum(axis=1, keepdims=True))
+    return (n / np.maximum(ln, _F(1e-30))).astype(_F)
+
+
 def _walk(prims, prefix=""):
     for p in sorted(prims, key=lambda q: q["name"]):  # path order, as the render index returns ids
         path = prefix + "/" + p["name"]
@@ -309,14 +346,26 @@ def ingest(doc: dict) -> Scene:
         a = p["attrs"]
         if p["type"] == "Mesh":
             counts = np.asarray(a["faceVertexCounts"][0], dtype=np.int64)
-            assert np.all(counts == 3), "twins hold triangles only (HdMeshUtil's n-gon triangulation is not restated)"
             fvi = np.asarray(a["faceVertexIndices"][0], dtype=np.int64)
             points = np.asarray(a["points"][0], dtype=_F).reshape(-1, 3)
-            normals, meta = a["normals"]
-            assert meta.get("interpolation") == "faceVarying", "vertex normals would be overwritten by smooth normals (quirk Q21)"
-            normals = np.asarray(normals, dtype=_F).reshape(-1, 3)
-            pos = points[fvi]  # Mesh.cpp:143-145: three new vertices per face
-            vb = make_vertices(pos, normals=normals, tangents=_compute_tangent(normals))
+            left = "orientation" in a and a["orientation"][0] == "leftHanded"
+            tri_v, tri_c = triangulate(counts, fvi, left)
+            if "normals" in a and a["normals"][1].get("interpolation") == "faceVarying":
+                fv = np.asarray(a["normals"][0], dtype=_F).reshape(-1, 3)
+                normals = fv[tri_c.reshape(-1)]  # triangulated face-varying primvar, used as authored
+            else:
+                # authored vertex normals are read and then REPLACED by smooth normals (quirk Q21, Mesh.cpp:251-279)
+                normals = smooth_normals(points, counts, fvi, left)[tri_v.reshape(-1)]
+            uvs = None
+            for key in ("primvars:st", "st"):
+                if key in a:
+                    st_vals = np.asarray(a[key][0], dtype=_F).reshape(-1, 2)
+                    interp = a[key][1].get("interpolation", "vertex")
+                    uv = st_vals[tri_c.reshape(-1)] if interp == "faceVarying" else st_vals[tri_v.reshape(-1)]
+                    uvs = np.stack([uv[:, 0], _F(1.0) - uv[:, 1]], axis=1)  # v flipped, RenderPass.cpp:104
+                    break
+            pos = points[tri_v.reshape(-1)]  # Mesh.cpp:143-145: three new vertices per triangle
+            vb = make_vertices(pos, normals=normals, tangents=_compute_tangent(normals), uvs=uvs)
             if "material:binding" in a:
                 mat = get_or_create_material(a["material:binding"][0].strip("<>"))
             else:

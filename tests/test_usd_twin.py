@@ -64,3 +64,41 @@ def test_curve_twin_recreates_phantom_points(tmp_path):
     a = pyoracle.OracleScene(s).render(st, w, h, 2)[0]
     b = pyoracle.OracleScene(s2).render(st, w, h, 2)[0]
     assert rel_rmse(a, b) < 1e-3
+
+
+def test_ingest_triangulates_quads_and_replaces_vertex_normals_q21(tmp_path):
+    # a unit cube authored with quads and (wrong) vertex normals: the delegate fan-triangulates (HdMeshUtil) and
+    # replaces vertex-interpolated normals by smooth normals (quirk Q21), so the bogus normals must not survive
+    path = tmp_path / "cube.usda"
+    path.write_text("""#usda 1.0
+(
+    upAxis = "Y"
+)
+def Xform "World"
+{
+    def Mesh "cube"
+    {
+        matrix4d xformOp:transform = ( (1, 0, 0, 0), (0, 1, 0, 0), (0, 0, 1, 0), (0, 0, 0, 1) )
+        uniform token[] xformOpOrder = ["xformOp:transform"]
+        int[] faceVertexCounts = [4, 4, 4, 4, 4, 4]
+        int[] faceVertexIndices = [0, 1, 3, 2, 4, 6, 7, 5, 0, 4, 5, 1, 2, 3, 7, 6, 0, 2, 6, 4, 1, 5, 7, 3]
+        point3f[] points = [(-1, -1, -1), (-1, -1, 1), (-1, 1, -1), (-1, 1, 1), (1, -1, -1), (1, -1, 1), (1, 1, -1), (1, 1, 1)]
+        normal3f[] normals = [(0, 1, 0), (0, 1, 0), (0, 1, 0), (0, 1, 0), (0, 1, 0), (0, 1, 0), (0, 1, 0), (0, 1, 0)] (
+            interpolation = "vertex"
+        )
+    }
+}
+""")
+    s2 = usd_twin.ingest(usd_twin.read_usda(str(path)))
+    a = s2.arrays()
+    assert len(a["vertices"]) == 36 and len(a["indices"]) == 36  # 12 triangles, un-indexed
+    from strelka_b200.scene import unpack_normal
+
+    n = unpack_normal(a["vertices"]["normal"])
+    p = a["vertices"]["pos"]
+    expect = p / np.linalg.norm(p, axis=1, keepdims=True)  # smooth normals of a cube point along the diagonals
+    assert np.abs(n - expect).max() < 4e-3  # 10-bit quantisation
+    # outward winding is preserved by the fan
+    tri = p.reshape(12, 3, 3)
+    face_n = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    assert np.all((face_n * tri.mean(axis=1)).sum(axis=1) > 0)
