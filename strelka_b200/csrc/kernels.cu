@@ -150,7 +150,7 @@ __device__ __forceinline__ void flush_stats(StatCounters* g, const TravStats& st
 // sensitive to its control-flow shape -- one extra early-return inside trav_node cost 50 % -- so keep it flat:
 // one trav_step per lane, ONE warp-wide ballot per iteration.
 #ifndef SB_REFILL
-#define SB_REFILL 24
+#define SB_REFILL 28
 #endif
 constexpr int kRefill = SB_REFILL;
 struct WarpFetch
