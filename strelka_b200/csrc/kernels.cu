@@ -36,7 +36,10 @@ uint32_t* upload_sobol_table(cudaStream_t stream)
 
 constexpr int kBlock = 128;
 constexpr int kBlockWarps = kBlock / 32;
-constexpr uint32_t kTinyBvhNodes = 64; // at or below this many wide nodes traversal is a few steps: no dynamic fetch
+#ifndef SB_TINY_NODES
+#define SB_TINY_NODES 64
+#endif
+constexpr uint32_t kTinyBvhNodes = SB_TINY_NODES; // at or below this many wide nodes traversal is a few steps: no dynamic fetch
 
 // Block-aggregated queue allocation.  The first ncu source view of k_shade had a third of its stall samples
 // on the two warp-aggregated atomicAdds of the queue cursors: every warp of the chip hits the same two L2
