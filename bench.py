@@ -289,7 +289,7 @@ def run_b200(args) -> None:
             with open(tpath) as f:
                 traffic = json.load(f).get("c2", {}).get(f"k_{trav}", {}).get("dram_bytes_per_launch")
         roofline = {
-            "bound": "hbm", "kernel": f"k_{trav}", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+            "bound": "hbm", "kernel": f"k_{trav}" + (" (k_primary for the camera rays + k_extend_simple)" if trav == "extend" else ""), "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
             "traffic": traffic, "traffic_unit": "bytes per launch (ncu --set full, profiles/ncu_traffic.json)",
             "alg_bytes_per_launch": per_ray[trav] * n_rays / max(stage_n[trav], 1),
             "peak_source": peak_src, "alg_bytes_per_ray": per_ray[trav],

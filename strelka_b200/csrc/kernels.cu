@@ -141,6 +141,38 @@ __device__ __forceinline__ void flush_stats(StatCounters* g, const TravStats& st
     }
 }
 
+// Camera rays generated and traced in one kernel (images whose size is a whole number of 8x4 tiles: no padding
+// pixels, so path id == queue slot and nothing needs allocating).  Saves writing the primary rays only to read them
+// back, and one launch per batch.
+template <bool STATS, bool CURVES>
+__global__ void __launch_bounds__(kBlock, 8) k_primary(FrameParams P, SceneDev S, Queues Q)
+{
+    const uint32_t n = P.nPixPadded * P.chunk;
+    TravStats st = { 0, 0, 0, 0 };
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        PathState ps;
+        raygen_state(P, i, ps);
+        float4 ha;
+        uint32_t hb;
+        trace_closest<STATS, CURVES>(S, ps.o, ps.d, P.materialTmin, ha, hb, &st);
+        Q.Lacc[i] = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+        Q.rayO[0][i] = mk4(ps.o, u2f(i));
+        Q.rayD[0][i] = mk4(ps.d, 0.0f);
+        Q.thr[0][i] = mk4(1.0f, 1.0f, 1.0f, u2f(0u));
+        Q.hitA[i] = ha;
+        Q.hitB[i] = hb;
+    }
+    if (STATS)
+        flush_stats(Q.stats, st, false);
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        Q.counts[count_path(0)] = n;
+        atomicAdd(&Q.stats->paths, (unsigned long long)n);
+        atomicAdd(&Q.stats->radianceRays, (unsigned long long)n);
+    }
+}
+
 // ---- persistent traversal kernels with dynamic ray fetch ----------------------------------------------
 // Incoherent secondary rays finish after very different numbers of steps; with one ray per thread the first
 // ncu capture on the 2 M-triangle scene showed 7 of 32 lanes active on average.  Here every warp keeps its
@@ -568,6 +600,9 @@ __global__ void __launch_bounds__(kBlock, SB_FUSED_MIN_BLOCKS) k_path_fused(Fram
 // them.  Measured on C2: one-ray-per-thread traversal kernels 16 -> 256 CTAs/SM: -8 %; shade 8 -> 128: -4 % (each
 // shade CTA first fills 16 KB of shared-memory tables, so more than that costs again); 1024+: launch overhead shows.
 // The persistent kernels balance themselves through the dynamic ray fetch and stay at one wave.
+#ifndef SB_FUSED_PRIMARY
+#define SB_FUSED_PRIMARY 1
+#endif
 #ifndef SB_ACC_GRID
 #define SB_ACC_GRID 32
 #endif
@@ -799,6 +834,26 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
         SB_CUDA_CHECK(cudaGetLastError());
         return;
     }
+    const bool fusedPrimary = SB_FUSED_PRIMARY && P.nPixPadded == P.width * P.height; // no padding pixels
+    if (fusedPrimary)
+    {
+        ScopedStage sc(cfg, kStageExtend);
+        if (curves)
+        {
+            if (stats)
+                k_primary<true, true><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(P, S, Q);
+            else
+                k_primary<false, true><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(P, S, Q);
+        }
+        else
+        {
+            if (stats)
+                k_primary<true, false><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(P, S, Q);
+            else
+                k_primary<false, false><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(P, S, Q);
+        }
+    }
+    else
     {
         ScopedStage sc(cfg, kStageRaygen);
         k_raygen<<<grid_for(cfg, SB_RAYGEN_GRID), kBlock, 0, st>>>(P, Q);
@@ -813,6 +868,7 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
             std::swap(Q.rayD[0], Q.rayD[1]);
             std::swap(Q.thr[0], Q.thr[1]);
         }
+        if (depth > 0 || !fusedPrimary)
         {
             ScopedStage sc(cfg, kStageExtend);
             // primary rays are coherent, and a scene of a few nodes is traversed in a few steps: one ray per thread
