@@ -228,6 +228,11 @@ __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FramePa
     RayPrep rp;
     HitRec hit;
     Traversal T;
+#if SB_SMEM_STACK
+    static_assert(kTravBlock == kBlock, "shared-memory traversal stack stride");
+    __shared__ uint2 s_stack[SB_SMEM_STACK * kBlock];
+    T.sstack = s_stack + threadIdx.x;
+#endif
     for (;;)
     {
         const uint32_t got = fetch_slots(head, n, !active, exhausted);
@@ -272,9 +277,9 @@ __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FramePa
                     more = trav_step_unit<2, false, STATS>(T, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
 #else
                 if (phase == 0)
-                    more = trav_step<1, false, STATS>(T, S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
+                    more = trav_step<1, false, STATS, (SB_SMEM_STACK > 0)>(T, S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
                 else if (CURVES && phase == 1)
-                    more = trav_step<2, false, STATS>(T, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
+                    more = trav_step<2, false, STATS, (SB_SMEM_STACK > 0)>(T, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
 #endif
                 if (!more)
                 {
@@ -325,6 +330,11 @@ __global__ void __launch_bounds__(kBlock, SB_SHADOW_MIN_BLOCKS) k_shadow(SceneDe
     RayPrep rp;
     HitRec hit;
     Traversal T;
+#if SB_SMEM_STACK
+    static_assert(kTravBlock == kBlock, "shared-memory traversal stack stride");
+    __shared__ uint2 s_stack[SB_SMEM_STACK * kBlock];
+    T.sstack = s_stack + threadIdx.x;
+#endif
     for (;;)
     {
         const uint32_t got = fetch_slots(head, n, !active, exhausted);
@@ -360,9 +370,9 @@ __global__ void __launch_bounds__(kBlock, SB_SHADOW_MIN_BLOCKS) k_shadow(SceneDe
                     more = trav_step_ww<2, true, STATS>(T, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st);
 #elif SB_SHADOW_UNIT_STEP
                 if (phase == 0)
-                    more = trav_step_unit<1, true, STATS>(T, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st);
+                    more = trav_step_unit<1, true, STATS, (SB_SMEM_STACK > 0)>(T, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st);
                 else if (CURVES && phase == 1)
-                    more = trav_step_unit<2, true, STATS>(T, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st);
+                    more = trav_step_unit<2, true, STATS, (SB_SMEM_STACK > 0)>(T, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st);
 #else
                 if (phase == 0)
                     more = trav_step<1, true, STATS>(T, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st);

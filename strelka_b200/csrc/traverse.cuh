@@ -10,6 +10,9 @@
 #include "bvh.cuh"
 #include "curve.cuh"
 
+#ifndef SB_SMEM_STACK
+#define SB_SMEM_STACK 8
+#endif
 #ifndef SB_F32X2
 #define SB_F32X2 1
 #endif
@@ -236,10 +239,16 @@ SB_HD RayPrep prepare_ray(const float3& d)
 
 // Traversal state of one ray in one BVH.  A "node group" is (child base index, hit bits | inner mask), a
 // "primitive group" is (primitive base index, hit bits); the stack holds postponed node groups only.
+// SB_SMEM_STACK > 0: the first SB_SMEM_STACK stack levels of the persistent kernels live in shared memory
+// (strided by the block size, bank-conflict free), deeper ones in local memory.
+constexpr int kTravBlock = 128; // threads per block of the kernels that use the shared-memory stack
 struct Traversal
 {
     uint2 ngroup, tgroup;
     int sp;
+#if defined(__CUDACC__)
+    uint2* sstack; // this thread's column of the block's shared-memory stack (SSTACK traversals only)
+#endif
     uint2 stack[kStackSize];
 };
 SB_HD void trav_init(Traversal& T)
@@ -256,14 +265,20 @@ SB_HD void trav_init(Traversal& T)
 //   trav_node : if the lane has no primitives pending, visit the next node (returns false when nothing is left)
 //   trav_prim : if the lane has primitives pending, test exactly one
 // KIND 1: triangles (prims = TriRec), KIND 2: curve segments (prims = SegRec).  ANY: shadow rays.
-template <bool STATS>
+template <bool STATS, bool SSTACK = false>
 SB_HD bool trav_node(Traversal& T, const WideNode* __restrict__ nodes, const Ray& ray, const RayPrep& rp, TravStats* st)
 {
     if (T.ngroup.y <= 0x00ffffffu)
     {
         if (T.sp == 0)
             return false;
-        T.ngroup = T.stack[--T.sp];
+        --T.sp;
+#if defined(__CUDA_ARCH__) && SB_SMEM_STACK
+        if (SSTACK)
+            T.ngroup = (T.sp < SB_SMEM_STACK) ? T.sstack[T.sp * kTravBlock] : T.stack[T.sp - SB_SMEM_STACK];
+        else
+#endif
+            T.ngroup = T.stack[T.sp];
     }
     const uint32_t hits = T.ngroup.y;
     const uint32_t bit = bfind32(hits);
@@ -271,7 +286,20 @@ SB_HD bool trav_node(Traversal& T, const WideNode* __restrict__ nodes, const Ray
     if (T.ngroup.y > 0x00ffffffu)
     {
         if (T.sp < kStackSize)
-            T.stack[T.sp++] = T.ngroup;
+        {
+#if defined(__CUDA_ARCH__) && SB_SMEM_STACK
+            if (SSTACK)
+            {
+                if (T.sp < SB_SMEM_STACK)
+                    T.sstack[T.sp * kTravBlock] = T.ngroup;
+                else
+                    T.stack[T.sp - SB_SMEM_STACK] = T.ngroup;
+            }
+            else
+#endif
+                T.stack[T.sp] = T.ngroup;
+            ++T.sp;
+        }
         else if (STATS)
             st->overflow++;
     }
@@ -354,13 +382,13 @@ SB_HD bool trav_prim(Traversal& T, const void* __restrict__ prims, uint32_t rayM
 
 // one full step of one lane: node half-step if idle, then one primitive if any is pending.
 // Returns false when the traversal is finished; anyHit is set when an ANY query found an occluder.
-template <int KIND, bool ANY, bool STATS>
+template <int KIND, bool ANY, bool STATS, bool SSTACK = false>
 SB_HD bool trav_step(Traversal& T, const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask, Ray& ray,
                      const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st)
 {
     if (T.tgroup.y == 0u)
     {
-        if (!trav_node<STATS>(T, nodes, ray, rp, st))
+        if (!trav_node<STATS, SSTACK>(T, nodes, ray, rp, st))
             return false;
     }
     if (T.tgroup.y != 0u)
@@ -377,7 +405,7 @@ SB_HD bool trav_step(Traversal& T, const WideNode* __restrict__ nodes, const voi
 // Single-unit variant of trav_step: ONE primitive test if any is pending, else ONE node visit.  Measured on the
 // 2 M-triangle scene the any-hit (shadow) kernel runs 1.5x faster with this shape, the closest-hit kernel
 // slightly faster with the node+primitive shape above (profiles/r01_b_*).
-template <int KIND, bool ANY, bool STATS>
+template <int KIND, bool ANY, bool STATS, bool SSTACK = false>
 SB_HD bool trav_step_unit(Traversal& T, const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask, Ray& ray,
                           const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st)
 {
@@ -390,7 +418,7 @@ SB_HD bool trav_step_unit(Traversal& T, const WideNode* __restrict__ nodes, cons
         }
         return true;
     }
-    return trav_node<STATS>(T, nodes, ray, rp, st);
+    return trav_node<STATS, SSTACK>(T, nodes, ray, rp, st);
 }
 
 // "While-while" step: ONE node visit, then ALL the primitives it queued.  The lanes of a warp meet again at every
