@@ -22,7 +22,13 @@
 extern "C" {
 #endif
 
-#define SB_API_VERSION 1
+#define SB_API_VERSION 2
+
+/* Version / layout handshake for bindings: SB_API_VERSION of the built library, and sizeof() of the ABI structs
+ * (which: 0 sb_settings, 1 sb_device_cfg, 2 sb_counters, 3 sb_scene_view, 4 sb_material, 5 sb_light, 6 sb_instance,
+ * 7 sb_vertex, 8 sb_hit, 9 sb_mesh, 10 sb_curve, 11 sb_texture; 0 for anything else). */
+uint32_t sb_abi_version(void);
+uint32_t sb_abi_struct_size(uint32_t which);
 
 /* oka::Result, include/render/common.h:30-35 (declared but unused by the reference, which
  * assert(0)s instead, OptixRender.cpp:61-103; this ABI never aborts). */
@@ -132,8 +138,25 @@ typedef struct sb_material
     float hair_roughness_lon; /* beta_m */
     float hair_roughness_azi; /* beta_n */
     float hair_cuticle_angle; /* alpha, radians */
-    float pad[4];
+    /* UsdUVTexture inputs of a UsdPreviewSurface network (MaterialManager::Param::Type::eTexture params
+     * "<node>_file", Material.cpp:120-136; resolved by OptixRender.cpp:1346-1387): 1-based index into
+     * sb_scene_view.textures, 0 = no texture (MDL's invalid texture index, texture_support_cuda.h:300-304).
+     * diffuse_texture replaces base_color (rgb); normal_texture is a tangent-space normal map (rgb * 2 - 1). */
+    uint32_t diffuse_texture;
+    uint32_t normal_texture;
+    float pad[2];
 } sb_material; /* 96 B */
+
+/* One 2D texture as the reference creates it (OptiXRender::loadTextureFromFile, OptixRender.cpp:1191-1268):
+ * 8-bit RGBA texels (stbi STBI_rgb_alpha: row 0 = top of the image file), sampled with wrap addressing, linear
+ * filtering, normalised coordinates and normalised-float reads.  Texture coordinates are the vertices' packed
+ * st primvar with v already flipped by the delegate (RenderPass.cpp:109-114). */
+typedef struct sb_texture
+{
+    const uint8_t* pixels; /* width * height * 4 bytes, borrowed for the duration of sb_set_scene */
+    uint32_t width;
+    uint32_t height;
+} sb_texture;
 
 /* Borrowed view of the flattened scene (valid only for the duration of sb_set_scene()).
  * Mirrors the getters the OptiX backend reads: getVertices/getIndices/getMeshes/getCurves/
@@ -163,6 +186,8 @@ typedef struct sb_scene_view
     uint32_t num_lights;
     const sb_material* materials;
     uint32_t num_materials;
+    const sb_texture* textures; /* may be NULL */
+    uint32_t num_textures;
 } sb_scene_view;
 
 /* ------------------------------------------------------------------------------------------
@@ -313,6 +338,27 @@ sb_result sb_synchronize(sb_ctx* ctx);
 void* sb_accum_device_ptr(sb_ctx* ctx, uint64_t* num_floats);
 sb_result sb_resolve(sb_ctx* ctx, sb_buffer* output, uint32_t total_samples);
 
+/* Sample-sharded rendering over several GPUs behind the ABI (new: OptiXRender is single-GPU, OptixRender.cpp:163-189).
+ * One sb_ctx per GPU = one rank; every rank holds a scene/BVH replica and renders the global sample indices
+ * rank, rank + world, ... of every pixel with the reference's sampler indices unchanged (Params.maxSampleCount stays
+ * the global sppTotal, RandomSampler.h:130-137).  The only exchange is one NCCL sum of S per call.
+ *   sb_comm_get_unique_id : ncclGetUniqueId; called once (by rank 0), the SB_COMM_ID_BYTES bytes are handed to the other
+ *                           ranks by the host application (file, socket, MPI, ...)
+ *   sb_comm_init          : ncclCommInitRank on the context's device; collective over all ranks.  Sets the context's
+ *                           sample_offset / sample_stride to rank / world (later sb_set_settings calls must keep them)
+ *   sb_render_sharded     : sb_render_iterations for this rank's share of `iterations` samples PER RANK, then
+ *                           ncclAllReduce(sum) of S on the context's stream into a separate buffer and the resolve
+ *                           T^-1(S_global / n_global) (+post) into `output` on every rank.  S itself stays the rank's own
+ *                           partial sum, so the call can be repeated for progressive display.  Collective: every rank
+ *                           must issue the same sequence of calls.  Needs spp == 1, enableAcc, debug == 0.
+ * libnccl.so.2 is dlopen()ed by the first of these calls; single-GPU use never loads it. */
+#define SB_COMM_ID_BYTES 128
+sb_result sb_comm_get_unique_id(void* id_out);
+sb_result sb_comm_init(sb_ctx* ctx, const void* id, uint32_t rank, uint32_t world);
+sb_result sb_comm_destroy(sb_ctx* ctx);
+uint32_t sb_comm_world(const sb_ctx* ctx);
+sb_result sb_render_sharded(sb_ctx* ctx, sb_buffer* output, uint32_t iterations);
+
 /* ------------------------------------------------------------------------------------------
  * Counters (new: the reference has no ray counters)
  * ---------------------------------------------------------------------------------------- */
@@ -342,6 +388,9 @@ typedef struct sb_counters
      * order: raygen, extend, shade, shadow, accumulate, resolve, fused path kernel, (reserved) */
     double stage_ms[8];
     uint64_t stage_launches[8];
+    /* levels of the two wide BVHs; the builder refuses trees deeper than the traversal stack (sb_set_scene fails) */
+    uint64_t bvh_depth_tri;
+    uint64_t bvh_depth_curve;
 } sb_counters;
 
 sb_result sb_get_counters(sb_ctx* ctx, sb_counters* out); /* synchronizes */
@@ -364,7 +413,11 @@ sb_result sb_test_light_sample(sb_ctx* ctx, uint32_t n, const sb_light* lights, 
                                const float* u, uint32_t method, float* out);
 
 /* Trace arbitrary rays against the current scene.  rays: 8 floats each (ox,oy,oz,tmin,dx,dy,dz,tmax).
- * mode 0: closest hit with mask 255; mode 1: any hit with mask 3 (shadow).
+ * mode 0: closest hit with mask 255; mode 1: any hit with mask 3 (shadow) -- one ray per thread, whole traversal.
+ * mode 2 / 3: the same two queries through the PRODUCTION path: the rays are written into the wavefront queues and
+ * traced by the stage launchers sb_render uses for secondary rays (the persistent dynamic-fetch k_extend / k_shadow
+ * kernels on every scene of more than a few nodes).  Mode 2 requires one common tmin and tmax >= 1e16, like the
+ * reference's radiance rays (OptixRender.cu:120-129).
  * hits: per ray {float t; float u; float v; uint32 prim; uint32 instance; uint32 kind}
  * kind 0 miss, 1 triangle, 2 curve (u = curve parameter). */
 typedef struct sb_hit

@@ -68,7 +68,9 @@ MATERIAL_DTYPE = np.dtype(
         ("hair_roughness_lon", "<f4"),
         ("hair_roughness_azi", "<f4"),
         ("hair_cuticle_angle", "<f4"),
-        ("pad", "<f4", (4,)),
+        ("diffuse_texture", "<u4"),
+        ("normal_texture", "<u4"),
+        ("pad", "<f4", (2,)),
     ]
 )
 HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4"), ("instance", "<u4"), ("kind", "<u4")])
@@ -97,7 +99,12 @@ class sb_scene_view(C.Structure):
         ("instances", C.c_void_p), ("num_instances", C.c_uint32),
         ("lights", C.c_void_p), ("num_lights", C.c_uint32),
         ("materials", C.c_void_p), ("num_materials", C.c_uint32),
+        ("textures", C.c_void_p), ("num_textures", C.c_uint32),
     ]
+
+
+class sb_texture(C.Structure):
+    _fields_ = [("pixels", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32)]
 
 
 class sb_settings(C.Structure):
@@ -127,6 +134,7 @@ class sb_counters(C.Structure):
         ("build_ms", C.c_double), ("render_ms", C.c_double),
         ("kernel_launches", C.c_uint64),
         ("stage_ms", C.c_double * 8), ("stage_launches", C.c_uint64 * 8),
+        ("bvh_depth_tri", C.c_uint64), ("bvh_depth_curve", C.c_uint64),
     ]
 
     STAGES = ("raygen", "extend", "shade", "shadow", "accumulate", "resolve", "path_fused", "reserved")
@@ -141,13 +149,16 @@ class sb_counters(C.Structure):
 
 # Every symbol include/sb/sb_api.h declares (tests/test_abi.py checks they are all exported).
 ABI_SYMBOLS = [
-    "sb_settings_default", "sb_create", "sb_set_stream", "sb_destroy", "sb_last_error", "sb_set_scene", "sb_set_camera",
+    "sb_abi_version", "sb_abi_struct_size", "sb_settings_default", "sb_create", "sb_set_stream", "sb_destroy", "sb_last_error", "sb_set_scene", "sb_set_camera",
     "sb_set_camera_matrices", "sb_set_settings", "sb_reset_accumulation", "sb_subframe_index",
     "sb_buffer_create", "sb_buffer_destroy", "sb_buffer_resize", "sb_buffer_map", "sb_buffer_unmap", "sb_buffer_map_async", "sb_buffer_map_wait",
     "sb_buffer_host_ptr", "sb_buffer_host_size", "sb_buffer_device_ptr", "sb_buffer_width", "sb_buffer_height",
     "sb_render", "sb_render_iterations", "sb_synchronize", "sb_accum_device_ptr", "sb_resolve",
+    "sb_comm_get_unique_id", "sb_comm_init", "sb_comm_destroy", "sb_comm_world", "sb_render_sharded",
     "sb_get_counters", "sb_reset_counters", "sb_test_sampler", "sb_test_light_sample", "sb_test_trace",
 ]
+SB_COMM_ID_BYTES = 128
+SB_API_VERSION = 2
 
 _lib = None
 
@@ -167,6 +178,8 @@ def load_library() -> C.CDLL:
     vp, u32, u64, f32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_float
     P = C.POINTER
     sig = {
+        "sb_abi_version": (u32, []),
+        "sb_abi_struct_size": (u32, [u32]),
         "sb_settings_default": (None, [P(sb_settings)]),
         "sb_create": (C.c_int, [P(sb_device_cfg), P(vp)]),
         "sb_set_stream": (C.c_int, [vp, vp]),
@@ -195,6 +208,11 @@ def load_library() -> C.CDLL:
         "sb_synchronize": (C.c_int, [vp]),
         "sb_accum_device_ptr": (vp, [vp, P(u64)]),
         "sb_resolve": (C.c_int, [vp, vp, u32]),
+        "sb_comm_get_unique_id": (C.c_int, [vp]),
+        "sb_comm_init": (C.c_int, [vp, vp, u32, u32]),
+        "sb_comm_destroy": (C.c_int, [vp]),
+        "sb_comm_world": (u32, [vp]),
+        "sb_render_sharded": (C.c_int, [vp, vp, u32]),
         "sb_get_counters": (C.c_int, [vp, P(sb_counters)]),
         "sb_reset_counters": (C.c_int, [vp]),
         "sb_test_sampler": (C.c_int, [vp, u32, vp, vp, vp, vp, vp, vp, vp]),
@@ -205,6 +223,15 @@ def load_library() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    # layout handshake: a stale library (or a drifted mirror in this file) must not be driven
+    mirrors = [C.sizeof(sb_settings), C.sizeof(sb_device_cfg), C.sizeof(sb_counters), C.sizeof(sb_scene_view), MATERIAL_DTYPE.itemsize,
+               LIGHT_DTYPE.itemsize, INSTANCE_DTYPE.itemsize, VERTEX_DTYPE.itemsize, HIT_DTYPE.itemsize, MESH_DTYPE.itemsize,
+               CURVE_DTYPE.itemsize, C.sizeof(sb_texture)]
+    if lib.sb_abi_version() != SB_API_VERSION:
+        raise SbError(f"{path} implements ABI version {lib.sb_abi_version()}, this package expects {SB_API_VERSION}: rebuild it")
+    for which, size in enumerate(mirrors):
+        if lib.sb_abi_struct_size(which) != size:
+            raise SbError(f"ABI struct {which}: library says {lib.sb_abi_struct_size(which)} bytes, the Python mirror {size}")
     _lib = lib
     return lib
 

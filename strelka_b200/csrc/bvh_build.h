@@ -17,6 +17,8 @@
 #include "traverse.cuh"
 #include "../../include/sb/sb_api.h"
 #include <algorithm>
+#include <stdexcept>
+#include <string>
 #include <utility>
 #include <vector>
 
@@ -66,6 +68,7 @@ struct SceneDev
     WideNode* triNodes = nullptr;
     WideNode* segNodes = nullptr;
     uint32_t numTris = 0, numSegs = 0, numTriNodes = 0, numSegNodes = 0;
+    uint32_t triDepth = 0, segDepth = 0; // levels of the two wide BVHs (<= kStackSize, checked by the builder)
     bool onlyRectLights = false; // every light is a rect light (with rectLightSamplingMethod 0 the shade kernel keeps only that sampler)
     bool anyPreviewMaterial = true; // false: every material is a diffuse one (the shade kernel drops the UsdPreviewSurface code)
 };
@@ -84,6 +87,7 @@ struct WideBvh
     uint32_t numNodes = 0;
     uint32_t* primOrder = nullptr; // leaf-order position -> index into the unsorted primitive list
     uint32_t numPrims = 0;
+    uint32_t depth = 0; // levels of wide nodes (root = 1)
 };
 
 // double-precision inverse of an affine 3x4, rounded to float once (same formula as the oracle, so
@@ -282,12 +286,13 @@ inline WideBvh build_wide_bvh(Exec& ex, const Aabb* boxes, uint32_t n, uint32_t 
     rootItem.bvh2Node = root;
     rootItem.wideIndex = 0;
     ex.write(itemsA, rootItem);
-    uint32_t levelCount = 1, nodesUsed = 1, primsUsed = 0;
+    uint32_t levelCount = 1, nodesUsed = 1, primsUsed = 0, levels = 0;
     CollapseItem* curI = itemsA;
     CollapseItem* nxtI = itemsB;
     while (levelCount > 0)
     {
         const uint32_t lc = levelCount;
+        ++levels;
         const CollapseItem* items = curI;
         ex.pfor(lc + 1, SB_LAMBDA(size_t i) {
             if (i == lc)
@@ -343,6 +348,13 @@ inline WideBvh build_wide_bvh(Exec& ex, const Aabb* boxes, uint32_t n, uint32_t 
     out.nodes = wide;
     out.numNodes = nodesUsed;
     out.primOrder = primOrder;
+    out.depth = levels;
+    // The traversal stack holds at most one postponed node group per level above the current node, so a tree of
+    // `levels` levels needs levels - 1 entries: checked HERE, once per build, instead of trusting a counter at run
+    // time (an overflowing stack would silently drop geometry).
+    if (levels > uint32_t(kStackSize))
+        throw std::runtime_error("wide BVH is " + std::to_string(levels) + " levels deep; the traversal stack holds " +
+                                 std::to_string(kStackSize) + " (degenerate geometry? raise kStackSize)");
     return out;
 }
 
@@ -414,6 +426,7 @@ inline void build_scene_bvhs(Exec& ex, SceneDev& S, const uint32_t* instTriFirst
         S.triShade = shade;
         S.triNodes = bvh.nodes;
         S.numTriNodes = bvh.numNodes;
+        S.triDepth = bvh.depth;
     }
     if (numSegs)
     {
@@ -458,6 +471,7 @@ inline void build_scene_bvhs(Exec& ex, SceneDev& S, const uint32_t* instTriFirst
         S.segInfo = info;
         S.segNodes = bvh.nodes;
         S.numSegNodes = bvh.numNodes;
+        S.segDepth = bvh.depth;
     }
 }
 

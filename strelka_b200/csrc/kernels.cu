@@ -654,11 +654,11 @@ __global__ void __launch_bounds__(kBlock, SB_SIMPLE_MIN_BLOCKS) k_shadow_simple(
         atomicAdd(&Q.stats->shadowRays, (unsigned long long)n);
 }
 
-__global__ void __launch_bounds__(256) k_accumulate(FrameParams P, Queues Q, float4* S, float4* direct, float4* aovD, float4* aovS, uint32_t mode,
-                                                    uint32_t subframe)
+__global__ void __launch_bounds__(256) k_accumulate(FrameParams P, Queues Q, AccumTargets A, uint32_t mode, uint32_t subframe, uint32_t launchSamples,
+                                                    uint32_t batchFlags)
 {
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P.nPixPadded; p += gridDim.x * blockDim.x)
-        accumulate_pixel(P, Q, S, direct, aovD, aovS, mode, subframe, p);
+        accumulate_pixel(P, Q, A.S, A.direct, A.aovD, A.aovS, mode, subframe, p, launchSamples, batchFlags, A.scrD, A.scrS);
 }
 
 // format: SB_FORMAT_* of the output buffer
@@ -827,6 +827,98 @@ static void launch_shade_variant(bool a, bool b, bool c, F f)
         with_b(std::false_type());
 }
 
+// Closest-hit stage of bounce `depth` over path queue 0 of `Q` (the caller has already swapped the ping-pong pointers).
+// Camera rays (depth 0) are coherent and a scene of a few nodes is traversed in a few steps: one ray per thread;
+// everything else runs the persistent dynamic-fetch kernel.  Scenes without curves run kernels compiled without the
+// curve phase (the traversal loop is very sensitive to its size and shape).
+void launch_extend_stage(const LaunchCfg& cfg, const FrameParams& P, const SceneDev& S, const Queues& Q, uint32_t depth, bool stats)
+{
+    ScopedStage sc(cfg, kStageExtend);
+    cudaStream_t st = cfg.stream;
+    const bool tiny = (S.numTriNodes + S.numSegNodes) <= kTinyBvhNodes;
+    const bool curves = S.numSegNodes != 0u;
+    const bool persistent = !tiny && depth > 0;
+    if (persistent)
+    {
+        if (curves)
+        {
+            if (stats)
+                k_extend<true, true><<<grid_for(cfg, SB_EXTEND_MIN_BLOCKS), kBlock, 0, st>>>(P, S, Q, depth);
+            else
+                k_extend<false, true><<<grid_for(cfg, SB_EXTEND_MIN_BLOCKS), kBlock, 0, st>>>(P, S, Q, depth);
+        }
+        else
+        {
+            if (stats)
+                k_extend<true, false><<<grid_for(cfg, SB_EXTEND_MIN_BLOCKS), kBlock, 0, st>>>(P, S, Q, depth);
+            else
+                k_extend<false, false><<<grid_for(cfg, SB_EXTEND_MIN_BLOCKS), kBlock, 0, st>>>(P, S, Q, depth);
+        }
+    }
+    else
+    {
+        if (curves)
+        {
+            if (stats)
+                k_extend_simple<true, true><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
+            else
+                k_extend_simple<false, true><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
+        }
+        else
+        {
+            if (stats)
+                k_extend_simple<true, false><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
+            else
+                k_extend_simple<false, false><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
+        }
+    }
+    SB_CUDA_CHECK(cudaGetLastError());
+}
+
+// Any-hit stage over the shadow queue of bounce `depth`.
+void launch_shadow_stage(const LaunchCfg& cfg, const SceneDev& S, const Queues& Q, uint32_t depth, bool stats)
+{
+    ScopedStage sc(cfg, kStageShadow);
+    cudaStream_t st = cfg.stream;
+    const bool tiny = (S.numTriNodes + S.numSegNodes) <= kTinyBvhNodes;
+    const bool curves = S.numSegNodes != 0u;
+    if (!tiny)
+    {
+        if (curves)
+        {
+            if (stats)
+                k_shadow<true, true><<<grid_for(cfg, SB_SHADOW_MIN_BLOCKS), kBlock, 0, st>>>(S, Q, depth);
+            else
+                k_shadow<false, true><<<grid_for(cfg, SB_SHADOW_MIN_BLOCKS), kBlock, 0, st>>>(S, Q, depth);
+        }
+        else
+        {
+            if (stats)
+                k_shadow<true, false><<<grid_for(cfg, SB_SHADOW_MIN_BLOCKS), kBlock, 0, st>>>(S, Q, depth);
+            else
+                k_shadow<false, false><<<grid_for(cfg, SB_SHADOW_MIN_BLOCKS), kBlock, 0, st>>>(S, Q, depth);
+        }
+    }
+    else
+    {
+        if (curves)
+        {
+            if (stats)
+                k_shadow_simple<true, true><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(S, Q, depth);
+            else
+                k_shadow_simple<false, true><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(S, Q, depth);
+        }
+        else
+        {
+            if (stats)
+                k_shadow_simple<true, false><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(S, Q, depth);
+            else
+                k_shadow_simple<false, false><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(S, Q, depth);
+        }
+    }
+    SB_CUDA_CHECK(cudaGetLastError());
+}
+
 void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const SceneDev& S, const Queues& Qbase, bool stats)
 {
     const Queues& Q = Qbase;
@@ -879,47 +971,7 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
             std::swap(Q.thr[0], Q.thr[1]);
         }
         if (depth > 0 || !fusedPrimary)
-        {
-            ScopedStage sc(cfg, kStageExtend);
-            // primary rays are coherent, and a scene of a few nodes is traversed in a few steps: one ray per thread
-            const bool persistent = !tiny && depth > 0;
-            if (persistent)
-            {
-                // scenes without curves run kernels compiled without the curve phase (the traversal loop is very
-                // sensitive to its size and shape)
-                if (curves)
-                {
-                    if (stats)
-                        k_extend<true, true><<<grid_for(cfg, SB_EXTEND_MIN_BLOCKS), kBlock, 0, st>>>(P, S, Q, depth);
-                    else
-                        k_extend<false, true><<<grid_for(cfg, SB_EXTEND_MIN_BLOCKS), kBlock, 0, st>>>(P, S, Q, depth);
-                }
-                else
-                {
-                    if (stats)
-                        k_extend<true, false><<<grid_for(cfg, SB_EXTEND_MIN_BLOCKS), kBlock, 0, st>>>(P, S, Q, depth);
-                    else
-                        k_extend<false, false><<<grid_for(cfg, SB_EXTEND_MIN_BLOCKS), kBlock, 0, st>>>(P, S, Q, depth);
-                }
-            }
-            else
-            {
-                if (curves)
-                {
-                    if (stats)
-                        k_extend_simple<true, true><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
-                    else
-                        k_extend_simple<false, true><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
-                }
-                else
-                {
-                    if (stats)
-                        k_extend_simple<true, false><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
-                    else
-                        k_extend_simple<false, false><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
-                }
-            }
-        }
+            launch_extend_stage(cfg, P, S, Q, depth, stats);
         {
             ScopedStage sc(cfg, kStageShade);
             // the variant without the code paths this scene cannot take
@@ -930,50 +982,16 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
         }
         if (P.debug == 1u)
             break; // debug normals: only the first hit is shaded (OptixRender.cu:151-152)
-        ScopedStage sc(cfg, kStageShadow);
-        if (!tiny)
-        {
-            if (curves)
-            {
-                if (stats)
-                    k_shadow<true, true><<<grid_for(cfg, SB_SHADOW_MIN_BLOCKS), kBlock, 0, st>>>(S, Q, depth);
-                else
-                    k_shadow<false, true><<<grid_for(cfg, SB_SHADOW_MIN_BLOCKS), kBlock, 0, st>>>(S, Q, depth);
-            }
-            else
-            {
-                if (stats)
-                    k_shadow<true, false><<<grid_for(cfg, SB_SHADOW_MIN_BLOCKS), kBlock, 0, st>>>(S, Q, depth);
-                else
-                    k_shadow<false, false><<<grid_for(cfg, SB_SHADOW_MIN_BLOCKS), kBlock, 0, st>>>(S, Q, depth);
-            }
-        }
-        else
-        {
-            if (curves)
-            {
-                if (stats)
-                    k_shadow_simple<true, true><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(S, Q, depth);
-                else
-                    k_shadow_simple<false, true><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(S, Q, depth);
-            }
-            else
-            {
-                if (stats)
-                    k_shadow_simple<true, false><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(S, Q, depth);
-                else
-                    k_shadow_simple<false, false><<<grid_for(cfg, SB_SIMPLE_GRID), kBlock, 0, st>>>(S, Q, depth);
-            }
-        }
+        launch_shadow_stage(cfg, S, Q, depth, stats);
     }
     SB_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_accumulate(const LaunchCfg& cfg, const FrameParams& P, const Queues& Q, float4* S, float4* direct, float4* aovD, float4* aovS,
-                       uint32_t mode, uint32_t subframe)
+void launch_accumulate(const LaunchCfg& cfg, const FrameParams& P, const Queues& Q, const AccumTargets& A, uint32_t mode, uint32_t subframe,
+                       uint32_t launchSamples, uint32_t batchFlags)
 {
     ScopedStage sc(cfg, kStageAccumulate);
-    k_accumulate<<<grid_for(cfg, SB_ACC_GRID), 256, 0, cfg.stream>>>(P, Q, S, direct, aovD, aovS, mode, subframe);
+    k_accumulate<<<grid_for(cfg, SB_ACC_GRID), 256, 0, cfg.stream>>>(P, Q, A, mode, subframe, launchSamples, batchFlags);
     SB_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -1079,6 +1097,81 @@ __global__ void k_test_trace(SceneDev S, uint32_t n, const float* rays, uint32_t
         }
         hits[i] = h;
     }
+}
+
+// ---- sb_test_trace modes 2 / 3: the caller's rays through the REAL queues and the production stage launchers --------
+__global__ void k_test_fill_extend(Queues Q, uint32_t n, const float* rays, uint32_t depth)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const float* r = rays + 8 * size_t(i);
+        Q.rayO[0][i] = mk4(r[0], r[1], r[2], u2f(i));
+        Q.rayD[0][i] = mk4(r[4], r[5], r[6], 0.0f);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        Q.counts[count_path(depth)] = n;
+}
+__global__ void k_test_read_hits(SceneDev S, Queues Q, const uint32_t* instTriFirst, uint32_t n, sb_hit* hits)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const float4 ha = Q.hitA[i];
+        const uint32_t hb = Q.hitB[i];
+        sb_hit h;
+        h.t = ha.x;
+        h.u = ha.y;
+        h.v = ha.z;
+        h.kind = hb >> 30;
+        h.instance = hb & 0x0fffffffu;
+        h.prim = 0u;
+        if (h.kind == 1u)
+            h.prim = f2u(ha.w) - instTriFirst[h.instance]; // global triangle id -> index inside the instance's mesh
+        else if (h.kind == 2u)
+            h.prim = S.segInfo[f2u(ha.w)].prim;
+        hits[i] = h;
+    }
+}
+__global__ void k_test_fill_shadow(Queues Q, uint32_t n, const float* rays, uint32_t depth)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const float* r = rays + 8 * size_t(i);
+        Q.shO[i] = mk4(r[0], r[1], r[2], r[3]);
+        Q.shD[i] = mk4(r[4], r[5], r[6], r[7]);
+        Q.shC[i] = mk4(1.0f, 0.0f, 0.0f, u2f(i));
+        Q.Lacc[i] = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        Q.counts[count_shadow(depth)] = n;
+}
+__global__ void k_test_read_occlusion(Queues Q, uint32_t n, sb_hit* hits)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        sb_hit h = { 0, 0, 0, 0, 0, 0 };
+        h.kind = Q.Lacc[i].x == 0.0f ? 1u : 0u; // the unoccluded ones received their contribution of 1
+        hits[i] = h;
+    }
+}
+
+void launch_test_trace_production(const LaunchCfg& cfg, const FrameParams& P, const SceneDev& S, const Queues& Q, const uint32_t* instTriFirst,
+                                  uint32_t n, const float* rays, uint32_t mode, sb_hit* hits, bool stats)
+{
+    const uint32_t depth = 1u; // any bounce after the camera rays: the dispatch of secondary rays
+    SB_CUDA_CHECK(cudaMemsetAsync(Q.counts, 0, sizeof(uint32_t) * kNumCounts, cfg.stream));
+    if (mode == 2u)
+    {
+        k_test_fill_extend<<<grid_for(cfg, 2), 128, 0, cfg.stream>>>(Q, n, rays, depth);
+        launch_extend_stage(cfg, P, S, Q, depth, stats);
+        k_test_read_hits<<<grid_for(cfg, 2), 128, 0, cfg.stream>>>(S, Q, instTriFirst, n, hits);
+    }
+    else
+    {
+        k_test_fill_shadow<<<grid_for(cfg, 2), 128, 0, cfg.stream>>>(Q, n, rays, depth);
+        launch_shadow_stage(cfg, S, Q, depth, stats);
+        k_test_read_occlusion<<<grid_for(cfg, 2), 128, 0, cfg.stream>>>(Q, n, hits);
+    }
+    SB_CUDA_CHECK(cudaGetLastError());
 }
 
 void launch_test_sampler(const LaunchCfg& cfg, uint32_t n, const uint32_t* x, const uint32_t* y, const uint32_t* sample, const uint32_t* maxs,

@@ -49,8 +49,15 @@ struct LaunchCfg
 uint32_t* upload_sobol_table(cudaStream_t stream); // also returns the device copy of the byte-sliced tables
 // one wavefront batch: raygen, then per bounce extend -> shade -> shadow
 void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const SceneDev& S, const Queues& Q, bool stats);
-void launch_accumulate(const LaunchCfg& cfg, const FrameParams& P, const Queues& Q, float4* S, float4* direct, float4* aovD, float4* aovS,
-                       uint32_t mode, uint32_t subframe);
+// accumulation targets of one frame: S (beauty sum of T(L)), direct (non-accumulated launch result / running linear sum
+// of a multi-batch launch), the two AOV sums and their multi-batch scratch (may be null when a launch fits one batch)
+struct AccumTargets
+{
+    float4 *S, *direct, *aovD, *aovS, *scrD, *scrS;
+};
+// launchSamples / batchFlags: see accumulate_pixel (launches of more samples than one wavefront batch holds)
+void launch_accumulate(const LaunchCfg& cfg, const FrameParams& P, const Queues& Q, const AccumTargets& A, uint32_t mode, uint32_t subframe,
+                       uint32_t launchSamples, uint32_t batchFlags);
 void launch_resolve(const LaunchCfg& cfg, const float4* S, void* out, uint32_t npix, uint32_t n, const float exposure[3], uint32_t tonemapper,
                     float gamma, uint32_t format);
 void launch_copy_image(const LaunchCfg& cfg, const float4* src, void* out, uint32_t npix, uint32_t format, const float exposure[3],
@@ -59,5 +66,11 @@ void launch_test_sampler(const LaunchCfg& cfg, uint32_t n, const uint32_t* x, co
                          const uint32_t* depth, const uint32_t* dim, float* out);
 void launch_test_light_sample(const LaunchCfg& cfg, uint32_t n, const sb_light* lights, const float* hp, const float* u, uint32_t method, float* out);
 void launch_test_trace(const LaunchCfg& cfg, const SceneDev& S, uint32_t n, const float* rays, uint32_t mode, sb_hit* hits);
+// the stages of one bounce as launch_wavefront_batch dispatches them (persistent kernels for secondary rays of non-tiny scenes)
+void launch_extend_stage(const LaunchCfg& cfg, const FrameParams& P, const SceneDev& S, const Queues& Q, uint32_t depth, bool stats);
+void launch_shadow_stage(const LaunchCfg& cfg, const SceneDev& S, const Queues& Q, uint32_t depth, bool stats);
+// sb_test_trace modes 2 (closest hit) / 3 (any hit): caller rays through the real queues and the stage launchers above
+void launch_test_trace_production(const LaunchCfg& cfg, const FrameParams& P, const SceneDev& S, const Queues& Q, const uint32_t* instTriFirst,
+                                  uint32_t n, const float* rays, uint32_t mode, sb_hit* hits, bool stats);
 
 } // namespace sb

@@ -13,6 +13,8 @@
 
 #include <chrono>
 #include <cstdio>
+#include <dlfcn.h>
+#include <nccl.h> // types only: the library is dlopen()ed when a communicator is first asked for (nccl_api below)
 #include <cstring>
 #include <string>
 #include <vector>
@@ -71,11 +73,19 @@ struct sb_ctx
     float4* direct = nullptr; // non-accumulated launch result
     float4* aovD = nullptr; // diffuse / specular AOVs (debug views 2 / 3): count * A in xyz, count in w
     float4* aovS = nullptr;
+    float4* aovScrD = nullptr; // AOV running sums of a launch larger than one wavefront batch (allocated on demand)
+    float4* aovScrS = nullptr;
     Queues Q = {};
     StatCounters* stats = nullptr;
     uint32_t* sobolTab = nullptr;
 
     double buildMs = 0.0, renderMs = 0.0;
+
+    // multi-GPU sample sharding (sb_comm_*): one context = one rank
+    ncclComm_t comm = nullptr;
+    int commRank = 0, commWorld = 1;
+    float4* Sglobal = nullptr; // all-reduced copy of S (S itself stays this rank's partial sum)
+    uint64_t shardRequested = 0; // iterations asked of sb_render_sharded since the last accumulation reset
 };
 
 namespace
@@ -149,6 +159,9 @@ void free_frame(sb_ctx* c)
     dev_free(c->direct);
     dev_free(c->aovD);
     dev_free(c->aovS);
+    dev_free(c->aovScrD);
+    dev_free(c->aovScrS);
+    dev_free(c->Sglobal);
     free_queues(c);
     dev_free(c->Q.counts);
     c->width = c->height = 0;
@@ -239,6 +252,7 @@ uint32_t local_sample_budget(const sb_settings& st)
 void reset_accum(sb_ctx* c)
 {
     c->subframe = 0;
+    c->shardRequested = 0;
     if (c->S)
     {
         const size_t bytes = sizeof(float4) * size_t(c->width) * c->height;
@@ -311,17 +325,27 @@ void render_samples(sb_ctx* c, uint32_t samples, uint32_t mode, bool debugNormal
     const LaunchCfg cfg = launch_cfg(c);
     const uint32_t chunkMax = c->batchPaths / c->nPixPadded;
     uint32_t done = 0;
+    // modes 1/2 form the linear mean of the whole launch (any render/pt/spp, like the reference's samples_per_launch
+    // loop, OptixRender.cu:94-167): a launch larger than one wavefront batch keeps its running sum between batches
+    const bool multiBatchAov = mode != 0u && samples > chunkMax && P.debug >= 2u;
+    if (multiBatchAov && !c->aovScrD)
+    {
+        c->aovScrD = dev_alloc<float4>(size_t(c->width) * c->height);
+        c->aovScrS = dev_alloc<float4>(size_t(c->width) * c->height);
+    }
+    const AccumTargets A = { c->S, c->direct, c->aovD, c->aovS, c->aovScrD, c->aovScrS };
     while (done < samples)
     {
-        // modes 1/2 need the whole launch in one batch to form its linear mean
-        const uint32_t chunk = (mode == 0u) ? std::min(samples - done, chunkMax) : samples;
-        if (chunk > chunkMax)
-            throw std::runtime_error("render/pt/spp larger than the wavefront batch allows; raise sb_device_cfg.max_batch_paths");
+        const uint32_t chunk = std::min(samples - done, chunkMax);
         P.chunk = chunk;
         ensure_queues(c, size_t(c->nPixPadded) * chunk);
         P.sampleBase = st.sample_offset + (c->subframe + done) * P.sampleStride;
         launch_wavefront_batch(cfg, P, c->scene, c->Q, c->trackStats);
-        launch_accumulate(cfg, P, c->Q, c->S, c->direct, c->aovD, c->aovS, mode, c->subframe + done);
+        const uint32_t flags = (done == 0u ? kBatchFirst : 0u) | (done + chunk == samples ? kBatchLast : 0u);
+        if (mode == 0u)
+            launch_accumulate(cfg, P, c->Q, A, 0u, c->subframe + done, chunk, kBatchFirst | kBatchLast);
+        else
+            launch_accumulate(cfg, P, c->Q, A, mode, c->subframe, samples, flags);
         done += chunk;
     }
 }
@@ -405,9 +429,72 @@ void render_impl(sb_ctx* c, sb_buffer* out, uint32_t iterations)
     SB_CUDA_CHECK(cudaEventRecord(c->evStop, c->stream));
 }
 
+// ---- NCCL, loaded on demand ------------------------------------------------------------------------------------
+// A single-GPU host never needs libnccl; a process that already holds one (torch's bundled copy) must share it.
+// dlopen("libnccl.so.2") resolves to the copy already mapped under that SONAME, else to the system one;
+// STRELKA_B200_NCCL names an explicit path.
+struct NcclApi
+{
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GetVersion)(int*) = nullptr;
+};
+NcclApi& nccl_api()
+{
+    static NcclApi api;
+    if (api.handle)
+        return api;
+    const char* env = getenv("STRELKA_B200_NCCL");
+    void* h = dlopen(env && *env ? env : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h)
+        throw std::runtime_error(std::string("multi-GPU rendering needs NCCL: ") + dlerror());
+    auto sym = [&](const char* name) {
+        void* p = dlsym(h, name);
+        if (!p)
+            throw std::runtime_error(std::string("libnccl lacks ") + name);
+        return p;
+    };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    api.GetVersion = reinterpret_cast<decltype(api.GetVersion)>(sym("ncclGetVersion"));
+    api.handle = h;
+    return api;
+}
+void nccl_check(ncclResult_t r, const char* what)
+{
+    if (r != ncclSuccess)
+        throw std::runtime_error(std::string(what) + ": " + nccl_api().GetErrorString(r));
+}
+
+// samples with global index < sppTotal that rank r of `world` owns (indices r, r + world, ...)
+uint32_t shard_budget(uint32_t sppTotal, uint32_t r, uint32_t world)
+{
+    return r >= sppTotal ? 0u : (sppTotal - r + world - 1u) / world;
+}
+
 } // namespace
 
 extern "C" {
+
+uint32_t sb_abi_version(void)
+{
+    return SB_API_VERSION;
+}
+
+uint32_t sb_abi_struct_size(uint32_t which)
+{
+    static const uint32_t sizes[] = { sizeof(sb_settings), sizeof(sb_device_cfg), sizeof(sb_counters), sizeof(sb_scene_view),
+                                      sizeof(sb_material), sizeof(sb_light),      sizeof(sb_instance), sizeof(sb_vertex),
+                                      sizeof(sb_hit),      sizeof(sb_mesh),       sizeof(sb_curve),    sizeof(sb_texture) };
+    return which < sizeof(sizes) / sizeof(sizes[0]) ? sizes[which] : 0u;
+}
 
 void sb_settings_default(sb_settings* s)
 {
@@ -490,6 +577,8 @@ void sb_destroy(sb_ctx* c)
         return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->comm)
+        nccl_api().CommDestroy(c->comm);
     c->timer.release();
     free_scene(c);
     free_frame(c);
@@ -627,10 +716,17 @@ sb_result sb_set_camera_matrices(sb_ctx* c, const float clipToView[16], const fl
     if (!c || !clipToView || !viewToWorld)
         return SB_FAIL;
     SB_API_BEGIN(c)
-    std::memcpy(c->clipToViewRaw, clipToView, sizeof(c->clipToViewRaw));
-    std::memcpy(c->viewToWorld, viewToWorld, sizeof(c->viewToWorld));
-    c->rawMatrices = true;
-    reset_accum(c);
+    // like the reference, which resets only when the matrices differ from the previous frame's (OptixRender.cpp:903-908):
+    // a host that sets raw matrices every frame keeps accumulating while the camera stands still
+    const bool changed = !c->rawMatrices || std::memcmp(c->clipToViewRaw, clipToView, sizeof(c->clipToViewRaw)) != 0 ||
+                         std::memcmp(c->viewToWorld, viewToWorld, sizeof(c->viewToWorld)) != 0;
+    if (changed)
+    {
+        std::memcpy(c->clipToViewRaw, clipToView, sizeof(c->clipToViewRaw));
+        std::memcpy(c->viewToWorld, viewToWorld, sizeof(c->viewToWorld));
+        c->rawMatrices = true;
+        reset_accum(c);
+    }
     SB_API_END
 }
 
@@ -878,6 +974,8 @@ sb_result sb_get_counters(sb_ctx* c, sb_counters* out)
     out->bvh_nodes_tri = c->scene.numTriNodes;
     out->bvh_nodes_curve = c->scene.numSegNodes;
     out->build_ms = c->buildMs;
+    out->bvh_depth_tri = c->scene.triDepth;
+    out->bvh_depth_curve = c->scene.segDepth;
     float ms = 0.0f;
     if (cudaEventElapsedTime(&ms, c->evStart, c->evStop) == cudaSuccess)
         c->renderMs = ms;
@@ -896,6 +994,95 @@ sb_result sb_reset_counters(sb_ctx* c)
     SB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     c->timer.reset();
     c->launchCount = 0;
+    SB_API_END
+}
+
+// ---- multi-GPU: sample-stride sharding + one NCCL sum of S ---------------------------------------
+sb_result sb_comm_get_unique_id(void* idOut)
+{
+    if (!idOut)
+        return SB_FAIL;
+    SB_API_BEGIN(nullptr)
+    static_assert(SB_COMM_ID_BYTES == NCCL_UNIQUE_ID_BYTES, "sb_api.h and nccl.h disagree on the id size");
+    ncclUniqueId id;
+    nccl_check(nccl_api().GetUniqueId(&id), "ncclGetUniqueId");
+    std::memcpy(idOut, &id, sizeof(id));
+    SB_API_END
+}
+
+sb_result sb_comm_init(sb_ctx* c, const void* idBytes, uint32_t rank, uint32_t world)
+{
+    if (!c || !idBytes || world == 0 || rank >= world)
+        return SB_FAIL;
+    SB_API_BEGIN(c)
+    if (c->comm)
+        throw std::runtime_error("sb_comm_init: this context already belongs to a group");
+    ncclUniqueId id;
+    std::memcpy(&id, idBytes, sizeof(id));
+    nccl_check(nccl_api().CommInitRank(&c->comm, int(world), id, int(rank)), "ncclCommInitRank");
+    c->commRank = int(rank);
+    c->commWorld = int(world);
+    // this rank renders the global sample indices rank, rank + world, ... (sampler indices unchanged)
+    c->settings.sample_offset = rank;
+    c->settings.sample_stride = world;
+    reset_accum(c);
+    SB_API_END
+}
+
+sb_result sb_comm_destroy(sb_ctx* c)
+{
+    if (!c)
+        return SB_FAIL;
+    SB_API_BEGIN(c)
+    if (c->comm)
+    {
+        SB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        nccl_api().CommDestroy(c->comm);
+        c->comm = nullptr;
+        c->commRank = 0;
+        c->commWorld = 1;
+        c->settings.sample_offset = 0;
+        c->settings.sample_stride = 1;
+        reset_accum(c);
+    }
+    SB_API_END
+}
+
+uint32_t sb_comm_world(const sb_ctx* c)
+{
+    return c ? uint32_t(c->commWorld) : 0u;
+}
+
+sb_result sb_render_sharded(sb_ctx* c, sb_buffer* out, uint32_t iterations)
+{
+    if (!c)
+        return SB_FAIL;
+    SB_API_BEGIN(c)
+    const sb_settings& st = c->settings;
+    if (st.spp != 1u || st.enable_acc == 0u || st.debug != 0u)
+        throw std::runtime_error("sb_render_sharded: sample sharding needs render/pt/spp 1, enableAcc on and no debug view "
+                                 "(only then is the accumulation a plain sum over samples, SURVEY.md 8e / quirk Q1)");
+    if (st.sample_offset != uint32_t(c->commRank) || st.sample_stride != uint32_t(c->commWorld))
+        throw std::runtime_error("sb_render_sharded: settings.sample_offset / sample_stride must be this context's rank / world size");
+    render_impl(c, out, iterations); // this rank's share: stops at its own budget
+    if (c->commWorld > 1)
+    {
+        // every rank is driven with the same call sequence, so the global sample count needs no exchange
+        c->shardRequested += iterations;
+        uint64_t total = 0;
+        for (int r = 0; r < c->commWorld; ++r)
+            total += std::min<uint64_t>(c->shardRequested, shard_budget(st.spp_total, uint32_t(r), uint32_t(c->commWorld)));
+        const size_t npix = size_t(c->width) * c->height;
+        if (!c->Sglobal)
+            c->Sglobal = dev_alloc<float4>(npix);
+        // out of place: S stays this rank's partial sum, so further calls keep accumulating correctly
+        nccl_check(nccl_api().AllReduce(c->S, c->Sglobal, npix * 4, ncclFloat32, ncclSum, c->comm, c->stream), "ncclAllReduce");
+        const LaunchCfg cfg = launch_cfg(c);
+        float e[3];
+        compute_exposure(st, e);
+        launch_resolve(cfg, c->Sglobal, out->dev, uint32_t(npix), uint32_t(total), e, st.tonemapper_type, st.gamma, out->format);
+        SB_CUDA_CHECK(cudaEventRecord(c->evStop, c->stream));
+    }
     SB_API_END
 }
 
@@ -949,9 +1136,29 @@ sb_result sb_test_trace(sb_ctx* c, uint32_t n, const float* rays, uint32_t mode,
     if (!c->haveScene)
         throw std::runtime_error("sb_test_trace: no scene set");
     cudaStream_t st = c->stream;
+    if (mode > 3u)
+        throw std::runtime_error("sb_test_trace: mode must be 0..3");
     float* dr = dev_upload(rays, size_t(n) * 8, st);
     sb_hit* dh = dev_alloc<sb_hit>(n);
-    launch_test_trace(launch_cfg(c), c->scene, n, dr, mode, dh);
+    if (mode >= 2u)
+    {
+        // the production path: real queue records, the stage launchers of launch_wavefront_batch
+        FrameParams P;
+        std::memset(&P, 0, sizeof(P));
+        P.materialTmin = n ? rays[3] : 0.0f;
+        if (mode == 2u)
+            for (uint32_t i = 0; i < n; ++i)
+                if (rays[8 * size_t(i) + 3] != P.materialTmin || rays[8 * size_t(i) + 7] < 1e16f)
+                    throw std::runtime_error("sb_test_trace mode 2: radiance rays share one tmin and have tmax >= 1e16 (OptixRender.cu:120-129)");
+        ensure_queues(c, n);
+        if (!c->Q.counts)
+            c->Q.counts = dev_alloc<uint32_t>(kNumCounts);
+        c->Q.stats = c->stats;
+        c->Q.sobolTab = c->sobolTab;
+        launch_test_trace_production(launch_cfg(c), P, c->scene, c->Q, c->instTriFirst, n, dr, mode, dh, c->trackStats);
+    }
+    else
+        launch_test_trace(launch_cfg(c), c->scene, n, dr, mode, dh);
     SB_CUDA_CHECK(cudaMemcpyAsync(hits, dh, sizeof(sb_hit) * n, cudaMemcpyDeviceToHost, st));
     SB_CUDA_CHECK(cudaStreamSynchronize(st));
     cudaFree(dr);

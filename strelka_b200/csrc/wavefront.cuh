@@ -617,9 +617,19 @@ SB_HD float3 inverse_tonemap3(const float3& c, const float3& e)
 //  mode 0: S += sum_k T(L_k)                      (spp == 1 per launch: the reference's running mean of T)
 //  mode 1: reference lerp for a launch of `chunk` samples (quirk Q1: weight 1/(subframe+1))
 //  mode 2: no accumulation: `direct` receives the linear mean of the launch
+//  Modes 1 / 2 form the linear mean of the WHOLE launch (render/pt/spp samples).  A launch larger than one wavefront
+//  batch arrives in several calls: batchFlags bit 0 = first batch of the launch, bit 1 = last; launchSamples = samples
+//  of the whole launch.  Between batches the running linear sum waits in `direct` (beauty) and in scrD / scrS (the
+//  AOV sums, w = matching samples so far); the additions happen in the same order as in a single batch, so the
+//  result does not depend on the batch size bit for bit.
+constexpr uint32_t kBatchFirst = 1u, kBatchLast = 2u;
 SB_HD void accumulate_pixel(const FrameParams& P, const Queues& Q, float4* S, float4* direct, float4* aovD, float4* aovS, uint32_t mode,
-                            uint32_t subframe, uint32_t p)
+                            uint32_t subframe, uint32_t p, uint32_t launchSamples = 0u, uint32_t batchFlags = kBatchFirst | kBatchLast,
+                            float4* scrD = nullptr, float4* scrS = nullptr)
 {
+    if (launchSamples == 0u)
+        launchSamples = P.chunk;
+    const bool firstBatch = (batchFlags & kBatchFirst) != 0u, lastBatch = (batchFlags & kBatchLast) != 0u;
     const uint32_t tile = p >> 5, within = p & 31u;
     const uint32_t x = (tile % P.tilesX) * 8u + (within & 7u), y = (tile / P.tilesX) * 4u + (within >> 3);
     if (x >= P.width || y >= P.height)
@@ -654,8 +664,15 @@ SB_HD void accumulate_pixel(const FrameParams& P, const Queues& Q, float4* S, fl
             }
             else
             {
+                float4* scr = which == 0 ? scrD : scrS;
                 float3 mean = mk3(0.0f);
                 uint32_t n = 0;
+                if (!firstBatch)
+                {
+                    const float4 part = scr[lin];
+                    mean = mk3(part);
+                    n = uint32_t(part.w);
+                }
                 for (uint32_t k = 0; k < P.chunk; ++k)
                 {
                     const float4 L = Q.Lacc[k * P.nPixPadded + p];
@@ -664,6 +681,11 @@ SB_HD void accumulate_pixel(const FrameParams& P, const Queues& Q, float4* S, fl
                         mean += mk3(L);
                         ++n;
                     }
+                }
+                if (!lastBatch)
+                {
+                    scr[lin] = mk4(mean, float(n));
+                    continue;
                 }
                 if (n > 0u)
                 {
@@ -688,10 +710,15 @@ SB_HD void accumulate_pixel(const FrameParams& P, const Queues& Q, float4* S, fl
         S[lin] = mk4(s, 0.0f);
         return;
     }
-    float3 result = mk3(0.0f);
+    float3 result = firstBatch ? mk3(0.0f) : mk3(direct[lin]);
     for (uint32_t k = 0; k < P.chunk; ++k)
         result += mk3(Q.Lacc[k * P.nPixPadded + p]);
-    result = result / float(P.chunk);
+    if (!lastBatch)
+    {
+        direct[lin] = mk4(result, 0.0f);
+        return;
+    }
+    result = result / float(launchSamples);
     if (mode == 2u)
     {
         direct[lin] = mk4(result, 1.0f);
@@ -705,7 +732,7 @@ SB_HD void accumulate_pixel(const FrameParams& P, const Queues& Q, float4* S, fl
         const float a = 1.0f / float(subframe + 1u);
         A = lerp(prev, A, a);
     }
-    S[lin] = mk4(A * float(subframe + P.chunk), 0.0f);
+    S[lin] = mk4(A * float(subframe + launchSamples), 0.0f);
 }
 
 // the optional post-process of OptixRender.cpp:1045-1049: tone curve (Tonemappers.cu:17-109), then gamma

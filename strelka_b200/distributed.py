@@ -32,17 +32,32 @@ def allreduce_accumulation(tensor, group=None):
     return tensor
 
 
-def render_sharded(render, buffer, spp_total: int, group=None):
-    """Render this rank's share, all-reduce S over the render's stream and resolve the global image.
+def render_sharded(render, buffer, iterations: int, group=None):
+    """Render this rank's share of `iterations` samples per rank and resolve the global image on every rank.
 
-    `render` must have been put on torch's current stream (Render.set_stream) so that the collective is
-    stream-ordered with the kernels.  Returns the number of samples this rank rendered."""
+    With an sb_comm group on the render (Render.comm_init) everything happens inside the library: NCCL sum of S into
+    a separate buffer on the render's stream, resolve with the global sample count (sb_render_sharded).  Otherwise
+    (torch.distributed group, e.g. the gloo/CPU tests or a host that already owns a process group) S is summed with
+    torch on the current stream, resolved, and RESTORED to this rank's partial sum, so the call can be repeated and
+    later progressive renders keep accumulating correctly.  Returns the samples this rank rendered."""
+    before = render.getSharedContext().mSubframeIndex
+    if render.comm_world() > 1:
+        render.render_sharded(buffer, iterations)
+        return render.getSharedContext().mSubframeIndex - before
     import torch.distributed as dist
 
-    before = render.getSharedContext().mSubframeIndex
-    render.render_iterations(buffer, spp_total)  # stops at this rank's local budget
+    render.render_iterations(buffer, iterations)  # stops at this rank's local budget
     done = render.getSharedContext().mSubframeIndex - before
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        allreduce_accumulation(render.accum_tensor(sync=False), group)
-        render.resolve(buffer, spp_total)
+        import torch
+
+        s_probe = render.accum_tensor(sync=False)
+        count = torch.tensor([float(render.getSharedContext().mSubframeIndex)], dtype=torch.float64, device=s_probe.device)
+        dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
+        n_total = int(count.item())  # samples accumulated over all ranks
+        s_local = render.accum_tensor(sync=False)
+        keep = s_local.clone()
+        allreduce_accumulation(s_local, group)
+        render.resolve(buffer, n_total)
+        s_local.copy_(keep)
     return done

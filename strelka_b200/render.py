@@ -260,6 +260,34 @@ class Render:
 
         return torch.as_tensor(_Wrap(), device=f"cuda:{self._device}")
 
+    def comm_unique_id(self) -> bytes:
+        """ncclGetUniqueId through the ABI (rank 0); hand the bytes to the other ranks out of band."""
+        buf = C.create_string_buffer(_abi.SB_COMM_ID_BYTES)
+        _check(self._lib, None, self._lib.sb_comm_get_unique_id(buf), "sb_comm_get_unique_id")
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int) -> None:
+        """Join the NCCL group (collective).  The settings manager gets the matching sharding keys."""
+        assert len(unique_id) == _abi.SB_COMM_ID_BYTES
+        _check(self._lib, self._ctx, self._lib.sb_comm_init(self._ctx, unique_id, rank, world), "sb_comm_init")
+        sm = self.mSharedCtx.mSettingsManager
+        sm.setAs("render/b200/sampleOffset", int(rank))
+        sm.setAs("render/b200/sampleStride", int(world))
+        self._last_settings = None
+
+    def comm_world(self) -> int:
+        return int(self._lib.sb_comm_world(self._ctx)) if self._ctx else 1
+
+    def comm_destroy(self) -> None:
+        _check(self._lib, self._ctx, self._lib.sb_comm_destroy(self._ctx), "sb_comm_destroy")
+
+    def render_sharded(self, output: Buffer, iterations: int) -> None:
+        """This rank's share of `iterations` samples per rank, NCCL sum of S inside the library, global resolve."""
+        self._sync_inputs()
+        _check(self._lib, self._ctx, self._lib.sb_render_sharded(self._ctx, output._h, iterations), "sb_render_sharded")
+        self.mSharedCtx.mSubframeIndex = self._lib.sb_subframe_index(self._ctx)
+        self.mSharedCtx.mFrameNumber += iterations
+
     def resolve(self, output: Buffer, total_samples: int) -> None:
         _check(self._lib, self._ctx, self._lib.sb_resolve(self._ctx, output._h, total_samples), "sb_resolve")
 

@@ -31,7 +31,12 @@ def test_struct_sizes_match_header():
     # sizes implied by the header (checked against the ctypes/numpy mirrors)
     assert C.sizeof(_abi.sb_settings) == 16 * 4 + 16
     assert C.sizeof(_abi.sb_device_cfg) == 16
-    assert C.sizeof(_abi.sb_counters) == 14 * 8 + 16 + 8 + 8 * 8 + 8 * 8
+    assert C.sizeof(_abi.sb_counters) == 14 * 8 + 16 + 8 + 8 * 8 + 8 * 8 + 16
+    # ... and the sizeof() values the compiled library itself reports (load_library refuses a mismatch)
+    lib = _abi.load_library()
+    assert lib.sb_abi_version() == _abi.SB_API_VERSION
+    assert lib.sb_abi_struct_size(2) == C.sizeof(_abi.sb_counters) and lib.sb_abi_struct_size(3) == C.sizeof(_abi.sb_scene_view)
+    assert lib.sb_abi_struct_size(4) == 96 and lib.sb_abi_struct_size(99) == 0
     assert _abi.VERTEX_DTYPE.itemsize == 32 and _abi.LIGHT_DTYPE.itemsize == 112
     assert _abi.INSTANCE_DTYPE.itemsize == 80 and _abi.MATERIAL_DTYPE.itemsize == 96
 
