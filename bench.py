@@ -1,23 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the B200 path-tracing backend (contract: see README / DESIGN.md).
+"""bench.py -- headline benchmark of the B200 path-tracing backend (contract: README / DESIGN.md section 7).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--scenes c2,c3,c4]
 
-Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): synthetic Cornell box, diffuse + one rect light,
-1024x1024, 256 spp (1 spp per iteration), max depth 4.  One STEP = one complete render of that
-configuration (256 iterations of the hot path over all pixels).
+Headline workload (BASELINE.json configs[4], SURVEY.md 8d "C5", the largest single-GPU configuration):
+synthetic 10.24 M-triangle instanced scene, 3840x2160, max depth 4, sppTotal = 4096 (every sampler index is the real
+one, including the uint32 wrap of quirk Q3).  A full render is 34 G paths; one STEP is a bounded slice of that job: the
+first SLICE = 64 of the 4096 samples of EVERY pixel (531 M camera paths), accumulated, resolved into the output image.
 
-Metric: Mrays/s = (radiance rays + shadow rays actually traced, device counters) / time / 1e6, whole job.
-  value : device time (CUDA events on the render stream), scene + BVH already resident in HBM
-  e2e   : the same metric through the public API with HOST buffers -- scene upload from pinned host
-          memory + on-device BVH build + render + device->host read of the image, wall clock
-N > 1 (torchrun): one process per GPU, each holds a scene/BVH replica and renders a disjoint stride of
-sample indices (rank r: r, r+N, ...), then one NCCL all-reduce of the accumulation buffer S (float4 per
-pixel) + resolve.  Weak scaling: 256 spp per GPU (sppTotal = 256*N).
+Metric: Mrays/s = (radiance + shadow rays actually traced, device counters) / time / 1e6, whole job over all GPUs.
+  value : device time (CUDA events on the render stream; max over ranks), scene + BVH resident in HBM
+  e2e   : the same through the C ABI with HOST buffers: scene upload from pinned host memory, on-device BVH build,
+          render, device->host read of the float4 image; wall clock, max over ranks
+N > 1 (torchrun): STRONG scaling -- the same 64-sample slice is split by sample index (rank r renders r, r+N, ...;
+64/N samples per rank) on scene/BVH replicas; the float4 accumulation buffers S (132.7 MB) are summed with ONE
+ncclAllReduce issued by the library itself on the render stream (sb_render_sharded) and resolved on every rank, all
+inside the timed region.  torch.distributed (gloo) is used only as the control plane: the NCCL id hand-off, barriers
+and the max-over-ranks of the timings.
 
---impl reference: Strelka has no CPU renderer and its OptiX/MDL path cannot be built here,
-so the reference arm times oracle/ (the CPU restatement of the same integrator, all host threads) on a
-bounded sample of the same workload, on rank 0 only.
+Sub-records for the other configs (C2 Cornell, C3 kitchen-scale, C4 hair) are reported under "scenes" with the same
+fields (value, e2e, roofline, cpu_baseline at N = 1).
+
+--impl reference: Strelka has no CPU renderer and its OptiX/MDL path cannot be built here, so the reference
+arm times oracle/ (the CPU restatement of the same integrator, all host threads) on a bounded sample of the same
+workload, on rank 0 only.
 """
 from __future__ import annotations
 
@@ -34,8 +40,26 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-W, H, SPP, DEPTH = 1024, 1024, 256, 4
-WORKLOAD = "C2 cornell 1024x1024 256spp depth4 (BASELINE.json configs[1])"
+HEADLINE = "c5"
+# key -> (description, generator kwargs, samples per step (whole job over all ranks), CPU sample stride)
+CONFIGS = {
+    "c2": dict(desc="C2 cornell 1024x1024 256spp depth4 (BASELINE.json configs[1])", w=1024, h=1024, spp_total=256, depth=4, slice=256, cpu_stride=1,
+               cpu_spp=2),
+    "c3": dict(desc="C3 kitchen-scale 2.05M triangles, 50 UsdPreviewSurface materials, 1920x1080, sppTotal 2048, depth4 (configs[2])", w=1920,
+               h=1080, spp_total=2048, depth=4, slice=32, cpu_stride=2, cpu_spp=1),
+    "c4": dict(desc="C4 hair 1.0M cubic B-spline segments, 1024x1024, sppTotal 1024, depth6 (configs[3])", w=1024, h=1024, spp_total=1024,
+               depth=6, slice=32, cpu_stride=2, cpu_spp=1),
+    "c5": dict(desc="C5 10.24M instanced triangles, 3840x2160, sppTotal 4096, depth4 (BASELINE.json configs[4])", w=3840, h=2160, spp_total=4096,
+               depth=4, slice=64, cpu_stride=4, cpu_spp=1),
+}
+
+
+def make_scene(key):
+    from strelka_b200.scenes import make_cornell, make_hair, make_instanced, make_kitchen
+
+    c = CONFIGS[key]
+    mk = {"c2": make_cornell, "c3": make_kitchen, "c4": make_hair, "c5": make_instanced}[key]
+    return mk(c["w"], c["h"], c["spp_total"], depth=c["depth"])
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -89,7 +113,6 @@ class ClockSampler:
             for n, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        # samples under load = the upper half of the clock readings (the sampler also sees idle gaps)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
@@ -102,235 +125,325 @@ def measured_peaks() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_record(key: str, kernel: str) -> dict:
+    """Per-launch figures of the shipped kernel from the committed `ncu --set full` capture (profiles/ncu_traffic.json):
+    DRAM bytes, L2 throughput, issue-active.  Static evidence, never measured under the benchmark's own timers."""
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(tpath):
+        return {}
+    with open(tpath) as f:
+        return json.load(f).get(key, {}).get(kernel, {})
+
+
 # ---------------------------------------------------------------------------------------------------
+def cpu_sample(key: str, threads: int):
+    """The oracle on the host cores over a bounded sample of config `key`: cpu_spp samples of every cpu_stride-th pixel
+    (in x and y) of the full-resolution pixel grid.  Returns (seconds, rays, paths, description)."""
+    import numpy as np
+
+    from oracle import pyoracle
+
+    c = CONFIGS[key]
+    scene, settings, (w, h) = make_scene(key)
+    t0 = time.perf_counter()
+    osc = pyoracle.OracleScene(scene)
+    build_s = time.perf_counter() - t0
+    xs, ys = np.meshgrid(np.arange(0, w, c["cpu_stride"]), np.arange(0, h, c["cpu_stride"]))
+    xs = np.tile(xs.reshape(-1), c["cpu_spp"])
+    ys = np.tile(ys.reshape(-1), c["cpu_spp"])
+    smp = np.repeat(np.arange(c["cpu_spp"]), len(xs) // c["cpu_spp"])
+    desc = (f"{c['cpu_spp']} of {c['spp_total']} spp over every {c['cpu_stride']}th pixel in x and y of the {w}x{h} grid "
+            f"({len(xs)} paths; Mrays/s does not depend on the sample size)")
+
+    def run():
+        cnt = {}
+        t = time.perf_counter()
+        osc.path_radiance(settings, w, h, xs, ys, smp, threads=threads, counters=cnt)
+        return time.perf_counter() - t, cnt["radiance_rays"] + cnt["shadow_rays"], cnt["paths"]
+
+    return run, desc, build_s, osc
+
+
 def run_reference(args) -> None:
-    """CPU arm: the oracle on the host cores, bounded sample of the same workload, rank 0 only."""
+    """CPU arm: the oracle on the host cores, bounded sample of the headline workload per step, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import pyoracle
-    from strelka_b200.scenes import make_cornell
-
     cores = os.cpu_count() or 1
-    scene, settings, _ = make_cornell(W, H, spp_total=SPP, depth=DEPTH)
-    osc = pyoracle.OracleScene(scene)
-    sample_spp = 2  # bounded sample per step: 2 of the 256 samples of every pixel (sample indices 0,1)
-    times, rays = [], 0
+    c = CONFIGS[HEADLINE]
+    run, sample, build_s, osc = cpu_sample(HEADLINE, cores)
+    times, rays, paths = [], 0, 0
     for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        _, _, _, cnt = osc.render(settings, W, H, sample_spp, threads=cores)
-        dt = time.perf_counter() - t0
+        dt, rays, paths = run()
         if i >= args.warmup:
             times.append(dt)
-            rays = cnt["radiance_rays"] + cnt["shadow_rays"]
+    osc.close()
     ms = 1e3 * sum(times) / len(times)
     value = rays / (ms * 1e-3) / 1e6
-    sample = f"{sample_spp} of {SPP} spp over all {W}x{H} pixels per step (throughput is spp-independent)"
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "width": W, "height": H, "spp": SPP, "depth": DEPTH, "sample": sample},
-        "spp_mpix_per_s": W * H * sample_spp / (ms * 1e-3) / 1e6,
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": c["desc"], "width": c["w"], "height": c["h"], "spp_total": c["spp_total"], "depth": c["depth"], "sample": sample},
+        "spp_mpix_per_s": paths / (ms * 1e-3) / 1e6,
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample, "bvh2_build_s": build_s},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference OptiX/MDL path unbuildable here (SURVEY 8c); this is the CPU oracle port of the same integrator",
+        "note": "reference OptiX/MDL path unbuildable here (SURVEY 8c); this is the CPU oracle port of the same integrator: a scalar "
+                "BVH2 walker, a stated baseline and not a tuned CPU ray tracer",
     }
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------
-def run_b200(args) -> None:
-    import numpy as np
-    import torch
+class Harness:
+    """One process = one rank = one GPU."""
 
-    from strelka_b200 import BufferDesc, BufferFormat, RenderFactory, RenderType, SharedContext
-    from strelka_b200.scenes import make_cornell
+    def __init__(self):
+        import torch
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the B200 backend has no CPU fallback")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the B200 backend has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
 
-        dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            self.dist = dist
+            dist.init_process_group("gloo")  # control plane only; the data plane is the library's own NCCL communicator
+        self.stream = torch.cuda.Stream()  # the render stream: kernels, NCCL and the timing events share it
+        torch.cuda.set_stream(self.stream)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
-    spp_total = SPP * world  # weak scaling: 256 samples per pixel per GPU
-    scene, settings, _ = make_cornell(W, H, spp_total=spp_total, depth=DEPTH)
-    settings.setAs("render/b200/sampleOffset", rank)
-    settings.setAs("render/b200/sampleStride", world)
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
 
-    def make_render(**kw):
-        r = RenderFactory.createRender(RenderType.eCompute, device=local, **kw)
+    def max_over_ranks(self, vals):
+        if self.dist is None:
+            return list(vals)
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def sum_over_ranks(self, vals):
+        if self.dist is None:
+            return list(vals)
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64)
+        self.dist.all_reduce(t)
+        return [float(x) for x in t]
+
+    def make_render(self, scene, settings, group=True, **kw):
+        from strelka_b200 import RenderFactory, RenderType, SharedContext
+
+        r = RenderFactory.createRender(RenderType.eCompute, device=self.local, **kw)
         r.setScene(scene)
         r.setSharedContext(SharedContext(mSettingsManager=settings))
         r.init()
+        r.set_stream(self.stream.cuda_stream)
+        if group and self.world > 1:
+            uid = [r.comm_unique_id() if self.rank == 0 else None]
+            self.dist.broadcast_object_list(uid, src=0)
+            r.comm_init(uid[0], self.rank, self.world)
         return r
 
-    render = make_render()
-    stream = torch.cuda.Stream()  # a dedicated stream shared by the render, the timing events and NCCL
-    torch.cuda.set_stream(stream)
-    render.set_stream(stream.cuda_stream)
-    buf = render.createBuffer(BufferDesc(W, H, BufferFormat.FLOAT4))
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
+def bench_scene(hx: Harness, key: str, steps: int, warmup: int, with_cpu: bool, sample_clocks: bool) -> dict:
+    """All measurements of one config; returns the record (rank 0) or {}."""
+    import copy
+
+    from strelka_b200 import BufferDesc, BufferFormat
+
+    c = CONFIGS[key]
+    W, H = c["w"], c["h"]
+    world, rank = hx.world, hx.rank
+    per_rank = max(c["slice"] // world, 1)
+    slice_total = per_rank * world
+    scene, settings, _ = make_scene(key)
+    render = hx.make_render(scene, settings)
+    buf = render.createBuffer(BufferDesc(W, H, BufferFormat.FLOAT4))
 
     def one_step():
-        """device-timed step: inputs (scene, BVH, camera, settings) already resident"""
+        """device-timed step: scene, BVH, camera and settings already resident"""
         render.reset_accumulation()
-        render.render_iterations(buf, SPP)
-        if dist is not None:
-            s_acc = render.accum_tensor_nosync()
-            dist.all_reduce(s_acc)
-            render.resolve(buf, spp_total)
+        if world > 1:
+            render.render_sharded(buf, per_rank)  # own share + ncclAllReduce(S) + global resolve, all on the render stream
+        else:
+            render.render_iterations(buf, per_rank)
 
-    # first call uploads the scene and builds the BVH (not part of `value`)
-    render.render_iterations(buf, 1)
+    one_step()  # first call: scene upload + BVH build (not part of `value`)
     render.synchronize()
-    build_ms = render.counters()["build_ms"]
-
-    for _ in range(args.warmup):
+    build_ms_first = render.counters()["build_ms"]
+    for _ in range(warmup):
         one_step()
-    barrier()
+    hx.barrier()
     render.reset_counters()
-    clocks = ClockSampler(local)
-    if rank == 0:
+    clocks = ClockSampler(hx.local) if (sample_clocks and rank == 0) else None
+    if clocks:
         clocks.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
+    torch = hx.torch
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    hx.barrier()
     t_wall0 = time.perf_counter()
     for a, b in ev:
-        flush.fill_(1)  # L2 flush between timed iterations (outside the event bracket)
-        a.record(stream)
+        hx.flush.fill_(1)  # L2 flush between timed iterations (outside the event bracket)
+        a.record(hx.stream)
         one_step()
-        b.record(stream)
-    barrier()
+        b.record(hx.stream)
+    hx.barrier()
     t_wall = time.perf_counter() - t_wall0
-    clk = clocks.stop() if rank == 0 else None
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
-    c = render.counters()
-    rays_step = (c["radiance_rays"] + c["shadow_rays"]) / args.steps
-    launches_step = c["kernel_launches"] / args.steps
+    clk = clocks.stop() if clocks else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    cnt = render.counters()
+    rays_step = (cnt["radiance_rays"] + cnt["shadow_rays"]) / steps
+    launches = cnt["kernel_launches"]
 
     # ---- e2e: host buffers in, host image out, through the public API (wall clock) ----------------
     view = scene.view(pinned=True)
     h2d = scene.host_bytes() + 16 * 4 + 4 + 96
     d2h = W * H * 16
-    e2e_times = []
-    for i in range(1 + max(1, args.steps // 2)):
-        barrier()
+    e2e_times, rebuild_ms = [], []
+    for i in range(1 + max(1, min(steps, 3))):
+        hx.barrier()
         t0 = time.perf_counter()
-        render.upload_scene_view(view)  # H2D of all scene arrays + on-device BVH build
-        render.render_iterations(buf, SPP)
-        if dist is not None:
-            dist.all_reduce(render.accum_tensor_nosync())
-            render.resolve(buf, spp_total)
+        render.upload_scene_view(view)  # H2D of all scene arrays + on-device BVH build (resets accumulation)
+        if world > 1:
+            render.render_sharded(buf, per_rank)
+        else:
+            render.render_iterations(buf, per_rank)
         img = buf.map()  # blocking D2H into the pinned mirror
         _ = float(img[0, 0, 0])
-        barrier()
+        dt = time.perf_counter() - t0
+        hx.barrier()
         if i > 0:
-            e2e_times.append(time.perf_counter() - t0)
+            e2e_times.append(dt)
+            rebuild_ms.append(render.counters()["build_ms"])
     e2e_s = sum(e2e_times) / len(e2e_times)
 
-    # ---- max over ranks / sums over ranks -----------------------------------------------------------
-    if dist is not None:
-        t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s = float(t[0]), float(t[1])
-        r_ = torch.tensor([rays_step, launches_step], dtype=torch.float64, device="cuda")
-        dist.all_reduce(r_)
-        rays_total, launches_total = float(r_[0]), float(r_[1])
-    else:
-        rays_total, launches_total = rays_step, launches_step
+    dev_ms, e2e_s = hx.max_over_ranks([dev_ms, e2e_s])
+    rays_total, launches_total = hx.sum_over_ranks([rays_step, launches])
+    buf.destroy()
+    render.destroy()
 
-    roofline = cpu_baseline = None
+    rec = {}
     if rank == 0:
-        # ---- roofline of the dominant kernel: one extra, separately instrumented step --------------
+        value = rays_total / (dev_ms * 1e-3) / 1e6
+        rec = {
+            "workload": c["desc"], "value": value, "unit": "Mrays/s", "ms_per_step": dev_ms,
+            "spp_mpix_per_s": W * H * slice_total / (dev_ms * 1e-3) / 1e6, "rays_per_step": rays_total,
+            "slice": f"samples 0..{slice_total - 1} of {c['spp_total']} per pixel per step ({per_rank} per rank x {world} ranks)",
+            "wall_ms_per_step": 1e3 * t_wall / steps,
+            "bvh_build_ms": {"first_call_cold_context": build_ms_first, "steady_state_from_pinned": statistics.median(rebuild_ms),
+                             "note": "first call = module load + first cudaMallocs + upload from pageable numpy arrays; steady state = "
+                                     "sb_set_scene again on the warm context from pinned host memory (what e2e contains)"},
+            "e2e": {"value": rays_total / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s, "includes": "scene upload from pinned host memory, on-device BVH build, render of the slice"
+                    + (", NCCL all-reduce + resolve" if world > 1 else "") + ", D2H of the float4 image"},
+            "gpu_launches": launches_total, "clocks": clk,
+        }
+    # ---- roofline of the traversal kernels: separately instrumented single-rank passes on rank 0 ---------------
+    if rank == 0:
         hbm, peak_src = measured_peaks()
-        prof = make_render(traversal_stats=True, stage_timers=True)
-        pbuf = prof.createBuffer(BufferDesc(W, H, BufferFormat.FLOAT4))
-        prof.render_iterations(pbuf, 1)
-        prof.reset_accumulation()
-        prof.reset_counters()
-        prof.render_iterations(pbuf, 32)  # 32 of the 256 iterations: same rays per iteration
-        pc = prof.counters()
-        # the timed pass of the stage timers must not carry the statistics atomics: time again without them
-        timed = make_render(stage_timers=True)
-        tbuf = timed.createBuffer(BufferDesc(W, H, BufferFormat.FLOAT4))
-        timed.render_iterations(tbuf, 1)
-        timed.reset_accumulation()
-        timed.reset_counters()
-        timed.render_iterations(tbuf, 32)
-        tc = timed.counters()
+        st1 = copy.deepcopy(settings)
+        st1.setAs("render/b200/sampleOffset", 0)
+        st1.setAs("render/b200/sampleStride", 1)
+        n_prof = min(c["slice"], 8 if key != "c2" else 32)
+
+        def prof_pass(**kw):
+            r = hx.make_render(scene, st1, group=False, **kw)
+            b = r.createBuffer(BufferDesc(W, H, BufferFormat.FLOAT4))
+            r.render_iterations(b, 1)
+            r.reset_accumulation()
+            r.reset_counters()
+            r.render_iterations(b, n_prof)
+            out = r.counters()
+            b.destroy()
+            r.destroy()
+            return out
+
+        pc = prof_pass(traversal_stats=True, stage_timers=True)  # n_node / n_tri / n_seg per ray
+        tc = prof_pass(stage_timers=True)  # per-stage device time WITHOUT the statistics atomics
         stages = ("raygen", "extend", "shade", "shadow", "accumulate", "resolve")
         stage_ms = dict(zip(stages, tc["stage_ms"]))
         stage_n = dict(zip(stages, tc["stage_launches"]))
-        top = max(stages, key=lambda s: stage_ms[s])
         rr, sr = max(pc["radiance_rays"], 1), max(pc["shadow_rays"], 1)
         per_ray = {
             "extend": 80.0 * pc["nodes_visited"] / rr + 48.0 * pc["tris_tested"] / rr + 64.0 * pc["segs_tested"] / rr + 48.0,
             "shadow": 80.0 * pc["nodes_visited_shadow"] / sr + 48.0 * pc["tris_tested_shadow"] / sr + 64.0 * pc["segs_tested_shadow"] / sr + 44.0,
         }
-        trav = top if top in per_ray else "extend"  # the roofline is defined for the traversal kernels (SURVEY 8d)
-        n_rays = tc["radiance_rays"] if trav == "extend" else tc["shadow_rays"]
-        achieved = per_ray[trav] * n_rays / (stage_ms[trav] * 1e-3) / 1e9 if stage_ms[trav] > 0 else 0.0
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                traffic = json.load(f).get("c2", {}).get(f"k_{trav}", {}).get("dram_bytes_per_launch")
-        roofline = {
-            "bound": "hbm", "kernel": f"k_{trav}" + (" (k_primary for the camera rays + k_extend_simple)" if trav == "extend" else ""), "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-            "traffic": traffic, "traffic_unit": "bytes per launch (ncu --set full, profiles/ncu_traffic.json)",
-            "alg_bytes_per_launch": per_ray[trav] * n_rays / max(stage_n[trav], 1),
-            "peak_source": peak_src, "alg_bytes_per_ray": per_ray[trav],
-            "avg_launch_ms": stage_ms[trav] / max(stage_n[trav], 1), "launches": stage_n[trav],
-            "nodes_per_ray": pc["nodes_visited"] / rr, "tris_per_ray": pc["tris_tested"] / rr,
-            "stage_ms_share": {s: stage_ms[s] / max(sum(stage_ms.values()), 1e-9) for s in stages},
-            "note": "scene fits L1/L2 (36 triangles): traversal is issue-bound, bytes are algorithmic (SURVEY 8d), not DRAM traffic",
-        }
-        pbuf.destroy(); prof.destroy(); tbuf.destroy(); timed.destroy()
-        # ---- CPU baseline: the oracle on the host cores, bounded sample ------------------------------
-        from oracle import pyoracle
+        n_rays = {"extend": tc["radiance_rays"], "shadow": tc["shadow_rays"]}
+        total_ms = max(sum(stage_ms.values()), 1e-9)
 
+        def roof(trav):
+            gbs = per_ray[trav] * n_rays[trav] / (stage_ms[trav] * 1e-3) / 1e9 if stage_ms[trav] > 0 else 0.0
+            ncu = ncu_record(key, f"k_{trav}")
+            nl = max(stage_n[trav], 1)
+            out = {"bound": "hbm", "kernel": f"k_{trav}", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                   "traffic": ncu.get("dram_bytes_per_launch"), "alg_bytes_per_launch": per_ray[trav] * n_rays[trav] / nl,
+                   "alg_bytes_per_ray": per_ray[trav], "avg_launch_ms": stage_ms[trav] / nl, "launches": stage_n[trav],
+                   "share_of_step": stage_ms[trav] / total_ms}
+            # what the memory system and the SMs actually did (north_star: achieved L2/HBM GB/s, SM issue utilisation)
+            for k in ("dram_gbs", "dram_frac_of_peak", "l2_gbs", "issue_active_pct", "warp_lanes_active", "source", "launch"):
+                if k in ncu:
+                    out["ncu_" + k] = ncu[k]
+            return out
+
+        top = "extend" if stage_ms["extend"] >= stage_ms["shadow"] else "shadow"
+        rec["roofline"] = roof(top)
+        rec["roofline"]["peak_source"] = peak_src
+        rec["roofline"]["definition"] = ("SURVEY 8(d): algorithmic bytes (80 B/node + 48 B/triangle + 64 B/curve span + ray/hit records, "
+                                         "n measured by the instrumented kernels) / kernel time (CUDA events per launch) / measured HBM copy peak; "
+                                         "the BVH is largely L2-resident, see ncu_* for real DRAM/L2 traffic and issue utilisation")
+        rec["roofline_other"] = roof("shadow" if top == "extend" else "extend")
+        rec["traversal"] = {"nodes_per_ray": pc["nodes_visited"] / rr, "tris_per_ray": pc["tris_tested"] / rr, "segs_per_ray": pc["segs_tested"] / rr,
+                            "nodes_per_shadow_ray": pc["nodes_visited_shadow"] / sr, "stack_overflows": pc["stack_overflows"],
+                            "bvh_depth": max(pc["bvh_depth_tri"], pc["bvh_depth_curve"]), "triangles": pc["num_triangles"],
+                            "curve_spans": pc["num_segments"]}
+        rec["stage_ms_share"] = {s: stage_ms[s] / total_ms for s in stages}
+    # ---- CPU baseline: the oracle on the host cores, bounded sample (rank 0, N = 1 only) -----------------------
+    if rank == 0 and with_cpu:
         cores = os.cpu_count() or 1
-        osc = pyoracle.OracleScene(scene)
-        sample_spp = 4
-        t0 = time.perf_counter()
-        _, _, _, cnt = osc.render(settings, W, H, sample_spp, threads=cores)
-        dt = time.perf_counter() - t0
-        cpu_baseline = {"value": (cnt["radiance_rays"] + cnt["shadow_rays"]) / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                        "sample": f"{sample_spp} of {SPP} spp over all {W}x{H} pixels ({dt:.1f} s)"}
+        run, sample, build_s, osc = cpu_sample(key, cores)
+        dt, rays, _ = run()
+        osc.close()
+        rec["cpu_baseline"] = {"value": rays / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample + f", {dt:.1f} s",
+                               "bvh2_build_s": build_s,
+                               "note": "scalar BVH2 walker of the CPU oracle: a stated baseline, not a tuned CPU ray tracer; the GPU/CPU "
+                                       "ratio says nothing about kernel quality"}
+    return rec
 
+
+def run_b200(args) -> None:
+    hx = Harness()
+    world, rank = hx.world, hx.rank
+    with_cpu = world == 1
+    head = bench_scene(hx, HEADLINE, args.steps, args.warmup, with_cpu, True)
+    scenes = {}
+    for key in [k for k in args.scenes.split(",") if k and k != HEADLINE]:
+        scenes[key] = bench_scene(hx, key, max(2, min(args.steps, 3)), 3, with_cpu, False)
     if rank == 0:
-        value = rays_total / (dev_ms * 1e-3) / 1e6
+        c = CONFIGS[HEADLINE]
         line = {
-            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "width": W, "height": H, "spp_per_gpu": SPP, "spp_total": spp_total, "depth": DEPTH,
-                       "parallelism": f"sample-stride x{world} + NCCL all-reduce of S" if world > 1 else "single GPU",
-                       "l2": "explicit 256 MiB flush between timed steps; per-batch path state (32 spp x 1 Mpix x 180 B = 5.8 GB) also exceeds L2"},
-            "spp_mpix_per_s": W * H * spp_total / (dev_ms * 1e-3) / 1e6,
-            "rays_per_step": rays_total, "wall_ms_per_step": 1e3 * t_wall / args.steps, "bvh_build_ms": build_ms,
-            "e2e": {"value": rays_total / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_s, "includes": "scene upload from pinned host memory, on-device BVH build, render, D2H of the image"},
-            "gpu_launches": launches_total * args.steps,
-            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "metric": "Mrays/s", "value": head["value"], "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": c["desc"] + f"; step = {head['slice']}", "width": c["w"], "height": c["h"], "spp_total": c["spp_total"],
+                       "depth": c["depth"],
+                       "parallelism": (f"sample-stride x{world}: scene/BVH replicas, ncclAllReduce of the 132.7 MB float4 S buffer + resolve "
+                                       "inside the timed region (sb_render_sharded)") if world > 1 else "single GPU",
+                       "l2": "explicit 256 MiB flush between timed steps; the per-batch path state (4 spp x 8.3 Mpix x 180 B = 6 GB) also exceeds L2"},
+            "spp_mpix_per_s": head["spp_mpix_per_s"], "rays_per_step": head["rays_per_step"], "wall_ms_per_step": head["wall_ms_per_step"],
+            "bvh_build_ms": head["bvh_build_ms"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
+            "roofline": head.get("roofline"), "roofline_other": head.get("roofline_other"), "traversal": head.get("traversal"),
+            "stage_ms_share": head.get("stage_ms_share"), "cpu_baseline": head.get("cpu_baseline"), "scenes": scenes,
         }
         print(json.dumps(line), flush=True)
-    buf.destroy()
-    render.destroy()
-    if dist is not None:
-        dist.destroy_process_group()
+    if hx.dist is not None:
+        hx.dist.destroy_process_group()
 
 
 def main() -> None:
@@ -339,6 +452,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scenes", default="c2,c3,c4", help="sub-records besides the headline config (comma list, empty for none)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

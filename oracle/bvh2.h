@@ -7,6 +7,8 @@
 // (equal t -> lower primitive id wins) that the CUDA traversal implements as well.
 #pragma once
 #include "vec.h"
+#include <atomic>
+#include <thread>
 #include <vector>
 #include <numeric>
 #include <limits>
@@ -51,30 +53,27 @@ struct Bvh2
     std::vector<Bvh2Node> nodes;
     std::vector<uint32_t> prims; // permutation of primitive ids
 
-    void build(const std::vector<Aabb>& boxes)
+    struct Task
     {
-        const uint32_t n = uint32_t(boxes.size());
-        nodes.clear();
-        prims.resize(n);
-        std::iota(prims.begin(), prims.end(), 0u);
-        if (n == 0)
-            return;
-        std::vector<f3> cent(n);
-        for (uint32_t i = 0; i < n; ++i)
-            cent[i] = (boxes[i].lo + boxes[i].hi) * 0.5f;
-        nodes.reserve(2 * n);
-        nodes.push_back(Bvh2Node{});
-        struct Task
-        {
-            uint32_t node, first, count;
-        };
-        std::vector<Task> stack;
-        stack.push_back(Task{ 0, 0, n });
+        uint32_t node, first, count;
+    };
+
+    // Top-down binned-SAH construction of the subtrees in `stack` into `out` (children appended at out.size()).
+    // Tasks of at most `deferBelow` primitives are not built but moved to `deferred` (parallel build, below).
+    void build_tasks(std::vector<Bvh2Node>& out, std::vector<Task>& stack, const std::vector<Aabb>& boxes, const std::vector<f3>& cent,
+                     uint32_t deferBelow, std::vector<Task>* deferred)
+    {
+        auto& nodes = out;
         constexpr int kBins = 16;
         while (!stack.empty())
         {
             const Task t = stack.back();
             stack.pop_back();
+            if (deferred && t.count <= deferBelow)
+            {
+                deferred->push_back(t);
+                continue;
+            }
             Aabb box, cbox;
             box.reset();
             cbox.reset();
@@ -178,6 +177,71 @@ struct Bvh2
             nodes[t.node].count = 0;
             stack.push_back(Task{ l, t.first, mid - t.first });
             stack.push_back(Task{ l + 1, mid, t.first + t.count - mid });
+        }
+    }
+
+    // The tree is built top-down; subtrees are independent, so the top of the tree is built serially until the open
+    // subtrees are small, then those are built on all host threads into private node arrays and appended.  Hits do
+    // not depend on the node order (exact tie-break on the primitive id), only the build time does.
+    void build(const std::vector<Aabb>& boxes)
+    {
+        const uint32_t n = uint32_t(boxes.size());
+        nodes.clear();
+        prims.resize(n);
+        std::iota(prims.begin(), prims.end(), 0u);
+        if (n == 0)
+            return;
+        std::vector<f3> cent(n);
+        for (uint32_t i = 0; i < n; ++i)
+            cent[i] = (boxes[i].lo + boxes[i].hi) * 0.5f;
+        nodes.reserve(2 * size_t(n));
+        nodes.push_back(Bvh2Node{});
+        std::vector<Task> stack, deferred;
+        stack.push_back(Task{ 0, 0, n });
+        unsigned nthreads = std::thread::hardware_concurrency();
+        if (nthreads == 0)
+            nthreads = 1;
+        if (n < 50000u || nthreads == 1)
+        {
+            build_tasks(nodes, stack, boxes, cent, 0u, nullptr);
+            return;
+        }
+        build_tasks(nodes, stack, boxes, cent, std::max<uint32_t>(n / (8u * nthreads), 1024u), &deferred);
+        std::vector<std::vector<Bvh2Node>> sub(deferred.size());
+        std::atomic<size_t> next{ 0 };
+        auto work = [&]() {
+            for (;;)
+            {
+                const size_t k = next.fetch_add(1);
+                if (k >= deferred.size())
+                    return;
+                std::vector<Bvh2Node>& loc = sub[k];
+                loc.reserve(2 * size_t(deferred[k].count));
+                loc.push_back(Bvh2Node{});
+                std::vector<Task> st;
+                st.push_back(Task{ 0, deferred[k].first, deferred[k].count });
+                build_tasks(loc, st, boxes, cent, 0u, nullptr);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < nthreads; ++t)
+            pool.emplace_back(work);
+        work();
+        for (auto& th : pool)
+            th.join();
+        for (size_t k = 0; k < deferred.size(); ++k)
+        {
+            // sub[k][0] is the subtree root (already allocated as nodes[deferred[k].node]); sub[k][i >= 1] lands at base + i - 1
+            const uint32_t base = uint32_t(nodes.size());
+            auto fix = [&](Bvh2Node nd) {
+                if (nd.count == 0)
+                    nd.left += base - 1u;
+                return nd;
+            };
+            nodes[deferred[k].node] = fix(sub[k][0]);
+            for (size_t i = 1; i < sub[k].size(); ++i)
+                nodes.push_back(fix(sub[k][i]));
+            sub[k] = std::vector<Bvh2Node>();
         }
     }
 

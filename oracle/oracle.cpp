@@ -912,9 +912,10 @@ uint32_t orc_render(const orc_scene* scene, const sb_settings* st, const float* 
 }
 
 // Individual radiance samples (before accumulation) for a list of (x, y, sampleIndex): 3 floats each.
+// nthreads <= 0: all host threads.  counters (optional) [paths, radiance rays, shadow rays] are added to.
 void orc_path_radiance(const orc_scene* scene, const sb_settings* st, const float* clipToView, const float* viewToWorld,
                        uint32_t width, uint32_t height, uint32_t n, const uint32_t* xs, const uint32_t* ys,
-                       const uint32_t* samples, float* out)
+                       const uint32_t* samples, float* out, int nthreads, uint64_t* counters)
 {
     RenderParams P;
     P.scene = scene;
@@ -924,14 +925,41 @@ void orc_path_radiance(const orc_scene* scene, const sb_settings* st, const floa
     P.width = width;
     P.height = height;
     P.exposure = compute_exposure(*st);
-    Counters cnt;
-    for (uint32_t i = 0; i < n; ++i)
-    {
-        const f3 r = trace_path(P, xs[i], ys[i], samples[i], cnt, nullptr);
-        out[3 * i] = r.x;
-        out[3 * i + 1] = r.y;
-        out[3 * i + 2] = r.z;
-    }
+    if (nthreads <= 0)
+        nthreads = int(std::thread::hardware_concurrency());
+    if (nthreads <= 0)
+        nthreads = 1;
+    std::vector<Counters> cnts(nthreads);
+    std::atomic<uint32_t> next{ 0 };
+    const uint32_t kGrab = 256;
+    auto worker = [&](int tid) {
+        for (;;)
+        {
+            const uint32_t b = next.fetch_add(kGrab);
+            if (b >= n)
+                break;
+            for (uint32_t i = b; i < std::min(n, b + kGrab); ++i)
+            {
+                const f3 r = trace_path(P, xs[i], ys[i], samples[i], cnts[tid], nullptr);
+                out[3 * size_t(i)] = r.x;
+                out[3 * size_t(i) + 1] = r.y;
+                out[3 * size_t(i) + 2] = r.z;
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; ++t)
+        pool.emplace_back(worker, t);
+    worker(0);
+    for (auto& th : pool)
+        th.join();
+    if (counters)
+        for (const Counters& c : cnts)
+        {
+            counters[0] += c.paths;
+            counters[1] += c.radianceRays;
+            counters[2] += c.shadowRays;
+        }
 }
 
 void orc_exposure(const sb_settings* st, float* out3)

@@ -38,7 +38,7 @@ def lib() -> C.CDLL:
         _lib.orc_render.argtypes = [C.c_void_p, C.POINTER(_abi.sb_settings), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                     C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib.orc_path_radiance.argtypes = [C.c_void_p, C.POINTER(_abi.sb_settings), C.c_void_p, C.c_void_p, C.c_uint32,
-                                           C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+                                           C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib.orc_trace.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
         _lib.orc_sampler.argtypes = [C.c_uint32] + [C.c_void_p] * 7
         _lib.orc_light_sample.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
@@ -95,12 +95,18 @@ class OracleScene:
                                _p(counters), threads, _p(aov) if aov is not None else None)
         return image, accum, sub, {"paths": int(counters[0]), "radiance_rays": int(counters[1]), "shadow_rays": int(counters[2])}
 
-    def path_radiance(self, settings, width, height, xs, ys, samples) -> np.ndarray:
+    def path_radiance(self, settings, width, height, xs, ys, samples, threads: int = 0, counters: dict | None = None) -> np.ndarray:
+        """Radiance of individual paths (x, y, sample index) at the given resolution, on `threads` host threads
+        (0 = all).  `counters` (optional dict) receives paths / radiance_rays / shadow_rays."""
         st = settings.to_sb_settings() if hasattr(settings, "to_sb_settings") else settings
         c2v, v2w = self.camera_matrices(width, height)
         xs, ys, samples = [np.ascontiguousarray(a, dtype=np.uint32) for a in (xs, ys, samples)]
         out = np.zeros((len(xs), 3), dtype=np.float32)
-        lib().orc_path_radiance(self._h, C.byref(st), _p(c2v), _p(v2w), width, height, len(xs), _p(xs), _p(ys), _p(samples), _p(out))
+        cnt = np.zeros(3, dtype=np.uint64)
+        lib().orc_path_radiance(self._h, C.byref(st), _p(c2v), _p(v2w), width, height, len(xs), _p(xs), _p(ys), _p(samples), _p(out),
+                                threads, _p(cnt))
+        if counters is not None:
+            counters.update(paths=int(cnt[0]), radiance_rays=int(cnt[1]), shadow_rays=int(cnt[2]))
         return out
 
     def trace(self, rays, mode: int = 0) -> np.ndarray:

@@ -1,0 +1,195 @@
+"""Parity on the BASELINE configs THEMSELVES (full scene size, full resolution), through the production kernels (-m gpu).
+
+Two kinds of checks per config (SURVEY.md 8d "Parity gate"):
+  * hits: 200 k caller rays are written into the real wavefront queues and traced by the stage launchers sb_render uses
+    for secondary rays (sb_test_trace modes 2 / 3: the persistent dynamic-fetch k_extend / k_shadow with their split
+    shared/local stack and refill ballots); (kind, t, u, v, prim, instance) must equal the oracle's BVH2 walk bit for bit.
+  * images: the GPU renders the config at its real resolution and sppTotal (so every sampler index, including the
+    uint32 wrap region of quirk Q3, is the real one); windows of the result are compared with the oracle's radiance for
+    exactly those (x, y, sample) paths.  Gate: relative RMSE <= 1e-3, mean within 0.5 %.
+The oracle builds its BVH2 once per scene (14-70 s of host time each).
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_rmse
+from oracle import pyoracle
+from strelka_b200 import BufferDesc, BufferFormat, SharedContext
+from strelka_b200.scenes import make_cornell, make_hair, make_instanced, make_kitchen
+
+pytestmark = pytest.mark.gpu
+
+RMSE_GATE = 1e-3  # north_star: per-pixel relative RMSE at equal spp
+MEAN_GATE = 5e-3  # north_star: mean within 0.5 %
+
+
+class FullScene:
+    def __init__(self, make):
+        self.scene, self.settings, (self.w, self.h) = make()
+        self.oracle = pyoracle.OracleScene(self.scene)
+
+
+@pytest.fixture(scope="module")
+def c3():
+    f = FullScene(lambda: make_kitchen(1920, 1080, 2048))
+    yield f
+    f.oracle.close()
+
+
+@pytest.fixture(scope="module")
+def c4():
+    f = FullScene(lambda: make_hair(1024, 1024, 1024))
+    yield f
+    f.oracle.close()
+
+
+@pytest.fixture(scope="module")
+def c5():
+    f = FullScene(lambda: make_instanced(3840, 2160, 4096))
+    yield f
+    f.oracle.close()
+
+
+def _rays(n, seed, lo, hi, target=None, spread=0.0, tmax=1e16):
+    """origins uniform in the box [lo, hi]; directions isotropic, or aimed at target + N(0, spread)"""
+    rng = np.random.default_rng(seed)
+    org = rng.uniform(lo, hi, (n, 3))
+    if target is None:
+        d = rng.normal(size=(n, 3))
+    else:
+        d = np.asarray(target) + rng.normal(size=(n, 3)) * spread - org
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    tm = np.full((n, 1), tmax) if np.isscalar(tmax) else np.asarray(tmax).reshape(n, 1)
+    return np.concatenate([org, np.zeros((n, 1)), d, tm], axis=1).astype(np.float32)
+
+
+def _check_hits(r, f, rays, min_hits):
+    r.setScene(f.scene)
+    ho = f.oracle.trace(rays, 0)
+    assert (ho["kind"] != 0).sum() >= min_hits, "ray set misses the scene"
+    hp = r.test_trace(rays, 2)  # production path
+    for k in ("kind", "t", "u", "v", "prim", "instance"):
+        assert np.array_equal(ho[k], hp[k]), f"closest hit field {k} differs from the oracle ({(ho[k] != hp[k]).sum()} rays)"
+    # any-hit: rays cut short at a random fraction of (or beyond) their closest hit
+    rng = np.random.default_rng(99)
+    sh = rays.copy()
+    t = np.where(ho["kind"] != 0, ho["t"], 10.0).astype(np.float32)
+    sh[:, 7] = t * rng.uniform(0.3, 1.7, len(t)).astype(np.float32)
+    so = f.oracle.trace(sh, 1)
+    sp = r.test_trace(sh, 3)
+    assert 0.1 < (so["kind"] != 0).mean() < 0.9
+    assert np.array_equal(so["kind"], sp["kind"]), f"any-hit differs on {(so['kind'] != sp['kind']).sum()} rays"
+    c = r.counters()
+    return c
+
+
+def test_c3_full_size_hits_through_production_kernels(gpu_render, c3):
+    rays = _rays(200_000, 31, (-2.9, -1.4, -2.4), (2.9, 1.4, 2.4))
+    c = _check_hits(gpu_render, c3, rays, 150_000)
+    assert c["num_triangles"] == 400 * 5120 + 12 + 2
+    assert 8 < c["bvh_depth_tri"] <= 32  # deeper than the shared-memory part of the traversal stack: the hand-over is exercised
+
+
+def test_c4_full_size_hits_through_production_kernels(gpu_render, c4):
+    rays = _rays(200_000, 41, (-0.6, -0.4, -0.6), (0.6, 0.6, 0.6), target=(0.0, 0.0, 0.0), spread=0.12)
+    c = _check_hits(gpu_render, c4, rays, 60_000)
+    assert c["num_segments"] == 62_500 * 16 * 8
+    assert 8 < c["bvh_depth_curve"] <= 32
+
+
+def test_c5_full_size_hits_through_production_kernels(gpu_render, c5):
+    rays = _rays(200_000, 51, (-12.0, 0.05, -8.0), (12.0, 12.0, 8.0))
+    c = _check_hits(gpu_render, c5, rays, 120_000)
+    assert c["num_triangles"] == 2000 * 5120 + 2 + 4 * 2
+    assert 8 < c["bvh_depth_tri"] <= 32
+
+
+def _render_full(r, f, iterations):
+    r.setScene(f.scene)
+    r.setSharedContext(SharedContext(mSettingsManager=f.settings))
+    r._last_settings = None
+    r.reset_accumulation()
+    buf = r.createBuffer(BufferDesc(f.w, f.h, BufferFormat.FLOAT4))
+    r.render_iterations(buf, iterations)
+    img = buf.map().copy()
+    buf.destroy()
+    return img
+
+
+def _check_windows(img, f, windows, sample=0):
+    """img: the GPU's 1-spp render (sample index `sample`) at full resolution; windows: (x0, y0, w, h)"""
+    for (x0, y0, ww, wh) in windows:
+        xs, ys = np.meshgrid(np.arange(x0, x0 + ww), np.arange(y0, y0 + wh))
+        xs, ys = xs.reshape(-1), ys.reshape(-1)
+        ref = f.oracle.path_radiance(f.settings, f.w, f.h, xs, ys, np.full(len(xs), sample)).reshape(wh, ww, 3)
+        got = img[y0:y0 + wh, x0:x0 + ww, :3]
+        assert ref.mean() > 0
+        err = rel_rmse(got, ref)
+        assert err <= RMSE_GATE, f"window {(x0, y0, ww, wh)}: relative RMSE {err:.3e}"
+        assert abs(got.mean() / ref.mean() - 1.0) <= MEAN_GATE
+
+
+def test_c2_full_resolution_image_matches_oracle(gpu_render):
+    """configs[1] as BASELINE.json states it except for the sample count: 1024 x 1024, depth 4, 32 of the 256 spp."""
+    s, st, (w, h) = make_cornell(1024, 1024, 256)
+    f = FullScene.__new__(FullScene)
+    f.scene, f.settings, f.w, f.h = s, st, w, h
+    img = _render_full(gpu_render, f, 32)
+    ref, _, _, _ = pyoracle.OracleScene(s).render(st, w, h, 32)
+    err = rel_rmse(img, ref)
+    assert err <= RMSE_GATE, err
+    assert abs(img[..., :3].mean() / ref[..., :3].mean() - 1.0) <= MEAN_GATE
+    # "per-pixel" reading of the gate as well: the RMS over pixels of the per-pixel relative error
+    num = np.linalg.norm(img[..., :3].astype(np.float64) - ref[..., :3], axis=-1)
+    den = np.maximum(np.linalg.norm(ref[..., :3].astype(np.float64), axis=-1), 1e-6)
+    assert np.sqrt(np.mean((num / den) ** 2)) <= RMSE_GATE
+
+
+def test_c3_full_resolution_windows_match_oracle(gpu_render, c3):
+    img = _render_full(gpu_render, c3, 1)  # 1920 x 1080, sppTotal 2048: rows y >= 1024 wrap the sample index (Q3)
+    _check_windows(img, c3, [(832, 412, 256, 256), (100, 1024, 256, 56), (1600, 900, 256, 180)])
+
+
+def test_c4_full_resolution_windows_match_oracle(gpu_render, c4):
+    img = _render_full(gpu_render, c4, 1)  # 1024 x 1024, sppTotal 1024, depth 6 (russian roulette live, Q9)
+    _check_windows(img, c4, [(384, 320, 256, 256), (300, 600, 192, 128)])
+
+
+def test_c5_full_resolution_windows_match_oracle(gpu_render, c5):
+    img = _render_full(gpu_render, c5, 1)  # 3840 x 2160, sppTotal 4096: x >= 1024 or y >= 1024 wrap (Q3)
+    _check_windows(img, c5, [(1792, 952, 256, 256), (900, 1000, 256, 64), (3500, 1900, 256, 200)])
+
+
+def test_launch_larger_than_one_wavefront_batch(gpu_render):
+    """render/pt/spp = 12 with batches of at most 5 samples: the reference lerp (quirk Q1) and the no-accumulation
+    mean must not depend on how the launch is cut into wavefront batches."""
+    from strelka_b200 import RenderFactory, RenderType
+
+    s, st, (w, h) = make_cornell(64, 64, 48)
+    st.setAs("render/pt/spp", 12)
+    imgs = []
+    for max_paths in (0, 64 * 64 * 5):
+        r = RenderFactory.createRender(RenderType.eCompute, max_batch_paths=max_paths)
+        r.init()
+        r.setScene(s)
+        r.setSharedContext(SharedContext(mSettingsManager=st))
+        buf = r.createBuffer(BufferDesc(w, h, BufferFormat.FLOAT4))
+        out = []
+        for acc in (1, 0):
+            st.setAs("render/pt/enableAcc", acc)
+            r.render(buf)
+            r.render(buf)
+            out.append(buf.map().copy())
+        for dbg in (2, 3):
+            st.setAs("render/pt/enableAcc", 1)
+            st.setAs("render/pt/debug", dbg)
+            r.render(buf)
+            r.render(buf)
+            out.append(buf.map().copy())
+        st.setAs("render/pt/debug", 0)
+        imgs.append(out)
+        buf.destroy()
+        r.destroy()
+    for a, b in zip(*imgs):
+        assert a[..., :3].max() > 0
+        assert np.array_equal(a, b)
