@@ -167,6 +167,7 @@ inline WideBvh build_wide_bvh(Exec& ex, const Aabb* boxes, uint32_t n, uint32_t 
         total[0] = b;
     });
 
+    ex.mark("  bounds");
     // ---- Morton codes + sort ---------------------------------------------------------------------
     uint64_t* keys = ex.alloc<uint64_t>(n);
     uint64_t* keysSorted = ex.alloc<uint64_t>(n);
@@ -186,6 +187,7 @@ inline WideBvh build_wide_bvh(Exec& ex, const Aabb* boxes, uint32_t n, uint32_t 
     ex.free(partial);
     ex.free(total);
 
+    ex.mark("  morton + sort");
     // ---- PLOC ----------------------------------------------------------------------------------
     const uint32_t numNodes2 = 2 * n - 1;
     Bvh2Node* nodes = ex.alloc<Bvh2Node>(numNodes2);
@@ -260,6 +262,7 @@ inline WideBvh build_wide_bvh(Exec& ex, const Aabb* boxes, uint32_t n, uint32_t 
         if (merges == 0)
             throw std::runtime_error("PLOC made no progress");
     }
+    ex.mark("  PLOC rounds", (long long)rounds.size());
     const uint32_t root = ex.read(cur); // the last surviving cluster
     ex.free(clusterA);
     ex.free(clusterB);
@@ -273,6 +276,7 @@ inline WideBvh build_wide_bvh(Exec& ex, const Aabb* boxes, uint32_t n, uint32_t 
         ex.pfor(rd.second, SB_LAMBDA(size_t i) { collapse_dp_node(nodes, count, dp, n, maxLeaf, cNode, cPrim, first + uint32_t(i)); });
     }
 
+    ex.mark("  BVH8 cut DP");
     // ---- collapse to 8-wide, level by level --------------------------------------------------------
     // upper bound on wide nodes: every wide node except a degenerate root has >= 2 children and every
     // inner child holds > maxLeaf primitives -> fewer than n nodes; keep it simple and safe.
@@ -330,6 +334,7 @@ inline WideBvh build_wide_bvh(Exec& ex, const Aabb* boxes, uint32_t n, uint32_t 
     if (primsUsed != n)
         throw std::runtime_error("wide BVH lost primitives during collapse");
 
+    ex.mark("  collapse levels", (long long)levels);
     // leaf order -> original primitive index
     uint32_t* primOrder = ex.alloc<uint32_t>(n);
     ex.pfor(n, SB_LAMBDA(size_t i) { primOrder[i] = sorted[primOrder2[i]]; });
@@ -345,6 +350,7 @@ inline WideBvh build_wide_bvh(Exec& ex, const Aabb* boxes, uint32_t n, uint32_t 
     ex.free(count);
     ex.free(sorted);
 
+    ex.mark("  frees");
     out.nodes = wide;
     out.numNodes = nodesUsed;
     out.primOrder = primOrder;
@@ -415,6 +421,7 @@ inline void build_scene_bvhs(Exec& ex, SceneDev& S, const uint32_t* instTriFirst
             aabb_grow(b, p[2]);
             boxes[g] = b;
         });
+        ex.mark("flatten triangles", (long long)numTris);
         WideBvh bvh = build_wide_bvh(ex, boxes, numTris, 3u, kCostNode, kCostTri);
         TriRec* ordered = ex.alloc<TriRec>(numTris);
         const uint32_t* order = bvh.primOrder;
@@ -427,6 +434,7 @@ inline void build_scene_bvhs(Exec& ex, SceneDev& S, const uint32_t* instTriFirst
         S.triNodes = bvh.nodes;
         S.numTriNodes = bvh.numNodes;
         S.triDepth = bvh.depth;
+        ex.mark("reorder triangles");
     }
     if (numSegs)
     {
@@ -453,6 +461,7 @@ inline void build_scene_bvhs(Exec& ex, SceneDev& S, const uint32_t* instTriFirst
             unsorted[g] = r;
             boxes[g] = b;
         });
+        ex.mark("flatten curve spans", (long long)numSegs);
         WideBvh bvh = build_wide_bvh(ex, boxes, numSegs, 1u, kCostNode, kCostSeg);
         SegRec* ordered = ex.alloc<SegRec>(numSegs);
         SegInfo* info = ex.alloc<SegInfo>(numSegs);
@@ -472,6 +481,7 @@ inline void build_scene_bvhs(Exec& ex, SceneDev& S, const uint32_t* instTriFirst
         S.segNodes = bvh.nodes;
         S.numSegNodes = bvh.numNodes;
         S.segDepth = bvh.depth;
+        ex.mark("reorder curve spans");
     }
 }
 

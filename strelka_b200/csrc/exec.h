@@ -7,6 +7,8 @@
 #pragma once
 #include "hd.cuh"
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstddef>
 #include <cstdlib>
 #include <stdexcept>
@@ -121,6 +123,20 @@ struct ExecCuda
         cubTemp = nullptr;
         cubTempBytes = 0;
     }
+    // STRELKA_B200_BUILD_TRACE=1: synchronise at every phase boundary of the builder and print the phase times
+    bool trace = false;
+    std::chrono::steady_clock::time_point traceT0;
+    void mark(const char* what, long long n = -1)
+    {
+        if (!trace)
+            return;
+        cudaStreamSynchronize(stream);
+        const auto now = std::chrono::steady_clock::now();
+        if (what)
+            fprintf(stderr, "[sb build] %-28s %9.3f ms%s\n", what, std::chrono::duration<double, std::milli>(now - traceT0).count(),
+                    n >= 0 ? (" (" + std::to_string(n) + ")").c_str() : "");
+        traceT0 = now;
+    }
 };
 using Exec = ExecCuda;
 #define SB_LAMBDA [=] __host__ __device__
@@ -135,6 +151,7 @@ struct ExecHost
         return static_cast<T*>(std::calloc(n ? n : 1, sizeof(T)));
     }
     void free(void* p) { std::free(p); }
+    void mark(const char*, long long = -1) {}
     template <class F>
     void pfor(size_t n, F f)
     {

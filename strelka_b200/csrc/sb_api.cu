@@ -613,8 +613,21 @@ sb_result sb_set_scene(sb_ctx* c, const sb_scene_view* v)
     const auto t0 = std::chrono::steady_clock::now();
     SB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     free_scene(c);
+    const char* traceEnv = getenv("STRELKA_B200_BUILD_TRACE");
+    const bool trace = traceEnv && *traceEnv && *traceEnv != '0';
+    auto tmark = std::chrono::steady_clock::now();
+    auto hostMark = [&](const char* what) {
+        if (!trace)
+            return;
+        cudaStreamSynchronize(c->stream);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[sb build] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - tmark).count());
+        tmark = now;
+    };
+    hostMark("free previous scene");
     ScenePrep prep;
     prepare_scene(v, prep);
+    hostMark("host prep (validate, instances)");
     const std::vector<InstDev>& inst = prep.inst;
     const std::vector<uint32_t>& triFirst = prep.triFirst;
     const std::vector<SegInfo>& segInfo = prep.segInfo;
@@ -661,11 +674,14 @@ sb_result sb_set_scene(sb_ctx* c, const sb_scene_view* v)
     c->instTriFirst = dev_upload(triFirst.data(), triFirst.size(), st);
     c->segInfoUnsorted = dev_upload(segInfo.data(), segInfo.size(), st);
     SB_CUDA_CHECK(cudaStreamSynchronize(st)); // the host vectors above go out of scope
+    hostMark("uploads");
 
     // ---- createAccelerationStructure (OptixRender.cpp:388-496), the B200 way ---------------------------
     ExecCuda ex;
     ex.stream = st;
     ex.numSms = c->numSms;
+    ex.trace = trace;
+    ex.traceT0 = std::chrono::steady_clock::now();
     try
     {
         build_scene_bvhs(ex, s, c->instTriFirst, uint32_t(numTris), nullptr, uint32_t(segInfo.size()), c->segInfoUnsorted, c->curveSplit);
