@@ -412,6 +412,13 @@ sb_result sb_test_sampler(sb_ctx* ctx, uint32_t n, const uint32_t* x, const uint
 sb_result sb_test_light_sample(sb_ctx* ctx, uint32_t n, const sb_light* lights, const float* hit_points,
                                const float* u, uint32_t method, float* out);
 
+/* The material protocol of closest_hit.cu:474-545 on caller inputs: per item mdlcode_sample(k1, xi) and
+ * mdlcode_evaluate(k1, k2) of material `m` (the device implementations the shade kernel runs).
+ * in : 19 floats per item: shading normal[3], geometric normal[3], tangent_u[3], k1[3], xi[4], k2 for evaluate[3]
+ * out: 15 floats per item: sample k2[3], bsdf_over_pdf[3], pdf, event_type bits; evaluate bsdf_diffuse[3], bsdf_glossy[3]
+ *      (cosine included), pdf */
+sb_result sb_test_bsdf(sb_ctx* ctx, const sb_material* m, uint32_t n, const float* in, float* out);
+
 /* Trace arbitrary rays against the current scene.  rays: 8 floats each (ox,oy,oz,tmin,dx,dy,dz,tmax).
  * mode 0: closest hit with mask 255; mode 1: any hit with mask 3 (shadow) -- one ray per thread, whole traversal.
  * mode 2 / 3: the same two queries through the PRODUCTION path: the rays are written into the wavefront queues and

@@ -10,6 +10,8 @@
 // diffuse model is the Metal backend's Lambert (src/render/metal/shaders/pathtrace.metal:181-201).
 #pragma once
 #include "vec.h"
+#include "../include/sb/sb_api.h"
+#include "hair.h"
 #include "lights.h" // kPi
 #include "../include/sb/sb_api.h"
 
@@ -82,10 +84,11 @@ inline f3 schlick3(const f3& f0, float c)
     const float w = pow5(1.0f - c);
     return f0 + (mk3(1.0f) - f0) * w;
 }
-inline float ggx_d(float a, float nh)
+// see the device file for why sin^2 comes from the cross product
+inline float ggx_d(float a, float nh, float sin2h)
 {
     const float a2 = a * a;
-    const float d = nh * nh * (a2 - 1.0f) + 1.0f;
+    const float d = a2 * nh * nh + sin2h;
     return a2 / (kPi * d * d);
 }
 inline float smith_g1(float a, float nx)
@@ -183,7 +186,9 @@ inline BsdfEval ups_eval_core(const UpsLobes& L, const UpsWeights& w, const f3& 
     const f3 h = normalize(k1 + k2);
     const float nh = std::fmax(dot(n, h), 0.0f);
     const float hk = std::fmax(dot(k1, h), 0.0f);
-    const float ds = ggx_d(L.alpha, nh);
+    const f3 nxh = cross(n, h);
+    const float sin2h = dot(nxh, nxh);
+    const float ds = ggx_d(L.alpha, nh, sin2h);
     const float g1v = smith_g1(L.alpha, nk1);
     const float g1l = smith_g1(L.alpha, nk2);
     const f3 fs = schlick3(L.F0, hk);
@@ -192,7 +197,7 @@ inline BsdfEval ups_eval_core(const UpsLobes& L, const UpsWeights& w, const f3& 
     float pdf = w.ps * (g1v * ds / (4.0f * nk1)) + w.pd * (nk2 / kPi);
     if (L.cc > 0.0f)
     {
-        const float dc = ggx_d(L.ccAlpha, nh);
+        const float dc = ggx_d(L.ccAlpha, nh, sin2h);
         const float c1v = smith_g1(L.ccAlpha, nk1);
         const float c1l = smith_g1(L.ccAlpha, nk2);
         const float fc = L.cc * schlick(0.04f, hk);
@@ -209,9 +214,22 @@ inline BsdfEval ups_eval_core(const UpsLobes& L, const UpsWeights& w, const f3& 
 
 // mdlcode_evaluate stand-in.  n = shading normal, ng = geometric normal (both already flipped by
 // `inside`, closest_hit.cu:405-406), k1 = -ray_dir, k2 = direction to the light.
-inline BsdfEval bsdf_evaluate(const sb_material& m, const f3& n, const f3& ng, const f3& k1, const f3& k2)
+inline BsdfEval bsdf_evaluate(const sb_material& m, const f3& n, const f3& ng, const f3& tangent, const f3& k1, const f3& k2)
 {
     BsdfEval e{ mk3(0.0f), mk3(0.0f), 0.0f };
+    if (m.model == SB_MATERIAL_HAIR)
+    {
+        // fibre scattering (oracle/hair.h, written from the papers in double precision): everything in the glossy slot
+        const hair::Model H(m);
+        const hair::Frame F(tangent, n);
+        double wo[3], wi[3], fc[3], pdf;
+        F.to_local(k1, wo);
+        F.to_local(k2, wi);
+        H.eval(wo, wi, fc, pdf);
+        e.glossy = f3{ float(fc[0]), float(fc[1]), float(fc[2]) };
+        e.pdf = float(pdf);
+        return e;
+    }
     const float nk1 = dot(n, k1);
     const float nk2 = dot(n, k2);
     if (!(nk1 > 0.0f) || !(nk2 > 0.0f) || !(dot(ng, k1) > 0.0f) || !(dot(ng, k2) > 0.0f))
@@ -226,7 +244,7 @@ inline BsdfEval bsdf_evaluate(const sb_material& m, const f3& n, const f3& ng, c
             return e;
         return ups_eval_core(L, w, n, k1, k2, nk1, nk2);
     }
-    // SB_MATERIAL_DIFFUSE (and the first-pass stand-in for SB_MATERIAL_HAIR): Lambert
+    // SB_MATERIAL_DIFFUSE: Lambert
     const f3 c{ m.base_color[0], m.base_color[1], m.base_color[2] };
     e.diffuse = c * (nk2 / kPi);
     e.pdf = nk2 / kPi;
@@ -234,13 +252,31 @@ inline BsdfEval bsdf_evaluate(const sb_material& m, const f3& n, const f3& ng, c
 }
 
 // mdlcode_sample stand-in.  xi = (z1..z4) of closest_hit.cu:510-519.
-inline BsdfSample bsdf_sample(const sb_material& m, const f3& n, const f3& ng, const f3& k1, const f4& xi)
+inline BsdfSample bsdf_sample(const sb_material& m, const f3& n, const f3& ng, const f3& tangent, const f3& k1, const f4& xi)
 {
     BsdfSample s;
     s.k2 = mk3(0.0f);
     s.bsdf_over_pdf = mk3(0.0f);
     s.pdf = 0.0f;
     s.event = EV_ABSORB;
+    if (m.model == SB_MATERIAL_HAIR)
+    {
+        const hair::Model H(m);
+        const hair::Frame F(tangent, n);
+        double wo[3], wi[3], fc[3], pdf;
+        F.to_local(k1, wo);
+        const double u[4] = { xi.x, xi.y, xi.z, xi.w };
+        H.sample(wo, u, wi);
+        H.eval(wo, wi, fc, pdf);
+        if (!(pdf > 0.0))
+            return s;
+        s.k2 = F.to_world(wi);
+        s.pdf = float(pdf);
+        s.bsdf_over_pdf = f3{ float(fc[0] / pdf), float(fc[1] / pdf), float(fc[2] / pdf) };
+        // transmission = leaving through the other side of the geometric surface (inside toggles, closest_hit.cu:591-600)
+        s.event = EV_GLOSSY | (dot(ng, s.k2) >= 0.0f ? EV_REFLECTION : EV_TRANSMISSION);
+        return s;
+    }
     const float nk1 = dot(n, k1);
     if (!(nk1 > 0.0f) || !(dot(ng, k1) > 0.0f))
     {

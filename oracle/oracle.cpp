@@ -538,7 +538,7 @@ void hit_surface(const RenderParams& P, const InstanceData& inst, const Hit& h, 
     }
     const f4 xi{ rnd(kBSDF0, prd.sampler), rnd(kBSDF1, prd.sampler), rnd(kBSDF2, prd.sampler), rnd(kBSDF3, prd.sampler) };
     const f3 k1 = -rayD;
-    const BsdfSample bs = bsdf_sample(mat, sf.normal, sf.geomNormal, k1, xi);
+    const BsdfSample bs = bsdf_sample(mat, sf.normal, sf.geomNormal, sf.tangent, k1, xi);
     if (bs.event == EV_ABSORB)
     {
         if (prd.depth == 0)
@@ -593,7 +593,7 @@ void hit_surface(const RenderParams& P, const InstanceData& inst, const Hit& h, 
         const bool nextEventValid = ((dot(toLight, sf.normal) > 0.0f) != isInside) && lightPdf != 0.0f;
         if (nextEventValid)
         {
-            const BsdfEval ev = bsdf_evaluate(mat, sf.normal, sf.geomNormal, k1, toLight);
+            const BsdfEval ev = bsdf_evaluate(mat, sf.normal, sf.geomNormal, sf.tangent, k1, toLight);
             if (isnan3(ev.diffuse) || isnan3(ev.glossy))
             {
                 prd.radiance = f3{ 10000.0f, 0.0f, 0.0f };
@@ -1126,28 +1126,33 @@ void orc_offset_ray(const float* p, const float* n, float* out)
     out[2] = r.z;
 }
 
-// BSDF hooks: out_sample = k2[3], bsdf_over_pdf[3], pdf, event ; out_eval = diffuse[3], glossy[3], pdf
-void orc_bsdf(const sb_material* m, const float* n, const float* ng, const float* k1, const float* xi, const float* k2eval,
-              float* outSample, float* outEval)
+// BSDF hook, batched.  in: 19 floats per item (n[3], ng[3], tangent[3], k1[3], xi[4], k2 for evaluate[3]);
+// out: 15 floats per item (sample: k2[3], bsdf_over_pdf[3], pdf, event; evaluate: diffuse[3], glossy[3], pdf)
+void orc_bsdf_batch(const sb_material* m, uint32_t n, const float* in, float* out)
 {
-    const f3 N{ n[0], n[1], n[2] }, NG{ ng[0], ng[1], ng[2] }, K1{ k1[0], k1[1], k1[2] };
-    const BsdfSample s = bsdf_sample(*m, N, NG, K1, f4{ xi[0], xi[1], xi[2], xi[3] });
-    outSample[0] = s.k2.x;
-    outSample[1] = s.k2.y;
-    outSample[2] = s.k2.z;
-    outSample[3] = s.bsdf_over_pdf.x;
-    outSample[4] = s.bsdf_over_pdf.y;
-    outSample[5] = s.bsdf_over_pdf.z;
-    outSample[6] = s.pdf;
-    outSample[7] = float(s.event);
-    const BsdfEval e = bsdf_evaluate(*m, N, NG, K1, f3{ k2eval[0], k2eval[1], k2eval[2] });
-    outEval[0] = e.diffuse.x;
-    outEval[1] = e.diffuse.y;
-    outEval[2] = e.diffuse.z;
-    outEval[3] = e.glossy.x;
-    outEval[4] = e.glossy.y;
-    outEval[5] = e.glossy.z;
-    outEval[6] = e.pdf;
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const float* a = in + 19 * size_t(i);
+        float* o = out + 15 * size_t(i);
+        const f3 N{ a[0], a[1], a[2] }, NG{ a[3], a[4], a[5] }, T{ a[6], a[7], a[8] }, K1{ a[9], a[10], a[11] };
+        const BsdfSample s = bsdf_sample(*m, N, NG, T, K1, f4{ a[12], a[13], a[14], a[15] });
+        o[0] = s.k2.x;
+        o[1] = s.k2.y;
+        o[2] = s.k2.z;
+        o[3] = s.bsdf_over_pdf.x;
+        o[4] = s.bsdf_over_pdf.y;
+        o[5] = s.bsdf_over_pdf.z;
+        o[6] = s.pdf;
+        o[7] = float(s.event);
+        const BsdfEval e = bsdf_evaluate(*m, N, NG, T, K1, f3{ a[16], a[17], a[18] });
+        o[8] = e.diffuse.x;
+        o[9] = e.diffuse.y;
+        o[10] = e.diffuse.z;
+        o[11] = e.glossy.x;
+        o[12] = e.glossy.y;
+        o[13] = e.glossy.z;
+        o[14] = e.pdf;
+    }
 }
 
 // Camera matrices as uploaded by the reference (OptixRender.cpp:895-897, 953-954; camera.cpp:61-131):

@@ -50,7 +50,7 @@ def lib() -> C.CDLL:
         _lib.orc_curve_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.orc_curve_intersect_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.orc_offset_ray.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-        _lib.orc_bsdf.argtypes = [C.c_void_p] * 8
+        _lib.orc_bsdf_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib.orc_camera_matrices.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         _lib.orc_postprocess.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_float]
         _lib.orc_exposure.argtypes = [C.POINTER(_abi.sb_settings), C.c_void_p]
@@ -202,13 +202,26 @@ def offset_ray(p, n) -> np.ndarray:
     return out
 
 
-def bsdf(material, n, ng, k1, xi, k2):
+def bsdf_batch(material, n, ng, tangent, k1, xi, k2) -> tuple[np.ndarray, np.ndarray]:
+    """BSDF protocol of closest_hit.cu:474-545 for N items: sample(k1, xi) and evaluate(k1, k2).
+    Inputs broadcast to (N, 3) / (N, 4).  Returns (sample (N, 8): k2, bsdf_over_pdf, pdf, event; eval (N, 7): diffuse, glossy, pdf)."""
     m = np.ascontiguousarray(material, dtype=_abi.MATERIAL_DTYPE)
-    a = [np.ascontiguousarray(v, dtype=np.float32) for v in (n, ng, k1, xi, k2)]
-    s = np.zeros(8, dtype=np.float32)
-    e = np.zeros(7, dtype=np.float32)
-    lib().orc_bsdf(_p(m), *[_p(v) for v in a], _p(s), _p(e))
-    return s, e
+    inp = pack_bsdf_inputs(n, ng, tangent, k1, xi, k2)
+    out = np.zeros((len(inp), 15), dtype=np.float32)
+    lib().orc_bsdf_batch(_p(m), len(inp), _p(inp), _p(out))
+    return out[:, :8], out[:, 8:]
+
+
+def pack_bsdf_inputs(n, ng, tangent, k1, xi, k2) -> np.ndarray:
+    cols = [np.atleast_2d(np.asarray(a, dtype=np.float32)) for a in (n, ng, tangent, k1, xi, k2)]
+    count = max(len(c) for c in cols)
+    cols = [np.broadcast_to(c, (count, c.shape[1])) for c in cols]
+    return np.ascontiguousarray(np.concatenate(cols, axis=1), dtype=np.float32)
+
+
+def bsdf(material, n, ng, k1, xi, k2, tangent=(1.0, 0.0, 0.0)):
+    s, e = bsdf_batch(material, n, ng, tangent, k1, xi, k2)
+    return s[0].copy(), e[0].copy()
 
 
 def postprocess(image, tonemapper_type, exposure, gamma) -> np.ndarray:

@@ -5,6 +5,7 @@
 // (DESIGN.md "Materials") and are checked against the CPU oracle, which states the same formulas.
 #pragma once
 #include "hd.cuh"
+#include "hair.cuh"
 #include "../../include/sb/sb_api.h"
 
 namespace sb
@@ -76,10 +77,13 @@ SB_HD float3 schlick3(const float3& f0, float c)
     const float w = pow5(1.0f - c);
     return f0 + (mk3(1.0f) - f0) * w;
 }
-SB_HD float ggx_d(float a, float nh)
+// GGX normal distribution, D = a^2 / (pi (a^2 cos^2 + sin^2)^2) with sin^2 = |n x h|^2 taken from the cross product:
+// the textbook form cos^2 (a^2 - 1) + 1 cancels catastrophically at the peak of a smooth lobe (a^2 = 1e-4 leaves
+// three digits in fp32 -- found by the independent value pins of tests/test_bsdf_pins.py)
+SB_HD float ggx_d(float a, float nh, float sin2h)
 {
     const float a2 = a * a;
-    const float d = nh * nh * (a2 - 1.0f) + 1.0f;
+    const float d = a2 * nh * nh + sin2h;
     return a2 / (kPi * d * d);
 }
 SB_HD float smith_g1(float a, float nx)
@@ -177,7 +181,9 @@ SB_HD BsdfEval ups_eval_core(const UpsLobes& L, const UpsWeights& w, const float
     const float3 h = normalize(k1 + k2);
     const float nh = fmaxf(dot(n, h), 0.0f);
     const float hk = fmaxf(dot(k1, h), 0.0f);
-    const float ds = ggx_d(L.alpha, nh);
+    const float3 nxh = cross(n, h);
+    const float sin2h = dot(nxh, nxh);
+    const float ds = ggx_d(L.alpha, nh, sin2h);
     const float g1v = smith_g1(L.alpha, nk1);
     const float g1l = smith_g1(L.alpha, nk2);
     const float3 fs = schlick3(L.F0, hk);
@@ -186,7 +192,7 @@ SB_HD BsdfEval ups_eval_core(const UpsLobes& L, const UpsWeights& w, const float
     float pdf = w.ps * (g1v * ds / (4.0f * nk1)) + w.pd * (nk2 / kPi);
     if (L.cc > 0.0f)
     {
-        const float dc = ggx_d(L.ccAlpha, nh);
+        const float dc = ggx_d(L.ccAlpha, nh, sin2h);
         const float c1v = smith_g1(L.ccAlpha, nk1);
         const float c1l = smith_g1(L.ccAlpha, nk2);
         const float fc = L.cc * schlick(0.04f, hk);
@@ -203,14 +209,21 @@ SB_HD BsdfEval ups_eval_core(const UpsLobes& L, const UpsWeights& w, const float
 
 // mdlcode_evaluate stand-in.  n = shading normal, ng = geometric normal (both already flipped by
 // `inside`, closest_hit.cu:405-406), k1 = -ray_dir, k2 = direction to the light.
-// PREVIEW = false compiles the UsdPreviewSurface model out (scenes whose materials are all diffuse)
-template <bool PREVIEW = true>
-SB_HD BsdfEval bsdf_evaluate(const sb_material& m, const float3& n, const float3& ng, const float3& k1, const float3& k2)
+// PREVIEW = false compiles the UsdPreviewSurface model out (scenes whose materials are all diffuse), HAIR = false the
+// hair fibre model (scenes without an SB_MATERIAL_HAIR material).  tangent = state.tangent_u (closest_hit.cu:485).
+template <bool PREVIEW = true, bool HAIR = true>
+SB_HD BsdfEval bsdf_evaluate(const sb_material& m, const float3& n, const float3& ng, const float3& tangent, const float3& k1, const float3& k2)
 {
     BsdfEval e;
     e.diffuse = mk3(0.0f);
     e.glossy = mk3(0.0f);
     e.pdf = 0.0f;
+    if (HAIR && m.model == SB_MATERIAL_HAIR)
+    {
+        // a fibre scatters into the whole sphere: no hemisphere tests (hair.cuh)
+        hair_evaluate(m, n, tangent, k1, k2, e.glossy, e.pdf);
+        return e;
+    }
     const float nk1 = dot(n, k1);
     const float nk2 = dot(n, k2);
     if (!(nk1 > 0.0f) || !(nk2 > 0.0f) || !(dot(ng, k1) > 0.0f) || !(dot(ng, k2) > 0.0f))
@@ -225,7 +238,7 @@ SB_HD BsdfEval bsdf_evaluate(const sb_material& m, const float3& n, const float3
             return e;
         return ups_eval_core(L, w, n, k1, k2, nk1, nk2);
     }
-    // SB_MATERIAL_DIFFUSE (and the first-pass stand-in for SB_MATERIAL_HAIR): Lambert
+    // SB_MATERIAL_DIFFUSE: Lambert
     const float3 c = mk3(m.base_color[0], m.base_color[1], m.base_color[2]);
     e.diffuse = c * (nk2 / kPi);
     e.pdf = nk2 / kPi;
@@ -233,14 +246,20 @@ SB_HD BsdfEval bsdf_evaluate(const sb_material& m, const float3& n, const float3
 }
 
 // mdlcode_sample stand-in.  xi = (z1..z4) of closest_hit.cu:510-519.
-template <bool PREVIEW = true>
-SB_HD BsdfSample bsdf_sample(const sb_material& m, const float3& n, const float3& ng, const float3& k1, const float4& xi)
+template <bool PREVIEW = true, bool HAIR = true>
+SB_HD BsdfSample bsdf_sample(const sb_material& m, const float3& n, const float3& ng, const float3& tangent, const float3& k1, const float4& xi)
 {
     BsdfSample s;
     s.k2 = mk3(0.0f);
     s.bsdf_over_pdf = mk3(0.0f);
     s.pdf = 0.0f;
     s.event = EV_ABSORB;
+    if (HAIR && m.model == SB_MATERIAL_HAIR)
+    {
+        if (hair_sample(m, n, tangent, k1, xi, s.k2, s.bsdf_over_pdf, s.pdf))
+            s.event = EV_GLOSSY | (dot(ng, s.k2) >= 0.0f ? EV_REFLECTION : EV_TRANSMISSION);
+        return s;
+    }
     const float nk1 = dot(n, k1);
     if (!(nk1 > 0.0f) || !(dot(ng, k1) > 0.0f))
     {

@@ -71,6 +71,7 @@ struct SceneDev
     uint32_t triDepth = 0, segDepth = 0; // levels of the two wide BVHs (<= kStackSize, checked by the builder)
     bool onlyRectLights = false; // every light is a rect light (with rectLightSamplingMethod 0 the shade kernel keeps only that sampler)
     bool anyPreviewMaterial = true; // false: every material is a diffuse one (the shade kernel drops the UsdPreviewSurface code)
+    bool anyHairMaterial = false; // true: some material is SB_MATERIAL_HAIR (the shade kernel keeps the fibre BSDF)
 };
 
 // SAH constants of the BVH2 -> BVH8 cut (collapse_dp_node).  Ylitie 2017 uses node : triangle = 1 : 0.3; measured

@@ -48,21 +48,29 @@ struct ExecCuda
     void* cubTemp = nullptr;
     size_t cubTempBytes = 0;
 
+    // Stream-ordered allocation from the device's default memory pool (its release threshold is raised by sb_create,
+    // so freed blocks stay cached): a rebuild re-uses the blocks of the previous one instead of paying cudaMalloc /
+    // cudaFree for every temporary -- measured on the 10 M-triangle scene those calls were up to 550 ms of a build
+    // whose kernels take 80 ms.  Buffers that outlive the build (nodes, records) are later released with cudaFree,
+    // which accepts pool allocations.
     template <class T>
     T* alloc(size_t n)
     {
         void* p = nullptr;
         if (n == 0)
             n = 1;
-        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        cudaError_t e = cudaMallocAsync(&p, n * sizeof(T), stream);
         if (e != cudaSuccess)
+        {
+            cudaGetLastError();
             throw std::bad_alloc();
+        }
         return static_cast<T*>(p);
     }
     void free(void* p)
     {
         if (p)
-            cudaFree(p);
+            cudaFreeAsync(p, stream);
     }
     template <class F>
     void pfor(size_t n, F f)
@@ -79,8 +87,8 @@ struct ExecCuda
         if (bytes > cubTempBytes)
         {
             if (cubTemp)
-                cudaFree(cubTemp);
-            SB_CUDA_CHECK(cudaMalloc(&cubTemp, bytes));
+                cudaFreeAsync(cubTemp, stream);
+            SB_CUDA_CHECK(cudaMallocAsync(&cubTemp, bytes, stream));
             cubTempBytes = bytes;
         }
     }
@@ -119,7 +127,7 @@ struct ExecCuda
     void release()
     {
         if (cubTemp)
-            cudaFree(cubTemp);
+            cudaFreeAsync(cubTemp, stream);
         cubTemp = nullptr;
         cubTempBytes = 0;
     }

@@ -432,7 +432,7 @@ struct StagedSink
 #ifndef SB_SHADE_MIN_BLOCKS
 #define SB_SHADE_MIN_BLOCKS 8 // measured: 64 registers + a few L1 spills beat 111 registers at 25 % occupancy (latency-bound kernel)
 #endif
-template <bool CURVES, bool PREVIEW, bool RECT_UNIFORM>
+template <bool CURVES, bool PREVIEW, bool RECT_UNIFORM, bool HAIR = false>
 __global__ void __launch_bounds__(kBlock, SB_SHADE_MIN_BLOCKS) k_shade(FrameParams P, SceneDev S, Queues Q, uint32_t depth)
 {
     // 12 KB of byte-sliced Sobol tables per CTA (L2-resident source; 6 x 128-bit loads per thread)
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(kBlock, SB_SHADE_MIN_BLOCKS) k_shade(FramePara
                 ps.flags = f2u(th.w);
                 ps.pathId = f2u(ro.w);
                 ps.L = Q.Lacc[ps.pathId];
-                next = shade_bounce<CURVES, PREVIEW, RECT_UNIFORM>(P, S, ps, ha, hb, depth, s_tab, s_unpack, sink);
+                next = shade_bounce<CURVES, PREVIEW, RECT_UNIFORM, HAIR>(P, S, ps, ha, hb, depth, s_tab, s_unpack, sink);
             }
         }
         uint32_t sslot, nslot;
@@ -976,9 +976,18 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
             ScopedStage sc(cfg, kStageShade);
             // the variant without the code paths this scene cannot take
             const bool preview = S.anyPreviewMaterial, rectUniform = S.onlyRectLights && P.rectMethod == 0u;
-            launch_shade_variant(curves, preview, rectUniform, [&](auto c, auto p, auto r) {
-                k_shade<decltype(c)::value, decltype(p)::value, decltype(r)::value><<<grid_for(cfg, SB_SHADE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
-            });
+            if (S.anyHairMaterial)
+            {
+                // scenes with a hair material run the general variant (curves, every material model)
+                if (rectUniform)
+                    k_shade<true, true, true, true><<<grid_for(cfg, SB_SHADE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
+                else
+                    k_shade<true, true, false, true><<<grid_for(cfg, SB_SHADE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
+            }
+            else
+                launch_shade_variant(curves, preview, rectUniform, [&](auto c, auto p, auto r) {
+                    k_shade<decltype(c)::value, decltype(p)::value, decltype(r)::value><<<grid_for(cfg, SB_SHADE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
+                });
         }
         if (P.debug == 1u)
             break; // debug normals: only the first hit is shaded (OptixRender.cu:151-152)
@@ -1171,6 +1180,39 @@ void launch_test_trace_production(const LaunchCfg& cfg, const FrameParams& P, co
         launch_shadow_stage(cfg, S, Q, depth, stats);
         k_test_read_occlusion<<<grid_for(cfg, 2), 128, 0, cfg.stream>>>(Q, n, hits);
     }
+    SB_CUDA_CHECK(cudaGetLastError());
+}
+
+// sb_test_bsdf: the BSDF protocol (sample + evaluate) on caller inputs; 19 floats in, 15 floats out per item
+__global__ void k_test_bsdf(sb_material m, uint32_t n, const float* in, float* out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const float* a = in + 19 * size_t(i);
+        float* o = out + 15 * size_t(i);
+        const float3 N = mk3(a[0], a[1], a[2]), NG = mk3(a[3], a[4], a[5]), T = mk3(a[6], a[7], a[8]), K1 = mk3(a[9], a[10], a[11]);
+        const BsdfSample s = bsdf_sample<true, true>(m, N, NG, T, K1, mk4(a[12], a[13], a[14], a[15]));
+        o[0] = s.k2.x;
+        o[1] = s.k2.y;
+        o[2] = s.k2.z;
+        o[3] = s.bsdf_over_pdf.x;
+        o[4] = s.bsdf_over_pdf.y;
+        o[5] = s.bsdf_over_pdf.z;
+        o[6] = s.pdf;
+        o[7] = float(s.event);
+        const BsdfEval e = bsdf_evaluate<true, true>(m, N, NG, T, K1, mk3(a[16], a[17], a[18]));
+        o[8] = e.diffuse.x;
+        o[9] = e.diffuse.y;
+        o[10] = e.diffuse.z;
+        o[11] = e.glossy.x;
+        o[12] = e.glossy.y;
+        o[13] = e.glossy.z;
+        o[14] = e.pdf;
+    }
+}
+void launch_test_bsdf(const LaunchCfg& cfg, const sb_material& m, uint32_t n, const float* in, float* out)
+{
+    k_test_bsdf<<<grid_for(cfg, 4), 128, 0, cfg.stream>>>(m, n, in, out);
     SB_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -99,13 +99,25 @@ void dev_free(T*& p)
     p = nullptr;
 }
 
+// scene arrays come from (and return to) the stream-ordered pool, like the builder's temporaries (exec.h)
+template <class T>
+void pool_free(T*& p, cudaStream_t st)
+{
+    if (p)
+        cudaFreeAsync(p, st);
+    p = nullptr;
+}
+
 template <class T>
 T* dev_upload(const T* src, size_t n, cudaStream_t st)
 {
     T* d = nullptr;
     const size_t bytes = (n ? n : 1) * sizeof(T);
-    if (cudaMalloc(&d, bytes) != cudaSuccess)
+    if (cudaMallocAsync(&d, bytes, st) != cudaSuccess)
+    {
+        cudaGetLastError();
         throw std::bad_alloc();
+    }
     if (n)
         SB_CUDA_CHECK(cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
     return d;
@@ -114,24 +126,25 @@ T* dev_upload(const T* src, size_t n, cudaStream_t st)
 void free_scene(sb_ctx* c)
 {
     SceneDev& s = c->scene;
-    dev_free(s.vertices);
-    dev_free(s.indices);
-    dev_free(s.meshes);
-    dev_free(s.curves);
-    dev_free(s.curvePoints);
-    dev_free(s.curveRadii);
-    dev_free(s.curveVertexCounts);
-    dev_free(s.lights);
-    dev_free(s.materials);
-    dev_free(s.instances);
-    dev_free(s.tris);
-    dev_free(s.triShade);
-    dev_free(s.segs);
-    dev_free(s.segInfo);
-    dev_free(s.triNodes);
-    dev_free(s.segNodes);
-    dev_free(c->instTriFirst);
-    dev_free(c->segInfoUnsorted);
+    cudaStream_t st = c->stream; // the callers have synchronised it: nothing still reads these arrays
+    pool_free(s.vertices, st);
+    pool_free(s.indices, st);
+    pool_free(s.meshes, st);
+    pool_free(s.curves, st);
+    pool_free(s.curvePoints, st);
+    pool_free(s.curveRadii, st);
+    pool_free(s.curveVertexCounts, st);
+    pool_free(s.lights, st);
+    pool_free(s.materials, st);
+    pool_free(s.instances, st);
+    pool_free(s.tris, st);
+    pool_free(s.triShade, st);
+    pool_free(s.segs, st);
+    pool_free(s.segInfo, st);
+    pool_free(s.triNodes, st);
+    pool_free(s.segNodes, st);
+    pool_free(c->instTriFirst, st);
+    pool_free(c->segInfoUnsorted, st);
     s = SceneDev();
     c->haveScene = false;
 }
@@ -544,6 +557,16 @@ sb_result sb_create(const sb_device_cfg* cfg, sb_ctx** out)
         cudaDeviceProp prop;
         SB_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
         c->numSms = prop.multiProcessorCount;
+        {
+            // keep freed blocks of the stream-ordered pool (BVH-build temporaries, exec.h) cached across rebuilds
+            cudaMemPool_t pool = nullptr;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+            {
+                uint64_t keep = UINT64_MAX;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            cudaGetLastError();
+        }
         SB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
         c->stream = c->ownStream;
         c->stageTimers = cfg && (cfg->flags & SB_CFG_STAGE_TIMERS);
@@ -665,8 +688,12 @@ sb_result sb_set_scene(sb_ctx* c, const sb_scene_view* v)
     for (uint32_t i = 0; i < v->num_lights; ++i)
         s.onlyRectLights = s.onlyRectLights && v->lights[i].type == 0;
     s.anyPreviewMaterial = false;
+    s.anyHairMaterial = false;
     for (uint32_t i = 0; i < v->num_materials; ++i)
+    {
         s.anyPreviewMaterial = s.anyPreviewMaterial || v->materials[i].model == SB_MATERIAL_USD_PREVIEW_SURFACE;
+        s.anyHairMaterial = s.anyHairMaterial || v->materials[i].model == SB_MATERIAL_HAIR;
+    }
     s.numMeshes = v->num_meshes;
     s.numCurves = v->num_curves;
     s.numCurvePoints = v->num_curve_points;
@@ -1140,6 +1167,22 @@ sb_result sb_test_light_sample(sb_ctx* c, uint32_t n, const sb_light* lights, co
     cudaFree(dl);
     cudaFree(dh);
     cudaFree(du);
+    cudaFree(dout);
+    SB_API_END
+}
+
+sb_result sb_test_bsdf(sb_ctx* c, const sb_material* m, uint32_t n, const float* in, float* out)
+{
+    if (!c || !m || !in || !out)
+        return SB_FAIL;
+    SB_API_BEGIN(c)
+    cudaStream_t st = c->stream;
+    float* din = dev_upload(in, size_t(n) * 19, st);
+    float* dout = dev_alloc<float>(size_t(n) * 15);
+    launch_test_bsdf(launch_cfg(c), *m, n, din, dout);
+    SB_CUDA_CHECK(cudaMemcpyAsync(out, dout, sizeof(float) * 15 * size_t(n), cudaMemcpyDeviceToHost, st));
+    SB_CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFree(din);
     cudaFree(dout);
     SB_API_END
 }

@@ -268,9 +268,9 @@ SB_HD Surface curve_surface(const SceneDev& S, const InstDev& I, uint32_t segInd
 //   sink.radiance_changed(ps)                      ps.L changed (emitter hit, debug view, NaN guard, AOV tag)
 //   sink.shadow_ray(ps, shO, shD, contrib)         trace (origin.xyz + tmin, dir.xyz + tmax); add contrib to L if unoccluded
 // CURVES / PREVIEW = false compile the curve attributes / the UsdPreviewSurface model out for scenes without them,
-// RECT_UNIFORM = true everything but the uniform rect-light sampler (all lights rect, rectLightSamplingMethod 0)
-// (the shade kernel is register-bound; the host picks the variant per scene)
-template <bool CURVES = true, bool PREVIEW = true, bool RECT_UNIFORM = false, class Sink>
+// RECT_UNIFORM = true everything but the uniform rect-light sampler (all lights rect, rectLightSamplingMethod 0),
+// HAIR = false the hair fibre BSDF (the shade kernel is register-bound; the host picks the variant per scene)
+template <bool CURVES = true, bool PREVIEW = true, bool RECT_UNIFORM = false, bool HAIR = true, class Sink>
 SB_HD bool shade_bounce(const FrameParams& P, const SceneDev& S, PathState& ps, const float4& ha, uint32_t hb, uint32_t depth, const uint32_t* sobolTab,
                         const float* unpackLut, Sink& sink)
 {
@@ -339,7 +339,7 @@ SB_HD bool shade_bounce(const FrameParams& P, const SceneDev& S, PathState& ps, 
     // lightPoint = (v[3], v[4]), russian roulette = v[4]
     const Sample5 rn = sampler_sample5(sidx, depth, sobolTab);
     const float3 k1 = -rayD;
-    const BsdfSample bs = bsdf_sample<PREVIEW>(mat, sf.normal, sf.geomNormal, k1, mk4(rn.v[0], rn.v[1], rn.v[2], rn.v[3]));
+    const BsdfSample bs = bsdf_sample<PREVIEW, HAIR>(mat, sf.normal, sf.geomNormal, sf.tangent, k1, mk4(rn.v[0], rn.v[1], rn.v[2], rn.v[3]));
     if (bs.event == EV_ABSORB)
     {
         return false; // throughput = 0 (firstEventType = eAbsorb: counted by neither AOV)
@@ -386,7 +386,7 @@ SB_HD bool shade_bounce(const FrameParams& P, const SceneDev& S, PathState& ps, 
                 const bool nextEventValid = ((dot(ls.L, sf.normal) > 0.0f) != isInside) && lightPdf != 0.0f;
                 if (nextEventValid)
                 {
-                    const BsdfEval ev = bsdf_evaluate<PREVIEW>(mat, sf.normal, sf.geomNormal, k1, ls.L);
+                    const BsdfEval ev = bsdf_evaluate<PREVIEW, HAIR>(mat, sf.normal, sf.geomNormal, sf.tangent, k1, ls.L);
                     if (isnan3(ev.diffuse) || isnan3(ev.glossy))
                     {
                         ps.L = mk4(10000.0f, 0.0f, 0.0f, 0.0f);

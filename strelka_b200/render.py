@@ -311,6 +311,14 @@ class Render:
                "sb_test_light_sample")
         return out
 
+    def test_bsdf(self, material, packed_inputs) -> tuple[np.ndarray, np.ndarray]:
+        """Device BSDF sample + evaluate on (N, 19) packed inputs (n, ng, tangent, k1, xi, k2); returns (sample (N, 8), eval (N, 7))."""
+        m = np.ascontiguousarray(material, dtype=_abi.MATERIAL_DTYPE)
+        inp = np.ascontiguousarray(packed_inputs, dtype=np.float32).reshape(-1, 19)
+        out = np.zeros((len(inp), 15), dtype=np.float32)
+        _check(self._lib, self._ctx, self._lib.sb_test_bsdf(self._ctx, m.ctypes.data, len(inp), inp.ctypes.data, out.ctypes.data), "sb_test_bsdf")
+        return out[:, :8], out[:, 8:]
+
     def test_trace(self, rays, mode: int = 0) -> np.ndarray:
         if not self._scene_uploaded:
             v = self.mScene.view()

@@ -143,6 +143,21 @@ def test_random_scene_render_matches_oracle():
     assert rel_rmse(img_e, img_o) < 1e-5
 
 
+def test_hair_material_render_matches_oracle():
+    """C4 with the hair fibre BSDF (float device code in the host emulation vs the oracle's double-precision restatement
+    from the papers): transmission events toggle `inside`, russian roulette is live at depth 6"""
+    from strelka_b200.scenes import make_hair
+
+    s, st, _ = make_hair(48, 48, 4, depth=6, n_strands=1500, segments=6, material="hair")
+    o, e = pyoracle.OracleScene(s), pyemul.EmulScene(s)
+    img_o, _, _, cnt_o = o.render(st, 48, 48, 4)
+    img_e, _, cnt_e = e.render(st, 48, 48, 4, chunk_max=2)
+    assert img_o[..., :3].mean() > 1e-3
+    assert abs(cnt_o["radiance_rays"] / cnt_e["radiance_rays"] - 1.0) < 1e-3
+    assert rel_rmse(img_e, img_o) < 1e-3
+    assert abs(img_e[..., :3].mean() / img_o[..., :3].mean() - 1.0) < 5e-3
+
+
 def test_debug_normals_exact():
     s, st = random_scene(seed=2)
     st.setAs("render/pt/debug", 1)

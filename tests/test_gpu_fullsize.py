@@ -44,6 +44,13 @@ def c4():
 
 
 @pytest.fixture(scope="module")
+def c4_hair():
+    f = FullScene(lambda: make_hair(1024, 1024, 1024, material="hair"))
+    yield f
+    f.oracle.close()
+
+
+@pytest.fixture(scope="module")
 def c5():
     f = FullScene(lambda: make_instanced(3840, 2160, 4096))
     yield f
@@ -155,6 +162,11 @@ def test_c4_full_resolution_windows_match_oracle(gpu_render, c4):
     _check_windows(img, c4, [(384, 320, 256, 256), (300, 600, 192, 128)])
 
 
+def test_c4_hair_material_full_resolution_windows_match_oracle(gpu_render, c4_hair):
+    img = _render_full(gpu_render, c4_hair, 1)  # the same config with the Chiang fibre BSDF on the strands
+    _check_windows(img, c4_hair, [(384, 320, 256, 256), (300, 600, 192, 128)])
+
+
 def test_c5_full_resolution_windows_match_oracle(gpu_render, c5):
     img = _render_full(gpu_render, c5, 1)  # 3840 x 2160, sppTotal 4096: x >= 1024 or y >= 1024 wrap (Q3)
     _check_windows(img, c5, [(1792, 952, 256, 256), (900, 1000, 256, 64), (3300, 300, 256, 200)])
@@ -165,7 +177,11 @@ def test_launch_larger_than_one_wavefront_batch(gpu_render):
     mean must not depend on how the launch is cut into wavefront batches."""
     from strelka_b200 import RenderFactory, RenderType
 
-    s, st, (w, h) = make_cornell(64, 64, 48)
+    from util import random_scene
+
+    s, st = random_scene(seed=5)  # diffuse and UsdPreviewSurface materials: both AOVs have content
+    w = h = 64
+    st.setAs("render/pt/sppTotal", 48)
     st.setAs("render/pt/spp", 12)
     imgs = []
     for max_paths in (0, 64 * 64 * 5):
@@ -190,6 +206,6 @@ def test_launch_larger_than_one_wavefront_batch(gpu_render):
         imgs.append(out)
         buf.destroy()
         r.destroy()
-    for a, b in zip(*imgs):
-        assert a[..., :3].max() > 0
-        assert np.array_equal(a, b)
+    for name, a, b in zip(("accumulated", "no accumulation", "diffuse AOV", "specular AOV"), *imgs):
+        assert a[..., :3].max() > 0, name
+        assert np.array_equal(a, b), f"{name}: {(a != b).sum()} values differ, max |diff| {np.abs(a - b).max():.3e}"

@@ -39,6 +39,17 @@ def test_c4_hair_small_matches_oracle(gpu_render):
     assert rel_rmse(img_g, img_o) <= 1e-3
 
 
+def test_c4_hair_bsdf_small_matches_oracle(gpu_render):
+    """C4 with material = hair (Chiang fibre BSDF): GLOSSY | TRANSMISSION events flip `inside`, depth 6 keeps russian
+    roulette live; the oracle side is the double-precision restatement from the papers (oracle/hair.h)"""
+    s, st, _ = make_hair(96, 96, 8, depth=6, n_strands=3000, segments=8, material="hair")
+    img_g = _render(gpu_render, s, st, 96, 96, 8)
+    img_o, _, _, _ = pyoracle.OracleScene(s).render(st, 96, 96, 8)
+    assert img_o[..., :3].mean() > 1e-3
+    assert rel_rmse(img_g, img_o) <= 1e-3
+    assert abs(img_g[..., :3].mean() / img_o[..., :3].mean() - 1.0) <= 5e-3
+
+
 def test_c4_curve_trace_hits_match_oracle(gpu_render):
     s, _, _ = make_hair(32, 32, 1, n_strands=2000, segments=8)
     rng = np.random.default_rng(3)

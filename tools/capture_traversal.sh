@@ -9,6 +9,7 @@ for cfg in "$@"; do
       python tools/profile_step.py $cfg 4 > gpurun_out/${tag}_${cfg}_${k}.log 2>&1
     ncu -i gpurun_out/${tag}_${cfg}_${k}.ncu-rep --page raw --csv > gpurun_out/${tag}_${cfg}_${k}_raw.csv 2>/dev/null
     ncu -i gpurun_out/${tag}_${cfg}_${k}.ncu-rep --page source --csv > gpurun_out/${tag}_${cfg}_${k}_source.csv 2>/dev/null
+    rm -f gpurun_out/${tag}_${cfg}_${k}.ncu-rep  # gpurun_out/ is capped at 64 MiB: the two CSV pages are what gets read
   done
 done
 ls -la gpurun_out | grep ${tag}_ | head -40
