@@ -81,6 +81,10 @@ struct SceneDev
 #define SB_COST_TRI 1.0f
 #endif
 constexpr float kCostNode = 1.0f, kCostTri = SB_COST_TRI, kCostSeg = 1.0f;
+#ifndef SB_MAX_LEAF
+#define SB_MAX_LEAF 3
+#endif
+constexpr uint32_t kMaxLeafTris = SB_MAX_LEAF; // triangles per leaf slot (the 24-bit leaf field of a node holds 8 x 3)
 
 struct WideBvh
 {
@@ -423,7 +427,7 @@ inline void build_scene_bvhs(Exec& ex, SceneDev& S, const uint32_t* instTriFirst
             boxes[g] = b;
         });
         ex.mark("flatten triangles", (long long)numTris);
-        WideBvh bvh = build_wide_bvh(ex, boxes, numTris, 3u, kCostNode, kCostTri);
+        WideBvh bvh = build_wide_bvh(ex, boxes, numTris, kMaxLeafTris, kCostNode, kCostTri);
         TriRec* ordered = ex.alloc<TriRec>(numTris);
         const uint32_t* order = bvh.primOrder;
         ex.pfor(numTris, SB_LAMBDA(size_t i) { ordered[i] = unsorted[order[i]]; });

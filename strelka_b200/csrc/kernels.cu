@@ -188,27 +188,87 @@ __global__ void __launch_bounds__(kBlock, 8) k_primary(FrameParams P, SceneDev S
 #define SB_REFILL 28
 #endif
 constexpr int kRefill = SB_REFILL;
+
+// Queue slots are handed to the warps in chunks (one L2 atomic per kFetchChunk rays instead of one per refill); the warp
+// that takes a chunk prefetches its ray records, which the shade kernel streamed out to HBM, so that the refills that
+// follow find them on chip instead of stalling the whole warp on a DRAM round trip (ncu: 5 % of all stall samples of the
+// closest-hit kernel sat on the first use of a freshly fetched ray).
+#ifndef SB_FETCH_CHUNK
+#define SB_FETCH_CHUNK 128
+#endif
+constexpr uint32_t kFetchChunk = SB_FETCH_CHUNK;
 struct WarpFetch
 {
-    bool exhausted;
+    uint32_t next = 0, end = 0; // warp-uniform: the slots this warp still owns
+    bool exhausted = false; // warp-uniform: the queue has been handed out completely
 };
-
-// hands out queue slots to the lanes with need == true; returns the slot or 0xffffffff
-__device__ __forceinline__ uint32_t fetch_slots(uint32_t* head, uint32_t n, bool need, bool& exhausted)
+__device__ __forceinline__ void prefetch_l2(const void* p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+// hands out queue slots to the lanes with need == true; returns the slot or 0xffffffff.
+// recA / recB (/ recC): the float4 record arrays of the queue, prefetched per chunk.
+__device__ __forceinline__ uint32_t fetch_slots(WarpFetch& wf, uint32_t* head, uint32_t n, bool need, const float4* recA, const float4* recB,
+                                                const float4* recC)
 {
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned mask = __ballot_sync(0xffffffffu, need);
-    if (mask == 0u || exhausted)
-        return 0xffffffffu;
-    const int leader = __ffs(mask) - 1;
-    uint32_t base = 0;
-    if (int(lane) == leader)
-        base = atomicAdd(head, uint32_t(__popc(mask)));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (base + uint32_t(__popc(mask)) >= n)
-        exhausted = true; // warp-uniform: the queue has been handed out completely
-    const uint32_t idx = base + uint32_t(__popc(mask & ((1u << lane) - 1u)));
-    return (need && idx < n) ? idx : 0xffffffffu;
+    unsigned mask = __ballot_sync(0xffffffffu, need);
+    uint32_t slot = 0xffffffffu;
+    while (mask != 0u)
+    {
+        if (wf.next == wf.end)
+        {
+            if (wf.exhausted)
+                break;
+            // chunk size: large for long queues, down to one warp-load for short ones (a short queue cut into 128-ray
+            // chunks leaves some warps with two chunks and others with one: measured +7 % on the hair scene's shadow rays)
+            const uint32_t warpsInGrid = gridDim.x * (blockDim.x >> 5);
+            const uint32_t chunk = min(kFetchChunk, max(32u, (n / (warpsInGrid * 8u)) & ~31u));
+            uint32_t base = 0;
+            if (lane == 0u)
+                base = atomicAdd(head, chunk);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= n)
+            {
+                wf.exhausted = true;
+                break;
+            }
+            wf.next = base;
+            wf.end = min(base + chunk, n);
+            if (wf.end == n)
+                wf.exhausted = true; // nothing beyond this chunk
+#ifndef SB_FETCH_PREFETCH
+#define SB_FETCH_PREFETCH 1
+#endif
+#if SB_FETCH_PREFETCH
+            // 16-byte records: 8 per 128-byte line; every lane touches one line of each array
+            for (uint32_t i = wf.next + lane * 8u; i < wf.end; i += 256u)
+            {
+                prefetch_l2(recA + i);
+                prefetch_l2(recB + i);
+                if (recC)
+                    prefetch_l2(recC + i);
+            }
+#endif
+        }
+        const uint32_t avail = wf.end - wf.next;
+        const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
+        if (need && slot == 0xffffffffu && rank < avail)
+            slot = wf.next + rank;
+        wf.next += min(avail, uint32_t(__popc(mask)));
+        mask = __ballot_sync(0xffffffffu, need && slot == 0xffffffffu);
+    }
+    return slot;
+}
+
+// stage the first SB_TOP_SMEM nodes of a level-ordered BVH in shared memory (the top of the tree every ray walks)
+__device__ __forceinline__ void stage_top_nodes(uint4* dst, const WideNode* nodes, uint32_t numNodes)
+{
+#if SB_TOP_SMEM
+    const uint32_t words = min(uint32_t(SB_TOP_SMEM), numNodes) * 5u;
+    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x)
+        dst[i] = __ldg(reinterpret_cast<const uint4*>(nodes) + i);
+#endif
 }
 
 #ifndef SB_EXTEND_MIN_BLOCKS
@@ -221,21 +281,37 @@ __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FramePa
     uint32_t* head = &Q.counts[kHeadExtendBase + depth];
     const bool haveTris = S.numTriNodes != 0u, haveSegs = CURVES && S.numSegNodes != 0u; // CURVES = false: no curve code at all
     TravStats st = { 0, 0, 0, 0 };
-    bool active = false, exhausted = false;
+    bool active = false;
+    WarpFetch wf;
     uint32_t slot = 0;
     int phase = 0;
     Ray ray;
     RayPrep rp;
     HitRec hit;
     Traversal T;
+    TravStack K;
+    NodeRegs pn; // node in flight (SB_PIPE_NODE)
+    bool pnValid = false;
 #if SB_SMEM_STACK
     static_assert(kTravBlock == kBlock, "shared-memory traversal stack stride");
     __shared__ uint2 s_stack[SB_SMEM_STACK * kBlock];
     T.sstack = s_stack + threadIdx.x;
 #endif
+#if SB_TOP_SMEM
+    __shared__ uint4 s_top[(CURVES ? 2 : 1) * SB_TOP_SMEM * 5];
+    stage_top_nodes(s_top, S.triNodes, S.numTriNodes);
+    if (CURVES)
+        stage_top_nodes(s_top + SB_TOP_SMEM * 5, S.segNodes, S.numSegNodes);
+    __syncthreads();
+    const uint4* topTri = s_top;
+    const uint4* topSeg = s_top + (CURVES ? SB_TOP_SMEM * 5 : 0);
+#else
+    const uint4* topTri = nullptr;
+    const uint4* topSeg = nullptr;
+#endif
     for (;;)
     {
-        const uint32_t got = fetch_slots(head, n, !active, exhausted);
+        const uint32_t got = fetch_slots(wf, head, n, !active, Q.rayO[0], Q.rayD[0], nullptr);
         if (got != 0xffffffffu)
         {
             slot = got;
@@ -249,6 +325,7 @@ __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FramePa
             hit.prim = hit.inst = hit.kind = 0u;
             hit.gid = 0xffffffffu;
             trav_init(T);
+            pnValid = false;
             phase = haveTris ? 0 : (haveSegs ? 1 : 2);
             active = true;
         }
@@ -259,27 +336,19 @@ __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FramePa
             if (active)
             {
                 bool more = false, anyHit = false;
-// step shape per iteration: 0 = node + one primitive, 1 = one unit, 2 = node + all its primitives.  Measured on the
-// 2 M / 10 M-triangle and hair scenes: 0 is best here (2: +7 %), 1 is best for the any-hit kernel (2: +4 %);
-// the one-ray-per-thread kernels, which have no refill ballots, gain 15 % from shape 2 (traverse_bvh).
-#ifndef SB_EXTEND_UNIT_STEP
-#define SB_EXTEND_UNIT_STEP 0
-#endif
-#if SB_EXTEND_UNIT_STEP == 2
+                // step shape: node visit + one primitive test per iteration.  Measured on the 2 M / 10 M-triangle and hair
+                // scenes against one unit per iteration (best for the any-hit kernel) and node + all its primitives
+                // (+7 % here; best for the one-ray-per-thread kernels, which have no refill ballots).
+#if SB_PIPE_NODE >= 1
                 if (phase == 0)
-                    more = trav_step_ww<1, false, STATS>(T, S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
+                    more = trav_step_pipe<1, false, STATS, (SB_SMEM_STACK > 0)>(T, K, S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, anyHit, &st, pn, pnValid);
                 else if (CURVES && phase == 1)
-                    more = trav_step_ww<2, false, STATS>(T, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
-#elif SB_EXTEND_UNIT_STEP
-                if (phase == 0)
-                    more = trav_step_unit<1, false, STATS>(T, S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
-                else if (CURVES && phase == 1)
-                    more = trav_step_unit<2, false, STATS>(T, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
+                    more = trav_step_pipe<2, false, STATS, (SB_SMEM_STACK > 0)>(T, K, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st, pn, pnValid);
 #else
                 if (phase == 0)
-                    more = trav_step<1, false, STATS, (SB_SMEM_STACK > 0)>(T, S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
+                    more = trav_step<1, false, STATS, (SB_SMEM_STACK > 0)>(T, K, S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, anyHit, &st, topTri);
                 else if (CURVES && phase == 1)
-                    more = trav_step<2, false, STATS, (SB_SMEM_STACK > 0)>(T, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
+                    more = trav_step<2, false, STATS, (SB_SMEM_STACK > 0)>(T, K, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st, topSeg);
 #endif
                 if (!more)
                 {
@@ -287,6 +356,7 @@ __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FramePa
                     {
                         phase = 1;
                         trav_init(T);
+                        pnValid = false;
                     }
                     else
                     {
@@ -303,7 +373,7 @@ __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FramePa
                 }
             }
             const int busy = __popc(__ballot_sync(0xffffffffu, active));
-            if (busy == 0 || (!exhausted && busy < kRefill))
+            if (busy == 0 || (!(wf.exhausted && wf.next == wf.end) && busy < kRefill))
                 break;
         }
     }
@@ -323,21 +393,37 @@ __global__ void __launch_bounds__(kBlock, SB_SHADOW_MIN_BLOCKS) k_shadow(SceneDe
     uint32_t* head = &Q.counts[kHeadShadowBase + depth];
     const bool haveTris = S.numTriNodes != 0u, haveSegs = CURVES && S.numSegNodes != 0u; // CURVES = false: no curve code at all
     TravStats st = { 0, 0, 0, 0 };
-    bool active = false, exhausted = false;
+    bool active = false;
+    WarpFetch wf;
     uint32_t slot = 0;
     int phase = 0;
     Ray ray;
     RayPrep rp;
     HitRec hit;
     Traversal T;
+    TravStack K;
+    NodeRegs pn; // node in flight (SB_PIPE_NODE)
+    bool pnValid = false;
 #if SB_SMEM_STACK
     static_assert(kTravBlock == kBlock, "shared-memory traversal stack stride");
     __shared__ uint2 s_stack[SB_SMEM_STACK * kBlock];
     T.sstack = s_stack + threadIdx.x;
 #endif
+#if SB_TOP_SMEM
+    __shared__ uint4 s_top[(CURVES ? 2 : 1) * SB_TOP_SMEM * 5];
+    stage_top_nodes(s_top, S.triNodes, S.numTriNodes);
+    if (CURVES)
+        stage_top_nodes(s_top + SB_TOP_SMEM * 5, S.segNodes, S.numSegNodes);
+    __syncthreads();
+    const uint4* topTri = s_top;
+    const uint4* topSeg = s_top + (CURVES ? SB_TOP_SMEM * 5 : 0);
+#else
+    const uint4* topTri = nullptr;
+    const uint4* topSeg = nullptr;
+#endif
     for (;;)
     {
-        const uint32_t got = fetch_slots(head, n, !active, exhausted);
+        const uint32_t got = fetch_slots(wf, head, n, !active, Q.shO, Q.shD, Q.shC);
         if (got != 0xffffffffu)
         {
             slot = got;
@@ -350,6 +436,7 @@ __global__ void __launch_bounds__(kBlock, SB_SHADOW_MIN_BLOCKS) k_shadow(SceneDe
             hit.kind = 0u;
             hit.gid = 0xffffffffu;
             trav_init(T);
+            pnValid = false;
             phase = haveTris ? 0 : (haveSegs ? 1 : 2);
             active = true;
         }
@@ -360,24 +447,18 @@ __global__ void __launch_bounds__(kBlock, SB_SHADOW_MIN_BLOCKS) k_shadow(SceneDe
             if (active)
             {
                 bool more = false, occluded = false;
-#ifndef SB_SHADOW_UNIT_STEP
-#define SB_SHADOW_UNIT_STEP 1
-#endif
-#if SB_SHADOW_UNIT_STEP == 2
+                // step shape: ONE unit (a primitive test if one is pending, else a node visit) per iteration: measured
+                // 1.5x faster for any-hit rays than node + primitive (profiles/r01_b_*)
+#if SB_PIPE_NODE >= 2
                 if (phase == 0)
-                    more = trav_step_ww<1, true, STATS>(T, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st);
+                    more = trav_step_unit_pipe<1, true, STATS, (SB_SMEM_STACK > 0)>(T, K, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st, pn, pnValid);
                 else if (CURVES && phase == 1)
-                    more = trav_step_ww<2, true, STATS>(T, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st);
-#elif SB_SHADOW_UNIT_STEP
-                if (phase == 0)
-                    more = trav_step_unit<1, true, STATS, (SB_SMEM_STACK > 0)>(T, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st);
-                else if (CURVES && phase == 1)
-                    more = trav_step_unit<2, true, STATS, (SB_SMEM_STACK > 0)>(T, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st);
+                    more = trav_step_unit_pipe<2, true, STATS, (SB_SMEM_STACK > 0)>(T, K, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st, pn, pnValid);
 #else
                 if (phase == 0)
-                    more = trav_step<1, true, STATS>(T, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st);
+                    more = trav_step_unit<1, true, STATS, (SB_SMEM_STACK > 0)>(T, K, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st, topTri);
                 else if (CURVES && phase == 1)
-                    more = trav_step<2, true, STATS>(T, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st);
+                    more = trav_step_unit<2, true, STATS, (SB_SMEM_STACK > 0)>(T, K, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st, topSeg);
 #endif
                 if (!more)
                 {
@@ -385,6 +466,7 @@ __global__ void __launch_bounds__(kBlock, SB_SHADOW_MIN_BLOCKS) k_shadow(SceneDe
                     {
                         phase = 1;
                         trav_init(T);
+                        pnValid = false;
                     }
                     else
                     {
@@ -400,7 +482,7 @@ __global__ void __launch_bounds__(kBlock, SB_SHADOW_MIN_BLOCKS) k_shadow(SceneDe
                 }
             }
             const int busy = __popc(__ballot_sync(0xffffffffu, active));
-            if (busy == 0 || (!exhausted && busy < kRefill))
+            if (busy == 0 || (!(wf.exhausted && wf.next == wf.end) && busy < kRefill))
                 break;
         }
     }

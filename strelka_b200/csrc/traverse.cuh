@@ -242,6 +242,16 @@ SB_HD RayPrep prepare_ray(const float3& d)
 // SB_SMEM_STACK > 0: the first SB_SMEM_STACK stack levels of the persistent kernels live in shared memory
 // (strided by the block size, bank-conflict free), deeper ones in local memory.
 constexpr int kTravBlock = 128; // threads per block of the kernels that use the shared-memory stack
+#ifndef SB_STACK_SEPARATE
+#define SB_STACK_SEPARATE 1
+#endif
+// The postponed node groups live in their own array (TravStack), NOT inside Traversal: with a dynamically indexed array
+// member nvcc keeps the whole object addressable and writes ngroup / tgroup / sp back to local memory after every
+// update (4 STL per node visit in the SASS of the persistent kernels, 31 M local stores per 7 M-ray launch in ncu).
+struct TravStack
+{
+    uint2 e[kStackSize];
+};
 struct Traversal
 {
     uint2 ngroup, tgroup;
@@ -249,8 +259,15 @@ struct Traversal
 #if defined(__CUDACC__)
     uint2* sstack; // this thread's column of the block's shared-memory stack (SSTACK traversals only)
 #endif
+#if !SB_STACK_SEPARATE
     uint2 stack[kStackSize];
+#endif
 };
+#if SB_STACK_SEPARATE
+#define SB_TSTACK(T, K) (K).e
+#else
+#define SB_TSTACK(T, K) (T).stack
+#endif
 SB_HD void trav_init(Traversal& T)
 {
     T.ngroup.x = 0u;
@@ -265,8 +282,18 @@ SB_HD void trav_init(Traversal& T)
 //   trav_node : if the lane has no primitives pending, visit the next node (returns false when nothing is left)
 //   trav_prim : if the lane has primitives pending, test exactly one
 // KIND 1: triangles (prims = TriRec), KIND 2: curve segments (prims = SegRec).  ANY: shadow rays.
+#ifndef SB_PREFETCH_CHILDREN
+#define SB_PREFETCH_CHILDREN 0
+#endif
+#ifndef SB_PIPE_NODE
+#define SB_PIPE_NODE 0 // 1: closest-hit kernel, 2: any-hit kernel too -- software-pipelined node fetch (trav_step_pipe)
+#endif
+#ifndef SB_TOP_SMEM
+#define SB_TOP_SMEM 0 // number of top-level nodes (the first K of the level-ordered array) staged in shared memory
+#endif
 template <bool STATS, bool SSTACK = false>
-SB_HD bool trav_node(Traversal& T, const WideNode* __restrict__ nodes, const Ray& ray, const RayPrep& rp, TravStats* st)
+SB_HD bool trav_node(Traversal& T, TravStack& K, const WideNode* __restrict__ nodes, const Ray& ray, const RayPrep& rp, TravStats* st,
+                     const uint4* __restrict__ topNodes = nullptr)
 {
     if (T.ngroup.y <= 0x00ffffffu)
     {
@@ -275,10 +302,10 @@ SB_HD bool trav_node(Traversal& T, const WideNode* __restrict__ nodes, const Ray
         --T.sp;
 #if defined(__CUDA_ARCH__) && SB_SMEM_STACK
         if (SSTACK)
-            T.ngroup = (T.sp < SB_SMEM_STACK) ? T.sstack[T.sp * kTravBlock] : T.stack[T.sp - SB_SMEM_STACK];
+            T.ngroup = (T.sp < SB_SMEM_STACK) ? T.sstack[T.sp * kTravBlock] : SB_TSTACK(T, K)[T.sp - SB_SMEM_STACK];
         else
 #endif
-            T.ngroup = T.stack[T.sp];
+            T.ngroup = SB_TSTACK(T, K)[T.sp];
     }
     const uint32_t hits = T.ngroup.y;
     const uint32_t bit = bfind32(hits);
@@ -293,11 +320,11 @@ SB_HD bool trav_node(Traversal& T, const WideNode* __restrict__ nodes, const Ray
                 if (T.sp < SB_SMEM_STACK)
                     T.sstack[T.sp * kTravBlock] = T.ngroup;
                 else
-                    T.stack[T.sp - SB_SMEM_STACK] = T.ngroup;
+                    SB_TSTACK(T, K)[T.sp - SB_SMEM_STACK] = T.ngroup;
             }
             else
 #endif
-                T.stack[T.sp] = T.ngroup;
+                SB_TSTACK(T, K)[T.sp] = T.ngroup;
             ++T.sp;
         }
         else if (STATS)
@@ -305,16 +332,116 @@ SB_HD bool trav_node(Traversal& T, const WideNode* __restrict__ nodes, const Ray
     }
     const uint32_t slot = (bit - 24u) ^ (rp.octinv & 7u);
     const uint32_t rel = popc32(hits & ~(0xffffffffu << slot) & 0xffu);
-    const WideNode* np = nodes + (T.ngroup.x + rel);
-    const uint4 n0 = SB_LDG4(&np->n0), n1 = SB_LDG4(&np->n1), n2 = SB_LDG4(&np->n2), n3 = SB_LDG4(&np->n3), n4 = SB_LDG4(&np->n4);
+    const uint32_t ni = T.ngroup.x + rel;
+    const WideNode* np = nodes + ni;
+    uint4 n0, n1, n2, n3, n4;
+#if defined(__CUDA_ARCH__) && SB_TOP_SMEM
+    if (SSTACK && ni < uint32_t(SB_TOP_SMEM))
+    {
+        // the hot top of the tree: a copy in shared memory (the persistent kernels stage it once per CTA)
+        const uint4* sp_ = topNodes + 5u * ni;
+        n0 = sp_[0];
+        n1 = sp_[1];
+        n2 = sp_[2];
+        n3 = sp_[3];
+        n4 = sp_[4];
+    }
+    else
+#endif
+    {
+        n0 = SB_LDG4(&np->n0);
+        n1 = SB_LDG4(&np->n1);
+        n2 = SB_LDG4(&np->n2);
+        n3 = SB_LDG4(&np->n3);
+        n4 = SB_LDG4(&np->n4);
+    }
     if (STATS)
         st->nodes++;
     const uint32_t hm = wide_node_hits(n0, n1, n2, n3, n4, ray.o, rp.idir, rp.octinv4, rp.negx, rp.negy, rp.negz, ray.tmin, ray.tmax);
+#if defined(__CUDA_ARCH__) && SB_PREFETCH_CHILDREN
+    // the hit children that will wait on the stack: pull their nodes towards the SM now (children are contiguous)
+    if (SSTACK && (hm & 0xff000000u) != 0u)
+    {
+        const uint32_t imask = n0.w >> 24;
+        uint32_t rest = hm >> 24;
+        while (rest)
+        {
+            const uint32_t b = 31u - __clz(rest);
+            rest &= ~(1u << b);
+            const uint32_t sl = b ^ (rp.octinv & 7u);
+            const uint32_t r2 = popc32(imask & ~(0xffffffffu << sl));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nodes + (n1.x + r2)));
+        }
+    }
+#endif
     T.ngroup.x = n1.x;
     T.ngroup.y = (hm & 0xff000000u) | (n0.w >> 24);
     T.tgroup.x = n1.y;
     T.tgroup.y = hm & 0x00ffffffu;
     return true;
+}
+
+// ---- the two halves of trav_node, for the software-pipelined step (SB_PIPE_NODE) --------------------------------
+struct NodeRegs
+{
+    uint4 n0, n1, n2, n3, n4;
+};
+// pick the next node to visit (popping the stack when the current group is used up) and ISSUE its five loads;
+// the current group is consumed: its remaining hits are postponed on the stack.  False when nothing is left.
+template <bool SSTACK>
+SB_HD bool trav_select_load(Traversal& T, TravStack& K, const WideNode* __restrict__ nodes, const RayPrep& rp, NodeRegs& N)
+{
+    if (T.ngroup.y <= 0x00ffffffu)
+    {
+        if (T.sp == 0)
+            return false;
+        --T.sp;
+#if defined(__CUDA_ARCH__) && SB_SMEM_STACK
+        if (SSTACK)
+            T.ngroup = (T.sp < SB_SMEM_STACK) ? T.sstack[T.sp * kTravBlock] : SB_TSTACK(T, K)[T.sp - SB_SMEM_STACK];
+        else
+#endif
+            T.ngroup = SB_TSTACK(T, K)[T.sp];
+    }
+    const uint32_t hits = T.ngroup.y;
+    const uint32_t bit = bfind32(hits);
+    T.ngroup.y &= ~(1u << bit);
+    if (T.ngroup.y > 0x00ffffffu && T.sp < kStackSize)
+    {
+#if defined(__CUDA_ARCH__) && SB_SMEM_STACK
+        if (SSTACK)
+        {
+            if (T.sp < SB_SMEM_STACK)
+                T.sstack[T.sp * kTravBlock] = T.ngroup;
+            else
+                SB_TSTACK(T, K)[T.sp - SB_SMEM_STACK] = T.ngroup;
+        }
+        else
+#endif
+            SB_TSTACK(T, K)[T.sp] = T.ngroup;
+        ++T.sp;
+    }
+    T.ngroup.y = 0u; // consumed
+    const uint32_t slot = (bit - 24u) ^ (rp.octinv & 7u);
+    const uint32_t rel = popc32(hits & ~(0xffffffffu << slot) & 0xffu);
+    const WideNode* np = nodes + (T.ngroup.x + rel);
+    N.n0 = SB_LDG4(&np->n0);
+    N.n1 = SB_LDG4(&np->n1);
+    N.n2 = SB_LDG4(&np->n2);
+    N.n3 = SB_LDG4(&np->n3);
+    N.n4 = SB_LDG4(&np->n4);
+    return true;
+}
+template <bool STATS>
+SB_HD void trav_test_node(Traversal& T, const NodeRegs& N, const Ray& ray, const RayPrep& rp, TravStats* st)
+{
+    if (STATS)
+        st->nodes++;
+    const uint32_t hm = wide_node_hits(N.n0, N.n1, N.n2, N.n3, N.n4, ray.o, rp.idir, rp.octinv4, rp.negx, rp.negy, rp.negz, ray.tmin, ray.tmax);
+    T.ngroup.x = N.n1.x;
+    T.ngroup.y = (hm & 0xff000000u) | (N.n0.w >> 24);
+    T.tgroup.x = N.n1.y;
+    T.tgroup.y = hm & 0x00ffffffu;
 }
 
 // tests one pending primitive; returns true if an any-hit query is satisfied (ANY only)
@@ -383,12 +510,12 @@ SB_HD bool trav_prim(Traversal& T, const void* __restrict__ prims, uint32_t rayM
 // one full step of one lane: node half-step if idle, then one primitive if any is pending.
 // Returns false when the traversal is finished; anyHit is set when an ANY query found an occluder.
 template <int KIND, bool ANY, bool STATS, bool SSTACK = false>
-SB_HD bool trav_step(Traversal& T, const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask, Ray& ray,
-                     const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st)
+SB_HD bool trav_step(Traversal& T, TravStack& K, const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask, Ray& ray,
+                     const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st, const uint4* __restrict__ topNodes = nullptr)
 {
     if (T.tgroup.y == 0u)
     {
-        if (!trav_node<STATS, SSTACK>(T, nodes, ray, rp, st))
+        if (!trav_node<STATS, SSTACK>(T, K, nodes, ray, rp, st, topNodes))
             return false;
     }
     if (T.tgroup.y != 0u)
@@ -402,12 +529,62 @@ SB_HD bool trav_step(Traversal& T, const WideNode* __restrict__ nodes, const voi
     return true;
 }
 
+// Software-pipelined form of trav_step: the loads of the NEXT node are issued before the primitive test of the current
+// one, so that the two memory latencies of an iteration overlap (the choice of the next node does not depend on the
+// outcome of the primitive test; a closer hit only makes its box test stricter when it is finally run).
+// `pn` holds the node in flight, `pnValid` says whether there is one.
+template <int KIND, bool ANY, bool STATS, bool SSTACK = false>
+SB_HD bool trav_step_pipe(Traversal& T, TravStack& K, const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask,
+                          Ray& ray, const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st, NodeRegs& pn, bool& pnValid)
+{
+    if (T.tgroup.y == 0u)
+    {
+        if (!pnValid && !trav_select_load<SSTACK>(T, K, nodes, rp, pn))
+            return false;
+        trav_test_node<STATS>(T, pn, ray, rp, st);
+        pnValid = false;
+    }
+    if (!pnValid)
+        pnValid = trav_select_load<SSTACK>(T, K, nodes, rp, pn);
+    if (T.tgroup.y != 0u)
+    {
+        if (trav_prim<KIND, ANY, STATS>(T, prims, rayMask, ray, hit, st))
+        {
+            anyHit = true;
+            return false;
+        }
+    }
+    return pnValid || T.tgroup.y != 0u;
+}
+// ... and of trav_step_unit (any-hit rays)
+template <int KIND, bool ANY, bool STATS, bool SSTACK = false>
+SB_HD bool trav_step_unit_pipe(Traversal& T, TravStack& K, const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask,
+                               Ray& ray, const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st, NodeRegs& pn, bool& pnValid)
+{
+    if (T.tgroup.y != 0u)
+    {
+        if (!pnValid)
+            pnValid = trav_select_load<SSTACK>(T, K, nodes, rp, pn);
+        if (trav_prim<KIND, ANY, STATS>(T, prims, rayMask, ray, hit, st))
+        {
+            anyHit = true;
+            return false;
+        }
+        return pnValid || T.tgroup.y != 0u;
+    }
+    if (!pnValid && !trav_select_load<SSTACK>(T, K, nodes, rp, pn))
+        return false;
+    trav_test_node<STATS>(T, pn, ray, rp, st);
+    pnValid = false;
+    return true;
+}
+
 // Single-unit variant of trav_step: ONE primitive test if any is pending, else ONE node visit.  Measured on the
 // 2 M-triangle scene the any-hit (shadow) kernel runs 1.5x faster with this shape, the closest-hit kernel
 // slightly faster with the node+primitive shape above (profiles/r01_b_*).
 template <int KIND, bool ANY, bool STATS, bool SSTACK = false>
-SB_HD bool trav_step_unit(Traversal& T, const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask, Ray& ray,
-                          const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st)
+SB_HD bool trav_step_unit(Traversal& T, TravStack& K, const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask, Ray& ray,
+                          const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st, const uint4* __restrict__ topNodes = nullptr)
 {
     if (T.tgroup.y != 0u)
     {
@@ -418,16 +595,16 @@ SB_HD bool trav_step_unit(Traversal& T, const WideNode* __restrict__ nodes, cons
         }
         return true;
     }
-    return trav_node<STATS, SSTACK>(T, nodes, ray, rp, st);
+    return trav_node<STATS, SSTACK>(T, K, nodes, ray, rp, st, topNodes);
 }
 
 // "While-while" step: ONE node visit, then ALL the primitives it queued.  The lanes of a warp meet again at every
 // node test (the expensive half of the work) instead of drifting apart.
 template <int KIND, bool ANY, bool STATS>
-SB_HD bool trav_step_ww(Traversal& T, const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask, Ray& ray,
+SB_HD bool trav_step_ww(Traversal& T, TravStack& K, const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask, Ray& ray,
                         const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st)
 {
-    if (T.tgroup.y == 0u && !trav_node<STATS>(T, nodes, ray, rp, st))
+    if (T.tgroup.y == 0u && !trav_node<STATS>(T, K, nodes, ray, rp, st))
         return false;
     while (T.tgroup.y != 0u)
     {
@@ -447,6 +624,7 @@ SB_HD bool traverse_bvh(const WideNode* __restrict__ nodes, const void* __restri
                         HitRec& hit, TravStats* st)
 {
     Traversal T;
+    TravStack K;
     trav_init(T);
     const uint32_t kindBefore = hit.kind;
     const float tBefore = ray.tmax;
@@ -456,7 +634,7 @@ SB_HD bool traverse_bvh(const WideNode* __restrict__ nodes, const void* __restri
     // lanes of a warp meet again at every node test (the expensive half) instead of drifting apart
     for (;;)
     {
-        if (T.tgroup.y == 0u && !trav_node<STATS>(T, nodes, ray, rp, st))
+        if (T.tgroup.y == 0u && !trav_node<STATS>(T, K, nodes, ray, rp, st))
             break;
         while (T.tgroup.y != 0u)
         {
@@ -470,7 +648,7 @@ SB_HD bool traverse_bvh(const WideNode* __restrict__ nodes, const void* __restri
             break;
     }
 #else
-    while (trav_step<KIND, ANY, STATS>(T, nodes, prims, rayMask, ray, rp, hit, anyHit, st))
+    while (trav_step<KIND, ANY, STATS>(T, K, nodes, prims, rayMask, ray, rp, hit, anyHit, st))
     {
     }
 #endif

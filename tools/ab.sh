@@ -10,6 +10,6 @@ n=sys.argv[1]
 for l in open(f"gpurun_out/ab_{n}.log"):
     try: d=json.loads(l)
     except Exception: print(n, l.strip()[:200]); continue
-    print(f"{n:28s} {d['config']} mrays {d['mrays_s']:8.1f} gen {d['stage_ms']['raygen']:6.2f} ext {d['stage_ms']['extend']:7.2f} shd {d['stage_ms']['shade']:6.2f} sdw {d['stage_ms']['shadow']:7.2f} nodes/ray {d.get('nodes_per_ray')} tris/ray {d.get('tris_per_ray')} frac {d.get('extend_roofline_frac')}")
+    print(f"{n:28s} {d['config']} mrays {d['mrays_s']:8.1f} gen {d['stage_ms']['raygen']:6.2f} ext {d['stage_ms']['extend']:7.2f} shd {d['stage_ms']['shade']:6.2f} sdw {d['stage_ms']['shadow']:7.2f} nodes/ray {d.get('nodes_per_ray')} tris/ray {d.get('tris_per_ray')} frac ext {d.get('extend_roofline_frac')} sdw {d.get('shadow_roofline_frac')}")
 PY
 done

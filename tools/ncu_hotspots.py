@@ -21,7 +21,11 @@ STALLS = ["stall_long_sb", "stall_wait", "stall_short_sb", "stall_math", "stall_
 
 
 def ncu_rows(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True, check=True).stdout
+    # a saved `ncu -i x.ncu-rep --page source --csv` page works as well as the report itself
+    if rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(out.splitlines()))
     kernel = rows[0][1]
     hdr = rows[1]

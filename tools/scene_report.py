@@ -27,7 +27,8 @@ def run(name, spp):
     gen_s = time.time() - t0
     out = {"config": name, "width": w, "height": h, "spp_rendered": spp, "gen_s": round(gen_s, 2), "host_mb": round(scene.host_bytes() / 1e6, 1)}
     for mode in ("timed", "stats"):
-        r = RenderFactory.createRender(RenderType.eCompute, traversal_stats=(mode == "stats"), stage_timers=True)
+        r = RenderFactory.createRender(RenderType.eCompute, traversal_stats=(mode == "stats"), stage_timers=True,
+                                       curve_split=int(os.environ.get("STRELKA_CURVE_SPLIT", "0")))
         r.setScene(scene)
         r.setSharedContext(SharedContext(mSettingsManager=settings))
         r.init()
@@ -61,6 +62,7 @@ def run(name, spp):
                        extend_gbs=round(b_ext * timed["radiance_rays"] / (ext_ms * 1e-3) / 1e9, 1) if ext_ms else None,
                        shadow_gbs=round(b_sh * timed["shadow_rays"] / (sh_ms * 1e-3) / 1e9, 1) if sh_ms else None)
             out["extend_roofline_frac"] = round(out["extend_gbs"] / HBM, 3) if out["extend_gbs"] else None
+            out["shadow_roofline_frac"] = round(out["shadow_gbs"] / HBM, 3) if out["shadow_gbs"] else None
         buf.destroy()
         r.destroy()
     print(json.dumps(out), flush=True)
