@@ -260,8 +260,30 @@ class Render:
 
         return torch.as_tensor(_Wrap(), device=f"cuda:{self._device}")
 
+    @staticmethod
+    def _prefer_bundled_nccl() -> None:
+        """A Python process that (later) imports torch must share ONE libnccl with it: torch's wheel links against its
+        bundled copy (nvidia/nccl/lib/libnccl.so.2) and the dynamic loader reuses whatever object already carries that
+        SONAME -- an older system libnccl loaded first breaks `import torch` (undefined ncclDevCommCreate).  So point
+        the library's dlopen at the bundled copy when there is one (STRELKA_B200_NCCL, read by sb_comm_*)."""
+        import importlib.util
+        import os
+
+        if os.environ.get("STRELKA_B200_NCCL"):
+            return
+        try:
+            spec = importlib.util.find_spec("nvidia.nccl")
+        except (ImportError, ValueError):
+            spec = None
+        for base in (spec.submodule_search_locations if spec and spec.submodule_search_locations else []):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["STRELKA_B200_NCCL"] = cand
+                return
+
     def comm_unique_id(self) -> bytes:
         """ncclGetUniqueId through the ABI (rank 0); hand the bytes to the other ranks out of band."""
+        self._prefer_bundled_nccl()
         buf = C.create_string_buffer(_abi.SB_COMM_ID_BYTES)
         _check(self._lib, None, self._lib.sb_comm_get_unique_id(buf), "sb_comm_get_unique_id")
         return buf.raw
@@ -269,6 +291,7 @@ class Render:
     def comm_init(self, unique_id: bytes, rank: int, world: int) -> None:
         """Join the NCCL group (collective).  The settings manager gets the matching sharding keys."""
         assert len(unique_id) == _abi.SB_COMM_ID_BYTES
+        self._prefer_bundled_nccl()
         _check(self._lib, self._ctx, self._lib.sb_comm_init(self._ctx, unique_id, rank, world), "sb_comm_init")
         sm = self.mSharedCtx.mSettingsManager
         sm.setAs("render/b200/sampleOffset", int(rank))

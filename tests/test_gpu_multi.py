@@ -89,6 +89,6 @@ def test_two_ranks_sum_to_the_single_gpu_image():
     for i in range(2):
         np.testing.assert_allclose(out[i][1][..., :3], want[..., :3], rtol=2e-5, atol=1e-7)
     assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][0], out[1][0])
-    # the intermediate image is the estimate from the first 8 + 8 samples... of which only indices < 13 exist: 8 per rank
-    # asked, 7 / 6 owned -> after two calls of 4 the ranks hold 8 each?  no: 4 + 4 = 8 > 7: rank 0 stops at 7, rank 1 at 6
+    # after 4 + 4 iterations per rank the ranks already hold all their samples (7 and 6 of 13): the intermediate image
+    # is the final one
     np.testing.assert_allclose(out[0][0][..., :3], want[..., :3], rtol=2e-5, atol=1e-7)
