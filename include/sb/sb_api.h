@@ -412,6 +412,10 @@ sb_result sb_test_sampler(sb_ctx* ctx, uint32_t n, const uint32_t* x, const uint
 sb_result sb_test_light_sample(sb_ctx* ctx, uint32_t n, const sb_light* lights, const float* hit_points,
                                const float* u, uint32_t method, float* out);
 
+/* tex::lookup_float4 (texture_support_cuda.h:287-314) of texture `index` (0-based) of the current scene at n (u, v)
+ * pairs -> n rgba quadruples: the hardware-filtered lookups the shade kernel performs for textured materials. */
+sb_result sb_test_texture(sb_ctx* ctx, uint32_t index, uint32_t n, const float* uv, float* out);
+
 /* The material protocol of closest_hit.cu:474-545 on caller inputs: per item mdlcode_sample(k1, xi) and
  * mdlcode_evaluate(k1, k2) of material `m` (the device implementations the shade kernel runs).
  * in : 19 floats per item: shading normal[3], geometric normal[3], tangent_u[3], k1[3], xi[4], k2 for evaluate[3]

@@ -21,6 +21,7 @@
 #include "lights.h"
 #include "curve.h"
 #include "bsdf.h"
+#include "texture.h"
 #include "bvh2.h"
 
 #include <atomic>
@@ -163,6 +164,7 @@ struct orc_scene
     std::vector<uint32_t> curveVertexCounts;
     std::vector<sb_light> lights;
     std::vector<sb_material> materials;
+    std::vector<Texture> textures;
     std::vector<InstanceData> instances;
     std::vector<WorldTri> tris;
     std::vector<WorldSeg> segs;
@@ -178,6 +180,15 @@ void build_scene(orc_scene& S, const sb_scene_view& v)
     S.vertices.assign(v.vertices, v.vertices + v.num_vertices);
     S.indices.assign(v.indices, v.indices + v.num_indices);
     S.meshes.assign(v.meshes, v.meshes + v.num_meshes);
+    S.textures.clear();
+    for (uint32_t i = 0; v.textures && i < v.num_textures; ++i)
+    {
+        Texture t;
+        t.width = v.textures[i].width;
+        t.height = v.textures[i].height;
+        t.rgba.assign(v.textures[i].pixels, v.textures[i].pixels + size_t(t.width) * t.height * 4);
+        S.textures.push_back(std::move(t));
+    }
     S.curves.assign(v.curves, v.curves + v.num_curves);
     S.curvePoints.resize(v.num_curve_points);
     for (uint64_t i = 0; i < v.num_curve_points; ++i)
@@ -462,7 +473,17 @@ void hit_light(const RenderParams& P, const InstanceData& inst, const f3& rayO, 
 struct Surface
 {
     f3 position, normal, geomNormal, tangent;
+    f2 uv{ 0.5f, 0.5f }; // state.text_coords[0]: interpolated st for triangles, fixed 0.5 for curves (closest_hit.cu:446)
 };
+
+// unpackUV, closest_hit.cu:246-254
+inline f2 unpack_uv(uint32_t val)
+{
+    f2 uv;
+    uv.y = float((val & 0xffff0000u) >> 16) / 16383.99999f * 20.0f - 10.0f;
+    uv.x = float(val & 0x0000ffffu) / 16383.99999f * 20.0f - 10.0f;
+    return uv;
+}
 
 // fillTriangleGeomData, closest_hit.cu:365-421
 Surface tri_surface(const orc_scene& S, const InstanceData& inst, const Hit& h, bool inside)
@@ -483,6 +504,12 @@ Surface tri_surface(const orc_scene& S, const InstanceData& inst, const Hit& h, 
     s.normal = normalize(xform_normal(inst.w2o, objN));
     s.geomNormal = normalize(xform_normal(inst.w2o, cross(p1 - p0, p2 - p0)));
     s.tangent = normalize(xform_normal(inst.w2o, interp3(t0, t1, t2, h.u, h.v))); // quirk Q11
+    {
+        // interpolateAttrib(uv0, uv1, uv2, barycentrics), closest_hit.cu:391-396
+        const f2 a = unpack_uv(v0.uv), b = unpack_uv(v1.uv), c = unpack_uv(v2.uv);
+        const float w0 = 1.0f - h.u - h.v;
+        s.uv = f2{ a.x * w0 + b.x * h.u + c.x * h.v, a.y * w0 + b.y * h.u + c.y * h.v };
+    }
     const float flip = inside ? -1.0f : 1.0f;
     s.geomNormal *= flip;
     s.normal *= flip;
@@ -528,8 +555,33 @@ void hit_surface(const RenderParams& P, const InstanceData& inst, const Hit& h, 
 {
     const orc_scene& S = *P.scene;
     const bool isInside = prd.inside;
-    const Surface sf = (h.kind == 1) ? tri_surface(S, inst, h, isInside) : curve_surface(S, inst, h, rayO, rayD, isInside);
-    const sb_material& mat = S.materials[inst.material];
+    const Surface sf0 = (h.kind == 1) ? tri_surface(S, inst, h, isInside) : curve_surface(S, inst, h, rayO, rayD, isInside);
+    const sb_material& matRecord = S.materials[inst.material];
+    // mdlcode_init (closest_hit.cu:502) evaluates the material's texture inputs for this hit: the UsdUVTexture read by
+    // diffuseColor replaces the constant, the one read by `normal` (scale 2, bias -1) perturbs state.normal in the
+    // tangent frame (tangent_u, tangent_v = cross(N, T), N) (closest_hit.cu:408, 484-486)
+    sb_material mat = matRecord;
+    Surface sfm = sf0;
+    if (h.kind == 1 && !S.textures.empty())
+    {
+        if (mat.diffuse_texture >= 1 && mat.diffuse_texture <= S.textures.size())
+        {
+            const f4 c = texture_lookup(S.textures[mat.diffuse_texture - 1], sf0.uv.x, sf0.uv.y);
+            mat.base_color[0] = c.x;
+            mat.base_color[1] = c.y;
+            mat.base_color[2] = c.z;
+        }
+        if (mat.normal_texture >= 1 && mat.normal_texture <= S.textures.size())
+        {
+            const f4 c = texture_lookup(S.textures[mat.normal_texture - 1], sf0.uv.x, sf0.uv.y);
+            const f3 nts{ c.x * 2.0f - 1.0f, c.y * 2.0f - 1.0f, c.z * 2.0f - 1.0f };
+            const f3 bitangent = cross(sf0.normal, sf0.tangent);
+            const f3 nw = nts.x * sf0.tangent + nts.y * bitangent + nts.z * sf0.normal;
+            if (dot(nw, nw) > 0.0f)
+                sfm.normal = normalize(nw);
+        }
+    }
+    const Surface& sf = sfm;
 
     if (P.st.debug == 1)
     {
@@ -1124,6 +1176,19 @@ void orc_offset_ray(const float* p, const float* n, float* out)
     out[0] = r.x;
     out[1] = r.y;
     out[2] = r.z;
+}
+
+// texture lookup hook: n (u, v) pairs on texture `index0` (0-based) -> rgba
+void orc_texture_lookup(const orc_scene* scene, uint32_t index0, uint32_t n, const float* uv, float* out)
+{
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const f4 c = texture_lookup(scene->textures[index0], uv[2 * i], uv[2 * i + 1]);
+        out[4 * i] = c.x;
+        out[4 * i + 1] = c.y;
+        out[4 * i + 2] = c.z;
+        out[4 * i + 3] = c.w;
+    }
 }
 
 // BSDF hook, batched.  in: 19 floats per item (n[3], ng[3], tangent[3], k1[3], xi[4], k2 for evaluate[3]);

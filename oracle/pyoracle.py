@@ -50,6 +50,7 @@ def lib() -> C.CDLL:
         _lib.orc_curve_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.orc_curve_intersect_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.orc_offset_ray.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_texture_lookup.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib.orc_bsdf_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib.orc_camera_matrices.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         _lib.orc_postprocess.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_float]
@@ -107,6 +108,12 @@ class OracleScene:
                                 threads, _p(cnt))
         if counters is not None:
             counters.update(paths=int(cnt[0]), radiance_rays=int(cnt[1]), shadow_rays=int(cnt[2]))
+        return out
+
+    def texture_lookup(self, index: int, uv) -> np.ndarray:
+        uv = np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 2)
+        out = np.zeros((len(uv), 4), dtype=np.float32)
+        lib().orc_texture_lookup(self._h, index, len(uv), _p(uv), _p(out))
         return out
 
     def trace(self, rays, mode: int = 0) -> np.ndarray:

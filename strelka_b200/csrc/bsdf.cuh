@@ -123,10 +123,9 @@ struct UpsLobes
     float cc;
     float ccAlpha;
 };
-SB_HD UpsLobes ups_init(const sb_material& m)
+SB_HD UpsLobes ups_init(const sb_material& m, const float3& base)
 {
     UpsLobes L;
-    const float3 base = mk3(m.base_color[0], m.base_color[1], m.base_color[2]);
     const float metallic = saturate(m.metallic);
     const float rough = saturate(m.roughness);
     L.alpha = fmaxf(rough * rough, 1e-3f);
@@ -209,10 +208,12 @@ SB_HD BsdfEval ups_eval_core(const UpsLobes& L, const UpsWeights& w, const float
 
 // mdlcode_evaluate stand-in.  n = shading normal, ng = geometric normal (both already flipped by
 // `inside`, closest_hit.cu:405-406), k1 = -ray_dir, k2 = direction to the light.
+// base = the material's base colour after texturing (m.base_color, or the diffuse texture's texel).
 // PREVIEW = false compiles the UsdPreviewSurface model out (scenes whose materials are all diffuse), HAIR = false the
 // hair fibre model (scenes without an SB_MATERIAL_HAIR material).  tangent = state.tangent_u (closest_hit.cu:485).
 template <bool PREVIEW = true, bool HAIR = true>
-SB_HD BsdfEval bsdf_evaluate(const sb_material& m, const float3& n, const float3& ng, const float3& tangent, const float3& k1, const float3& k2)
+SB_HD BsdfEval bsdf_evaluate(const sb_material& m, const float3& base, const float3& n, const float3& ng, const float3& tangent, const float3& k1,
+                             const float3& k2)
 {
     BsdfEval e;
     e.diffuse = mk3(0.0f);
@@ -232,22 +233,22 @@ SB_HD BsdfEval bsdf_evaluate(const sb_material& m, const float3& n, const float3
     }
     if (PREVIEW && m.model == SB_MATERIAL_USD_PREVIEW_SURFACE)
     {
-        const UpsLobes L = ups_init(m);
+        const UpsLobes L = ups_init(m, base);
         const UpsWeights w = ups_weights(L, nk1);
         if (w.pc + w.ps + w.pd <= 0.0f)
             return e;
         return ups_eval_core(L, w, n, k1, k2, nk1, nk2);
     }
     // SB_MATERIAL_DIFFUSE: Lambert
-    const float3 c = mk3(m.base_color[0], m.base_color[1], m.base_color[2]);
-    e.diffuse = c * (nk2 / kPi);
+    e.diffuse = base * (nk2 / kPi);
     e.pdf = nk2 / kPi;
     return e;
 }
 
 // mdlcode_sample stand-in.  xi = (z1..z4) of closest_hit.cu:510-519.
 template <bool PREVIEW = true, bool HAIR = true>
-SB_HD BsdfSample bsdf_sample(const sb_material& m, const float3& n, const float3& ng, const float3& tangent, const float3& k1, const float4& xi)
+SB_HD BsdfSample bsdf_sample(const sb_material& m, const float3& base, const float3& n, const float3& ng, const float3& tangent, const float3& k1,
+                             const float4& xi)
 {
     BsdfSample s;
     s.k2 = mk3(0.0f);
@@ -267,7 +268,7 @@ SB_HD BsdfSample bsdf_sample(const sb_material& m, const float3& n, const float3
     }
     if (PREVIEW && m.model == SB_MATERIAL_USD_PREVIEW_SURFACE)
     {
-        const UpsLobes L = ups_init(m);
+        const UpsLobes L = ups_init(m, base);
         const UpsWeights w = ups_weights(L, nk1);
         if (w.pc + w.ps + w.pd <= 0.0f)
             return s;
@@ -303,7 +304,7 @@ SB_HD BsdfSample bsdf_sample(const sb_material& m, const float3& n, const float3
         return s;
     s.k2 = k2;
     s.pdf = nk2 / kPi;
-    s.bsdf_over_pdf = mk3(m.base_color[0], m.base_color[1], m.base_color[2]);
+    s.bsdf_over_pdf = base;
     s.event = EV_DIFFUSE | EV_REFLECTION;
     return s;
 }

@@ -45,6 +45,13 @@ struct alignas(16) TriShade
 };
 static_assert(sizeof(TriShade) == 64, "TriShade is fetched as four 16-byte loads");
 
+// one texture as the host emulation sees it (the product samples cudaTextureObject_t, never this)
+struct TexHost
+{
+    const uint8_t* pixels; // RGBA8
+    uint32_t width, height;
+};
+
 struct SceneDev
 {
     // uploaded scene arrays (same layouts as the host structs)
@@ -72,6 +79,12 @@ struct SceneDev
     bool onlyRectLights = false; // every light is a rect light (with rectLightSamplingMethod 0 the shade kernel keeps only that sampler)
     bool anyPreviewMaterial = true; // false: every material is a diffuse one (the shade kernel drops the UsdPreviewSurface code)
     bool anyHairMaterial = false; // true: some material is SB_MATERIAL_HAIR (the shade kernel keeps the fibre BSDF)
+    // textures (UsdUVTexture inputs): CUDA texture objects as the reference creates them (OptixRender.cpp:1191-1268);
+    // triUv = the packed st of the three corners per GLOBAL triangle id, only built for scenes that have a texture
+    const unsigned long long* textures = nullptr; // cudaTextureObject_t[numTextures] (device array)
+    uint32_t numTextures = 0;
+    uint4* triUv = nullptr; // x, y, z = sb_vertex.uv of corner 0, 1, 2
+    const struct TexHost* texHost = nullptr; // host emulation of the same lookups (tests/emul only)
 };
 
 // SAH constants of the BVH2 -> BVH8 cut (collapse_dp_node).  Ylitie 2017 uses node : triangle = 1 : 0.3; measured
@@ -415,6 +428,15 @@ inline void build_scene_bvhs(Exec& ex, SceneDev& S, const uint32_t* instTriFirst
             }
             sh.material = I.material;
             shade[g] = sh;
+            if (Sv.triUv)
+            {
+                uint4 puv;
+                puv.x = Sv.vertices[vi[0]].uv;
+                puv.y = Sv.vertices[vi[1]].uv;
+                puv.z = Sv.vertices[vi[2]].uv;
+                puv.w = 0u;
+                Sv.triUv[g] = puv;
+            }
             TriRec r;
             r.v0 = mk4(p[0], u2f(t));
             r.e1 = mk4(p[1] - p[0], u2f(inst | (I.mask << 28)));

@@ -514,7 +514,7 @@ struct StagedSink
 #ifndef SB_SHADE_MIN_BLOCKS
 #define SB_SHADE_MIN_BLOCKS 8 // measured: 64 registers + a few L1 spills beat 111 registers at 25 % occupancy (latency-bound kernel)
 #endif
-template <bool CURVES, bool PREVIEW, bool RECT_UNIFORM, bool HAIR = false>
+template <bool CURVES, bool PREVIEW, bool RECT_UNIFORM, bool HAIR = false, bool TEX = false>
 __global__ void __launch_bounds__(kBlock, SB_SHADE_MIN_BLOCKS) k_shade(FrameParams P, SceneDev S, Queues Q, uint32_t depth)
 {
     // 12 KB of byte-sliced Sobol tables per CTA (L2-resident source; 6 x 128-bit loads per thread)
@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(kBlock, SB_SHADE_MIN_BLOCKS) k_shade(FramePara
                 ps.flags = f2u(th.w);
                 ps.pathId = f2u(ro.w);
                 ps.L = Q.Lacc[ps.pathId];
-                next = shade_bounce<CURVES, PREVIEW, RECT_UNIFORM, HAIR>(P, S, ps, ha, hb, depth, s_tab, s_unpack, sink);
+                next = shade_bounce<CURVES, PREVIEW, RECT_UNIFORM, HAIR, TEX>(P, S, ps, ha, hb, depth, s_tab, s_unpack, sink);
             }
         }
         uint32_t sslot, nslot;
@@ -1058,7 +1058,15 @@ void launch_wavefront_batch(const LaunchCfg& cfg, const FrameParams& P, const Sc
             ScopedStage sc(cfg, kStageShade);
             // the variant without the code paths this scene cannot take
             const bool preview = S.anyPreviewMaterial, rectUniform = S.onlyRectLights && P.rectMethod == 0u;
-            if (S.anyHairMaterial)
+            if (S.numTextures != 0u)
+            {
+                // textured scenes run the general variant (every material model, texture lookups)
+                if (rectUniform)
+                    k_shade<true, true, true, true, true><<<grid_for(cfg, SB_SHADE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
+                else
+                    k_shade<true, true, false, true, true><<<grid_for(cfg, SB_SHADE_GRID), kBlock, 0, st>>>(P, S, Q, depth);
+            }
+            else if (S.anyHairMaterial)
             {
                 // scenes with a hair material run the general variant (curves, every material model)
                 if (rectUniform)
@@ -1265,6 +1273,24 @@ void launch_test_trace_production(const LaunchCfg& cfg, const FrameParams& P, co
     SB_CUDA_CHECK(cudaGetLastError());
 }
 
+// sb_test_texture: n lookups of texture index1 (1-based) at (u, v) -> rgba
+__global__ void k_test_texture(SceneDev S, uint32_t index1, uint32_t n, const float* uv, float* out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const float4 c = sample_texture(S, index1, uv[2 * i], uv[2 * i + 1]);
+        out[4 * i] = c.x;
+        out[4 * i + 1] = c.y;
+        out[4 * i + 2] = c.z;
+        out[4 * i + 3] = c.w;
+    }
+}
+void launch_test_texture(const LaunchCfg& cfg, const SceneDev& S, uint32_t index1, uint32_t n, const float* uv, float* out)
+{
+    k_test_texture<<<grid_for(cfg, 2), 128, 0, cfg.stream>>>(S, index1, n, uv, out);
+    SB_CUDA_CHECK(cudaGetLastError());
+}
+
 // sb_test_bsdf: the BSDF protocol (sample + evaluate) on caller inputs; 19 floats in, 15 floats out per item
 __global__ void k_test_bsdf(sb_material m, uint32_t n, const float* in, float* out)
 {
@@ -1273,7 +1299,8 @@ __global__ void k_test_bsdf(sb_material m, uint32_t n, const float* in, float* o
         const float* a = in + 19 * size_t(i);
         float* o = out + 15 * size_t(i);
         const float3 N = mk3(a[0], a[1], a[2]), NG = mk3(a[3], a[4], a[5]), T = mk3(a[6], a[7], a[8]), K1 = mk3(a[9], a[10], a[11]);
-        const BsdfSample s = bsdf_sample<true, true>(m, N, NG, T, K1, mk4(a[12], a[13], a[14], a[15]));
+        const float3 base = mk3(m.base_color[0], m.base_color[1], m.base_color[2]);
+        const BsdfSample s = bsdf_sample<true, true>(m, base, N, NG, T, K1, mk4(a[12], a[13], a[14], a[15]));
         o[0] = s.k2.x;
         o[1] = s.k2.y;
         o[2] = s.k2.z;
@@ -1282,7 +1309,7 @@ __global__ void k_test_bsdf(sb_material m, uint32_t n, const float* in, float* o
         o[5] = s.bsdf_over_pdf.z;
         o[6] = s.pdf;
         o[7] = float(s.event);
-        const BsdfEval e = bsdf_evaluate<true, true>(m, N, NG, T, K1, mk3(a[16], a[17], a[18]));
+        const BsdfEval e = bsdf_evaluate<true, true>(m, base, N, NG, T, K1, mk3(a[16], a[17], a[18]));
         o[8] = e.diffuse.x;
         o[9] = e.diffuse.y;
         o[10] = e.diffuse.z;

@@ -52,6 +52,8 @@ struct sb_ctx
 
     SceneDev scene;
     bool haveScene = false;
+    std::vector<cudaArray_t> texArrays; // one uchar4 array + one filtered texture object per sb_texture
+    std::vector<cudaTextureObject_t> texObjects;
     uint32_t* instTriFirst = nullptr;
     SegInfo* segInfoUnsorted = nullptr;
 
@@ -145,6 +147,17 @@ void free_scene(sb_ctx* c)
     pool_free(s.segNodes, st);
     pool_free(c->instTriFirst, st);
     pool_free(c->segInfoUnsorted, st);
+    pool_free(s.triUv, st);
+    {
+        unsigned long long* t = const_cast<unsigned long long*>(s.textures);
+        pool_free(t, st);
+    }
+    for (cudaTextureObject_t o : c->texObjects)
+        cudaDestroyTextureObject(o);
+    for (cudaArray_t a : c->texArrays)
+        cudaFreeArray(a);
+    c->texObjects.clear();
+    c->texArrays.clear();
     s = SceneDev();
     c->haveScene = false;
 }
@@ -680,6 +693,56 @@ sb_result sb_set_scene(sb_ctx* c, const sb_scene_view* v)
         def.base_color[0] = def.base_color[1] = def.base_color[2] = 1.0f;
         s.materials = dev_upload(&def, 1, st);
     }
+    // ---- textures (OptiXRender::loadTextureFromFile, OptixRender.cpp:1191-1268: uchar4 array, wrap, linear filter,
+    // normalised coordinates, normalised-float reads) ---------------------------------------------------------------
+    bool anyTexturedMaterial = false;
+    for (uint32_t i = 0; i < v->num_materials; ++i)
+    {
+        const sb_material& m = v->materials[i];
+        if (m.diffuse_texture > v->num_textures || m.normal_texture > v->num_textures)
+            throw std::runtime_error("sb_set_scene: material " + std::to_string(i) + " references a missing texture");
+        anyTexturedMaterial = anyTexturedMaterial || m.diffuse_texture != 0u || m.normal_texture != 0u;
+    }
+    if (v->num_textures && v->textures)
+    {
+        for (uint32_t i = 0; i < v->num_textures; ++i)
+        {
+            const sb_texture& t = v->textures[i];
+            if (!t.pixels || t.width == 0 || t.height == 0)
+                throw std::runtime_error("sb_set_scene: texture " + std::to_string(i) + " is empty");
+            const cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
+            cudaArray_t arr = nullptr;
+            SB_CUDA_CHECK(cudaMallocArray(&arr, &desc, t.width, t.height));
+            c->texArrays.push_back(arr);
+            SB_CUDA_CHECK(cudaMemcpy2DToArray(arr, 0, 0, t.pixels, size_t(t.width) * 4, size_t(t.width) * 4, t.height, cudaMemcpyHostToDevice));
+            cudaResourceDesc res;
+            std::memset(&res, 0, sizeof(res));
+            res.resType = cudaResourceTypeArray;
+            res.res.array.array = arr;
+            cudaTextureDesc td;
+            std::memset(&td, 0, sizeof(td));
+            td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeWrap;
+            td.filterMode = cudaFilterModeLinear;
+            td.readMode = cudaReadModeNormalizedFloat;
+            td.normalizedCoords = 1;
+            cudaTextureObject_t obj = 0;
+            SB_CUDA_CHECK(cudaCreateTextureObject(&obj, &res, &td, nullptr));
+            c->texObjects.push_back(obj);
+        }
+        static_assert(sizeof(cudaTextureObject_t) == sizeof(unsigned long long), "texture handles are passed as 64-bit integers");
+        s.textures = dev_upload(reinterpret_cast<const unsigned long long*>(c->texObjects.data()), c->texObjects.size(), st);
+        s.numTextures = v->num_textures;
+        if (anyTexturedMaterial && numTris)
+        {
+            void* p = nullptr;
+            if (cudaMallocAsync(&p, sizeof(uint4) * numTris, st) != cudaSuccess)
+            {
+                cudaGetLastError();
+                throw std::bad_alloc();
+            }
+            s.triUv = static_cast<uint4*>(p);
+        }
+    }
     s.instances = dev_upload(inst.data(), inst.size(), st);
     s.numInstances = v->num_instances;
     s.numLights = v->num_lights;
@@ -1167,6 +1230,24 @@ sb_result sb_test_light_sample(sb_ctx* c, uint32_t n, const sb_light* lights, co
     cudaFree(dl);
     cudaFree(dh);
     cudaFree(du);
+    cudaFree(dout);
+    SB_API_END
+}
+
+sb_result sb_test_texture(sb_ctx* c, uint32_t index, uint32_t n, const float* uv, float* out)
+{
+    if (!c || !uv || !out)
+        return SB_FAIL;
+    SB_API_BEGIN(c)
+    if (!c->haveScene || index >= c->scene.numTextures)
+        throw std::runtime_error("sb_test_texture: no such texture in the current scene");
+    cudaStream_t st = c->stream;
+    float* duv = dev_upload(uv, size_t(n) * 2, st);
+    float* dout = dev_alloc<float>(size_t(n) * 4);
+    launch_test_texture(launch_cfg(c), c->scene, index + 1u, n, duv, dout);
+    SB_CUDA_CHECK(cudaMemcpyAsync(out, dout, sizeof(float) * 4 * size_t(n), cudaMemcpyDeviceToHost, st));
+    SB_CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFree(duv);
     cudaFree(dout);
     SB_API_END
 }

@@ -270,7 +270,51 @@ SB_HD Surface curve_surface(const SceneDev& S, const InstDev& I, uint32_t segInd
 // CURVES / PREVIEW = false compile the curve attributes / the UsdPreviewSurface model out for scenes without them,
 // RECT_UNIFORM = true everything but the uniform rect-light sampler (all lights rect, rectLightSamplingMethod 0),
 // HAIR = false the hair fibre BSDF (the shade kernel is register-bound; the host picks the variant per scene)
-template <bool CURVES = true, bool PREVIEW = true, bool RECT_UNIFORM = false, bool HAIR = true, class Sink>
+// unpackUV, closest_hit.cu:246-254: 16-16 bit st over [-10, 10] (v already flipped by the delegate, RenderPass.cpp:109-114)
+SB_HD float2 unpack_uv(uint32_t val)
+{
+    float2 uv;
+    uv.y = float((val & 0xffff0000u) >> 16) / 16383.99999f * 20.0f - 10.0f;
+    uv.x = float(val & 0x0000ffffu) / 16383.99999f * 20.0f - 10.0f;
+    return uv;
+}
+
+// CUDA's documented linear filter (Programming Guide, "Texture Fetching": normalised coordinates, wrap addressing,
+// xB = x N - 0.5, i = floor(xB), alpha = frac(xB) kept as 1.8 fixed point) over RGBA8 texels read as normalised floats:
+// what tex2D<float4> does in hardware for the texture objects the reference creates (OptixRender.cpp:1229-1252).
+// Only the host emulation of the tests runs this function; device code samples the texture object.
+SB_HD float4 texture_bilinear_rgba8(const uint8_t* px, uint32_t w, uint32_t h, float u, float v)
+{
+    const float xb = (u - floorf(u)) * float(w) - 0.5f, yb = (v - floorf(v)) * float(h) - 0.5f;
+    const float xf = floorf(xb), yf = floorf(yb);
+    const float a = floorf((xb - xf) * 256.0f + 0.5f) * (1.0f / 256.0f), b = floorf((yb - yf) * 256.0f + 0.5f) * (1.0f / 256.0f);
+    const int x0 = ((int(xf) % int(w)) + int(w)) % int(w), y0 = ((int(yf) % int(h)) + int(h)) % int(h);
+    const int x1 = (x0 + 1) % int(w), y1 = (y0 + 1) % int(h);
+    float r[4];
+    for (int c = 0; c < 4; ++c)
+    {
+        const float t00 = float(px[4 * (size_t(y0) * w + x0) + c]) * (1.0f / 255.0f), t10 = float(px[4 * (size_t(y0) * w + x1) + c]) * (1.0f / 255.0f);
+        const float t01 = float(px[4 * (size_t(y1) * w + x0) + c]) * (1.0f / 255.0f), t11 = float(px[4 * (size_t(y1) * w + x1) + c]) * (1.0f / 255.0f);
+        r[c] = (1.0f - a) * (1.0f - b) * t00 + a * (1.0f - b) * t10 + (1.0f - a) * b * t01 + a * b * t11;
+    }
+    return mk4(r[0], r[1], r[2], r[3]);
+}
+
+// tex::lookup_float4 of texture `index1` (1-based; 0 / out of range = invalid -> zero, texture_support_cuda.h:300-304)
+SB_HD float4 sample_texture(const SceneDev& S, uint32_t index1, float u, float v)
+{
+    if (index1 == 0u || index1 > S.numTextures)
+        return mk4(0.0f, 0.0f, 0.0f, 0.0f);
+#if defined(__CUDA_ARCH__)
+    return tex2D<float4>(cudaTextureObject_t(S.textures[index1 - 1u]), u, v);
+#else
+    const TexHost& t = S.texHost[index1 - 1u];
+    return texture_bilinear_rgba8(t.pixels, t.width, t.height, u, v);
+#endif
+}
+
+// TEX = true: the scene has textures (UsdUVTexture diffuse colour / tangent-space normal maps)
+template <bool CURVES = true, bool PREVIEW = true, bool RECT_UNIFORM = false, bool HAIR = true, bool TEX = true, class Sink>
 SB_HD bool shade_bounce(const FrameParams& P, const SceneDev& S, PathState& ps, const float4& ha, uint32_t hb, uint32_t depth, const uint32_t* sobolTab,
                         const float* unpackLut, Sink& sink)
 {
@@ -323,15 +367,38 @@ SB_HD bool shade_bounce(const FrameParams& P, const SceneDev& S, PathState& ps, 
     // ---- __closesthit__radiance, closest_hit.cu:456-606 --------------------------------------------
     const bool isInside = (flags & kFlagInside) != 0u;
     const Surface sf = (!CURVES || kind == 1u) ? tri_surface(I, tri, ha.y, ha.z, isInside, unpackLut) : curve_surface(S, I, f2u(ha.w), ha.y, ha.x, rayO, rayD, isInside);
-    if (P.debug == 1u)
-    {
-        ps.L = mk4((sf.normal + mk3(1.0f)) * 0.5f, 0.0f); // closest_hit.cu:504-508
-        sink.radiance_changed(ps);
-        return false;
-    }
     // (measured: fetching the material or computing the Sobol values earlier, to overlap them with the fetches
     // above, lengthens live ranges in this register-bound kernel and costs 3-8 %)
     const sb_material& mat = S.materials[I.material];
+    float3 baseColor = mk3(mat.base_color[0], mat.base_color[1], mat.base_color[2]);
+    float3 shadingNormal = sf.normal;
+    if (TEX && kind == 1u && S.triUv != nullptr && (mat.diffuse_texture | mat.normal_texture) != 0u)
+    {
+        // state.text_coords[0] (closest_hit.cu:391-396); tangent_u / tangent_v = world tangent / cross(N, T) (:408, 485-486)
+        const uint4 puv = S.triUv[f2u(ha.w)];
+        const float2 uv0 = unpack_uv(puv.x), uv1 = unpack_uv(puv.y), uv2 = unpack_uv(puv.z);
+        const float w0 = 1.0f - ha.y - ha.z;
+        const float tu = uv0.x * w0 + uv1.x * ha.y + uv2.x * ha.z, tv = uv0.y * w0 + uv1.y * ha.y + uv2.y * ha.z;
+        if (mat.diffuse_texture)
+            baseColor = mk3(sample_texture(S, mat.diffuse_texture, tu, tv));
+        if (mat.normal_texture)
+        {
+            // UsdUVTexture normal map: scale 2, bias -1; tangent space (tangent_u, tangent_v, normal)
+            const float4 t = sample_texture(S, mat.normal_texture, tu, tv);
+            const float3 nts = mk3(t.x * 2.0f - 1.0f, t.y * 2.0f - 1.0f, t.z * 2.0f - 1.0f);
+            const float3 bitangent = cross(sf.normal, sf.tangent);
+            const float3 nw = nts.x * sf.tangent + nts.y * bitangent + nts.z * sf.normal;
+            if (dot(nw, nw) > 0.0f)
+                shadingNormal = normalize(nw);
+        }
+    }
+    if (P.debug == 1u)
+    {
+        // closest_hit.cu:504-508, after mdlcode_init (:502) has put the material's shading normal into state.normal
+        ps.L = mk4((shadingNormal + mk3(1.0f)) * 0.5f, 0.0f);
+        sink.radiance_changed(ps);
+        return false;
+    }
     uint32_t px, py, pk;
     path_pixel(P, pathId, px, py, pk);
     const uint32_t sidx = sampler_index(px, py, P.sampleBase + pk * P.sampleStride, P.sppTotal);
@@ -339,7 +406,7 @@ SB_HD bool shade_bounce(const FrameParams& P, const SceneDev& S, PathState& ps, 
     // lightPoint = (v[3], v[4]), russian roulette = v[4]
     const Sample5 rn = sampler_sample5(sidx, depth, sobolTab);
     const float3 k1 = -rayD;
-    const BsdfSample bs = bsdf_sample<PREVIEW, HAIR>(mat, sf.normal, sf.geomNormal, sf.tangent, k1, mk4(rn.v[0], rn.v[1], rn.v[2], rn.v[3]));
+    const BsdfSample bs = bsdf_sample<PREVIEW, HAIR>(mat, baseColor, shadingNormal, sf.geomNormal, sf.tangent, k1, mk4(rn.v[0], rn.v[1], rn.v[2], rn.v[3]));
     if (bs.event == EV_ABSORB)
     {
         return false; // throughput = 0 (firstEventType = eAbsorb: counted by neither AOV)
@@ -373,20 +440,20 @@ SB_HD bool shade_bounce(const FrameParams& P, const SceneDev& S, PathState& ps, 
             const sb_light& l = S.lights[lightId];
             const LightSample ls = sample_light<RECT_UNIFORM>(l, rn.v[3], rn.v[4], sf.position, P.rectMethod);
             const float3 Li = mk3(l.color[0], l.color[1], l.color[2]);
-            if (dot(sf.normal, ls.L) > 0.0f && -dot(ls.L, ls.normal) > 0.0 && all_nonzero(Li))
+            if (dot(shadingNormal, ls.L) > 0.0f && -dot(ls.L, ls.normal) > 0.0 && all_nonzero(Li))
             {
                 const float lightPdf = ls.pdf * lightSelectionPdf;
-                const float3 radiance = Li * saturate(dot(sf.normal, ls.L)); // visibility applied by the shadow ray
+                const float3 radiance = Li * saturate(dot(shadingNormal, ls.L)); // visibility applied by the shadow ray
                 if (isnan3(radiance) || isnanf_(lightPdf))
                 {
                     ps.L = mk4(10000.0f, 0.0f, 0.0f, 0.0f); // quirk Q17
                     sink.radiance_changed(ps);
                     return false;
                 }
-                const bool nextEventValid = ((dot(ls.L, sf.normal) > 0.0f) != isInside) && lightPdf != 0.0f;
+                const bool nextEventValid = ((dot(ls.L, shadingNormal) > 0.0f) != isInside) && lightPdf != 0.0f;
                 if (nextEventValid)
                 {
-                    const BsdfEval ev = bsdf_evaluate<PREVIEW, HAIR>(mat, sf.normal, sf.geomNormal, sf.tangent, k1, ls.L);
+                    const BsdfEval ev = bsdf_evaluate<PREVIEW, HAIR>(mat, baseColor, shadingNormal, sf.geomNormal, sf.tangent, k1, ls.L);
                     if (isnan3(ev.diffuse) || isnan3(ev.glossy))
                     {
                         ps.L = mk4(10000.0f, 0.0f, 0.0f, 0.0f);

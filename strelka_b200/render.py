@@ -334,6 +334,17 @@ class Render:
                "sb_test_light_sample")
         return out
 
+    def test_texture(self, index: int, uv) -> np.ndarray:
+        """Hardware-filtered lookups of texture `index` (0-based) of the current scene at (N, 2) st coordinates."""
+        if not self._scene_uploaded:
+            v = self.mScene.view()
+            _check(self._lib, self._ctx, self._lib.sb_set_scene(self._ctx, C.byref(v)), "sb_set_scene")
+            self._scene_uploaded = True
+        uv = np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 2)
+        out = np.zeros((len(uv), 4), dtype=np.float32)
+        _check(self._lib, self._ctx, self._lib.sb_test_texture(self._ctx, index, len(uv), uv.ctypes.data, out.ctypes.data), "sb_test_texture")
+        return out
+
     def test_bsdf(self, material, packed_inputs) -> tuple[np.ndarray, np.ndarray]:
         """Device BSDF sample + evaluate on (N, 19) packed inputs (n, ng, tangent, k1, xi, k2); returns (sample (N, 8), eval (N, 7))."""
         m = np.ascontiguousarray(material, dtype=_abi.MATERIAL_DTYPE)

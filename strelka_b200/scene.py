@@ -145,6 +145,7 @@ class Scene:
         self.lights: list[np.ndarray] = []
         self.light_descs: list[UniformLightDesc] = []
         self.materials: list[np.ndarray] = []
+        self.textures: list[np.ndarray] = []  # (h, w, 4) uint8, row 0 = first row of the image file
         self.cameras: list[Camera] = [Camera()]
         self._rect_mesh = self._disc_mesh = self._sphere_mesh = -1
         self._keep = None
@@ -183,8 +184,18 @@ class Scene:
         m["hair_roughness_lon"] = kw.get("hair_roughness_lon", 0.3)
         m["hair_roughness_azi"] = kw.get("hair_roughness_azi", 0.3)
         m["hair_cuticle_angle"] = kw.get("hair_cuticle_angle", 0.035)
+        m["diffuse_texture"] = kw.get("diffuse_texture", 0)  # 1-based index into self.textures, 0 = none
+        m["normal_texture"] = kw.get("normal_texture", 0)
         self.materials.append(m)
         return len(self.materials) - 1
+
+    def addTexture(self, rgba8) -> int:  # noqa: N802
+        """Register an 8-bit RGBA image (what stbi_load(..., STBI_rgb_alpha) hands OptiXRender::loadTextureFromFile,
+        OptixRender.cpp:1191-1268).  Returns the 1-based index materials refer to (0 = no texture)."""
+        a = np.ascontiguousarray(rgba8, dtype=np.uint8)
+        assert a.ndim == 3 and a.shape[2] == 4
+        self.textures.append(a)
+        return len(self.textures)
 
     # ---- curves (scene.cpp:463-489) -------------------------------------------------------------
     def createCurve(self, vertex_counts, points, widths) -> int:  # noqa: N802
@@ -337,7 +348,7 @@ class Scene:
 
     def host_bytes(self) -> int:
         """Bytes of all scene arrays a backend uploads (the H2D volume of sb_set_scene)."""
-        return int(sum(v.nbytes for v in self.arrays().values()))
+        return int(sum(v.nbytes for v in self.arrays().values()) + sum(t.nbytes for t in self.textures))
 
     def view(self, pinned: bool = False) -> _abi.sb_scene_view:
         """Borrowed sb_scene_view over freshly flattened arrays (kept alive on self).  pinned=True stages
@@ -368,6 +379,15 @@ class Scene:
         v.instances, v.num_instances = p(a["instances"]), len(a["instances"])
         v.lights, v.num_lights = p(a["lights"]), len(a["lights"])
         v.materials, v.num_materials = p(a["materials"]), len(a["materials"])
+        if self.textures:
+            recs = (_abi.sb_texture * len(self.textures))()
+            for i, t in enumerate(self.textures):
+                recs[i].pixels = t.ctypes.data
+                recs[i].width, recs[i].height = t.shape[1], t.shape[0]
+            self._keep_tex = recs
+            import ctypes as _C
+
+            v.textures, v.num_textures = _C.cast(recs, _C.c_void_p), len(self.textures)
         return v
 
     def stats(self) -> dict:

@@ -76,6 +76,28 @@ emul_scene* emul_scene_create(const sb_scene_view* v, uint32_t curveSplit, char*
         s.numCurves = v->num_curves;
         s.numCurvePoints = v->num_curve_points;
         s.numCurveRadii = v->num_curve_widths;
+        // textures: the host emulation samples private copies with the documented filter (wavefront.cuh)
+        if (v->num_textures && v->textures)
+        {
+            TexHost* th = static_cast<TexHost*>(std::calloc(v->num_textures, sizeof(TexHost)));
+            e->owned.push_back(th);
+            bool used = false;
+            for (uint32_t i = 0; i < v->num_textures; ++i)
+            {
+                th[i].width = v->textures[i].width;
+                th[i].height = v->textures[i].height;
+                th[i].pixels = dup(e, v->textures[i].pixels, size_t(th[i].width) * th[i].height * 4);
+            }
+            for (uint32_t i = 0; i < v->num_materials; ++i)
+                used = used || v->materials[i].diffuse_texture || v->materials[i].normal_texture;
+            s.texHost = th;
+            s.numTextures = v->num_textures;
+            if (used && prep.numTris)
+            {
+                s.triUv = static_cast<uint4*>(std::calloc(prep.numTris, sizeof(uint4)));
+                e->owned.push_back(s.triUv);
+            }
+        }
         uint32_t* triFirst = dup(e, prep.triFirst.data(), prep.triFirst.size());
         SegInfo* segInfo = dup(e, prep.segInfo.data(), prep.segInfo.size());
         ExecHost ex;
@@ -424,7 +446,8 @@ void emul_bsdf_batch(const sb_material* m, uint32_t n, const float* in, float* o
         const float* a = in + 19 * size_t(i);
         float* o = out + 15 * size_t(i);
         const float3 N = mk3(a[0], a[1], a[2]), NG = mk3(a[3], a[4], a[5]), T = mk3(a[6], a[7], a[8]), K1 = mk3(a[9], a[10], a[11]);
-        const BsdfSample s = bsdf_sample<true, true>(*m, N, NG, T, K1, mk4(a[12], a[13], a[14], a[15]));
+        const float3 base = mk3(m->base_color[0], m->base_color[1], m->base_color[2]);
+        const BsdfSample s = bsdf_sample<true, true>(*m, base, N, NG, T, K1, mk4(a[12], a[13], a[14], a[15]));
         o[0] = s.k2.x;
         o[1] = s.k2.y;
         o[2] = s.k2.z;
@@ -433,7 +456,7 @@ void emul_bsdf_batch(const sb_material* m, uint32_t n, const float* in, float* o
         o[5] = s.bsdf_over_pdf.z;
         o[6] = s.pdf;
         o[7] = float(s.event);
-        const BsdfEval e = bsdf_evaluate<true, true>(*m, N, NG, T, K1, mk3(a[16], a[17], a[18]));
+        const BsdfEval e = bsdf_evaluate<true, true>(*m, base, N, NG, T, K1, mk3(a[16], a[17], a[18]));
         o[8] = e.diffuse.x;
         o[9] = e.diffuse.y;
         o[10] = e.diffuse.z;
