@@ -168,10 +168,11 @@ sb_material B200Render::resolveMaterial(const Scene::MaterialDescription& desc)
     return m;
 }
 
-void B200Render::uploadScene()
+sb_scene_view B200Render::buildSceneView(SceneViewStorage& st)
 {
     Scene& s = *mScene;
-    std::vector<sb_instance> inst(s.getInstances().size());
+    std::vector<sb_instance>& inst = st.instances;
+    inst.resize(s.getInstances().size());
     for (size_t i = 0; i < inst.size(); ++i)
     {
         const Instance& in = s.getInstances()[i];
@@ -181,9 +182,43 @@ void B200Render::uploadScene()
         inst[i].material_id = in.mMaterialId;
         inst[i].light_id = in.mLightId;
     }
-    std::vector<sb_material> mats;
+    std::vector<sb_material>& mats = st.materials;
+    mats.clear();
+    st.textures.clear();
+    st.texturePixels.clear();
     for (const Scene::MaterialDescription& d : s.getMaterials())
-        mats.push_back(resolveMaterial(d));
+    {
+        sb_material m = resolveMaterial(d);
+        // texture inputs: "<node>_file" params of type eTexture (Material.cpp:120-136; OptixRender.cpp:1346-1387)
+        for (const MaterialManager::Param& p : d.params)
+        {
+            if (p.type != MaterialManager::Param::Type::eTexture || !mTextureLoader)
+                continue;
+            const std::string path(reinterpret_cast<const char*>(p.value.data()), p.value.size());
+            std::vector<uint8_t> px;
+            uint32_t w = 0, h = 0;
+            if (!mTextureLoader(path, px, w, h) || px.size() != size_t(w) * h * 4 || w == 0 || h == 0)
+            {
+                std::fprintf(stderr, "B200Render: unable to load texture %s\n", path.c_str());
+                continue;
+            }
+            st.texturePixels.push_back(std::move(px));
+            const uint32_t index1 = uint32_t(st.texturePixels.size());
+            // which input the texture feeds is encoded in the node name the delegate prefixes (e.g. diffuseColor_texture_file)
+            if (p.name.find("ormal") != std::string::npos)
+                m.normal_texture = index1;
+            else
+                m.diffuse_texture = index1;
+            sb_texture t;
+            t.pixels = nullptr; // patched below: the vector may still move
+            t.width = w;
+            t.height = h;
+            st.textures.push_back(t);
+        }
+        mats.push_back(m);
+    }
+    for (size_t i = 0; i < st.textures.size(); ++i)
+        st.textures[i].pixels = st.texturePixels[i].data();
     sb_scene_view v;
     std::memset(&v, 0, sizeof(v));
     v.vertices = reinterpret_cast<const sb_vertex*>(s.getVertices().data());
@@ -206,6 +241,15 @@ void B200Render::uploadScene()
     v.num_lights = uint32_t(s.getLights().size());
     v.materials = mats.data();
     v.num_materials = uint32_t(mats.size());
+    v.textures = st.textures.empty() ? nullptr : st.textures.data();
+    v.num_textures = uint32_t(st.textures.size());
+    return v;
+}
+
+void B200Render::uploadScene()
+{
+    SceneViewStorage storage;
+    const sb_scene_view v = buildSceneView(storage);
     if (sb_set_scene(mCtx, &v) != SB_OK)
         fail("sb_set_scene");
     else

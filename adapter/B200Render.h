@@ -7,6 +7,7 @@
 #include <render/render.h>
 #include <sb/sb_api.h>
 
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -46,8 +47,28 @@ public:
     const std::string& lastError() const { return mError; }
     sb_ctx* context() { return mCtx; }
 
+    // The flattened scene exactly as uploadScene() hands it to sb_set_scene: the oka::Scene arrays passed through, the
+    // instances and materials converted.  `storage` owns the converted arrays and the decoded textures; the view
+    // borrows from it and from the scene.  Public so that tools can inspect what a Strelka scene turns into.
+    struct SceneViewStorage
+    {
+        std::vector<sb_instance> instances;
+        std::vector<sb_material> materials;
+        std::vector<sb_texture> textures;
+        std::vector<std::vector<uint8_t>> texturePixels;
+    };
+    sb_scene_view buildSceneView(SceneViewStorage& storage);
+
+    // UsdUVTexture inputs arrive as MaterialManager::Param::Type::eTexture params holding a file path (Material.cpp:
+    // 120-136); OptiXRender decodes them with stb_image (OptixRender.cpp:1191-1200).  This adapter has no image
+    // library of its own: the host hands it a decoder (path -> RGBA8, width, height).  Without one, or when decoding
+    // fails, the material keeps its constant colour (the reference logs an error and binds an empty texture).
+    using TextureLoader = std::function<bool(const std::string& path, std::vector<uint8_t>& rgba, uint32_t& width, uint32_t& height)>;
+    void setTextureLoader(TextureLoader loader) { mTextureLoader = std::move(loader); }
+
 private:
     void uploadScene();
+    TextureLoader mTextureLoader;
     sb_settings readSettings();
     void fail(const char* what);
 

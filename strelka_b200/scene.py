@@ -149,12 +149,17 @@ class Scene:
         self.cameras: list[Camera] = [Camera()]
         self._rect_mesh = self._disc_mesh = self._sphere_mesh = -1
         self._keep = None
+        # journal of the oka::Scene API calls that built this scene, in order (tools replay it through the reference's own
+        # scene.cpp: adapter/adapter_ref_test.cpp).  None once an entry was appended behind the API's back.
+        self.journal: list | None = []
 
     # ---- meshes / instances (scene.cpp:15-88) --------------------------------------------------
     def createMesh(self, vb: np.ndarray, ib) -> int:  # noqa: N802
         vb = np.ascontiguousarray(vb, dtype=VERTEX_DTYPE)
         ib = np.ascontiguousarray(ib, dtype=np.uint32).reshape(-1)
         mesh_id = len(self.meshes)
+        if self.journal is not None and not getattr(self, "_in_light", False):
+            self.journal.append(("mesh", vb, ib))
         self.meshes.append((self._nidx, len(ib), self._nverts, len(vb)))
         self._vb.append(vb)
         self._ib.append(ib)
@@ -164,6 +169,8 @@ class Scene:
 
     def createInstance(self, type_: int, geom_id: int, material_id: int, transform, light_id: int = 0xFFFFFFFF) -> int:  # noqa: N802
         t = np.asarray(transform, dtype=np.float64).reshape(4, 4)
+        if self.journal is not None and not getattr(self, "_in_light", False):
+            self.journal.append(("instance", t.T.astype(_F).reshape(16), type_, geom_id, material_id & 0xFFFFFFFF))
         self.instances.append((t.T.astype(_F).reshape(16), type_, geom_id, material_id & 0xFFFFFFFF, light_id & 0xFFFFFFFF))
         return len(self.instances) - 1
 
@@ -186,6 +193,8 @@ class Scene:
         m["hair_cuticle_angle"] = kw.get("hair_cuticle_angle", 0.035)
         m["diffuse_texture"] = kw.get("diffuse_texture", 0)  # 1-based index into self.textures, 0 = none
         m["normal_texture"] = kw.get("normal_texture", 0)
+        if self.journal is not None:
+            self.journal.append(("material", m))
         self.materials.append(m)
         return len(self.materials) - 1
 
@@ -206,6 +215,8 @@ class Scene:
             wstart, wcount = self._ncwidths, len(widths)
         else:
             wstart, wcount = 0xFFFFFFFF, 0xFFFFFFFF
+        if self.journal is not None:
+            self.journal.append(("curve", counts, points, widths))
         self.curves.append((self._nccounts, len(counts), self._ncpoints, len(points), wstart, wcount))
         self._cpoints.append(points)
         self._ccounts.append(counts)
@@ -229,12 +240,14 @@ class Scene:
             seg = rings = 16
             pos, nrm, idx = [], [], []
             for i in range(rings + 1):
-                theta = _F(i) * _F(np.pi) / _F(rings)
-                st, ct = np.sin(theta, dtype=_F), np.cos(theta, dtype=_F)
+                # scene.cpp:160-176: float angles, ::sin / ::cos of the C library (double) narrowed to float, float products
+                # (pinned against the reference's own scene.cpp by tests/test_adapter_real_headers.py)
+                theta = _F(_F(i) * _F(np.pi) / _F(rings))
+                st, ct = _F(np.sin(np.float64(theta))), _F(np.cos(np.float64(theta)))
                 for j in range(seg + 1):
-                    phi = _F(j) * _F(2.0) * _F(np.pi) / _F(seg)
-                    sp, cp = np.sin(phi, dtype=_F), np.cos(phi, dtype=_F)
-                    p = (cp * st, ct, sp * st)
+                    phi = _F(_F(_F(j) * _F(2.0)) * _F(np.pi) / _F(seg))
+                    sp, cp = _F(np.sin(np.float64(phi))), _F(np.cos(np.float64(phi)))
+                    p = (_F(cp * st), ct, _F(sp * st))
                     pos.append(p)
                     nrm.append(p)
             for i in range(rings):
@@ -252,12 +265,12 @@ class Scene:
         if self._disc_mesh < 0:
             pos = [(0.0, 0.0, 0.0), (1.0, 0.0, 0.0)]
             idx = []
-            step = 2.0 * np.pi / 16
-            angle = 0.0
+            step = _F(2.0 * np.pi / 16)  # scene.cpp:224-231: `const float step`, `float angle` accumulated in float
+            angle = _F(0.0)
             for _ in range(16):
                 idx += [0, len(pos) - 1]
-                angle += step
-                pos.append((np.cos(angle), np.sin(angle), 0.0))
+                angle = _F(angle + step)
+                pos.append((_F(np.cos(np.float64(angle))), _F(np.sin(np.float64(angle))), 0.0))
                 idx.append(len(pos) - 1)
             vb = make_vertices(pos, normals=[(0.0, 0.0, 1.0)] * len(pos))
             vb["uv"] = 0
@@ -267,6 +280,9 @@ class Scene:
     # ---- lights (scene.cpp:306-408) ---------------------------------------------------------------
     def createLight(self, desc: UniformLightDesc) -> int:  # noqa: N802
         light_id = len(self.lights)
+        if self.journal is not None:
+            self.journal.append(("light", desc))
+        self._in_light = True  # the light's mesh and instance are created by Scene::createLight itself
         self.lights.append(np.zeros((), dtype=LIGHT_DTYPE))
         self.light_descs.append(desc)
         self.updateLight(light_id, desc)
@@ -284,7 +300,51 @@ class Scene:
             s = scale_matrix(desc.radius, desc.radius, desc.radius)
         transform = np.asarray(desc.xform, dtype=np.float64) @ s
         self.createInstance(SB_INSTANCE_LIGHT, mesh_id, 0xFFFFFFFF, transform, light_id)
+        self._in_light = False
         return light_id
+
+    def write_journal(self, path, width: int, height: int, spp_total: int, depth: int) -> None:
+        """Serialise the API-call journal for adapter/adapter_ref_test.cpp (which replays it through the reference's own
+        oka::Scene implementation)."""
+        import struct
+
+        if self.journal is None:
+            raise ValueError("this scene was not built through the Scene API alone")
+        cam = self.getCamera(0)
+
+        def vec(f, arr):
+            arr = np.ascontiguousarray(arr)
+            f.write(struct.pack("<Q", len(arr)))
+            f.write(arr.tobytes())
+
+        with open(path, "wb") as f:
+            f.write(struct.pack("<4I", width, height, spp_total, depth))
+            f.write(struct.pack("<8f", *cam.position, *cam.orientation, cam.fov))
+            for op in self.journal:
+                if op[0] == "mesh":
+                    f.write(struct.pack("<I", 1))
+                    vec(f, op[1])
+                    vec(f, op[2])
+                elif op[0] == "instance":
+                    f.write(struct.pack("<I", 2))
+                    f.write(np.asarray(op[1], dtype=_F).tobytes())
+                    f.write(struct.pack("<3I", op[2], op[3], op[4]))
+                elif op[0] == "light":
+                    d = op[1]
+                    f.write(struct.pack("<Ii", 3, d.type))
+                    f.write(np.asarray(d.xform, dtype=np.float64).reshape(4, 4).T.astype(_F).tobytes())
+                    f.write(struct.pack("<8f", *d.color, d.intensity, d.width, d.height, d.radius, d.halfAngle))
+                elif op[0] == "curve":
+                    f.write(struct.pack("<I", 4))
+                    vec(f, np.asarray(op[1], dtype=np.uint32))
+                    vec(f, np.asarray(op[2], dtype=_F).reshape(-1))
+                    vec(f, np.asarray(op[3], dtype=_F))
+                elif op[0] == "material":
+                    m = op[1]
+                    f.write(struct.pack("<I", 5))
+                    f.write(struct.pack("<I5f", int(m["model"] == _abi.SB_MATERIAL_USD_PREVIEW_SURFACE), *[float(x) for x in m["base_color"]],
+                                        float(m["roughness"]), float(m["metallic"])))
+            f.write(struct.pack("<I", 0))
 
     def updateLight(self, light_id: int, desc: UniformLightDesc) -> None:  # noqa: N802
         l = self.lights[light_id]  # noqa: E741

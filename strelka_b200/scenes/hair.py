@@ -72,6 +72,7 @@ def make_hair(width: int = 1024, height: int = 1024, spp_total: int = 1024, dept
         rad = np.concatenate([r[:1], r, r[-1:]]).astype(np.float32)
         ncp = n_user + 2
         # bulk-append instead of 62 500 createCurve calls (same resulting arrays)
+        s.journal = None  # appended behind the API's back
         base_counts, base_points, base_w = s._nccounts, s._ncpoints, s._ncwidths
         s._cpoints.append(allp.reshape(-1, 3))
         s._cwidths.append(np.tile(rad, n_strands))

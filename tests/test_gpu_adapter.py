@@ -44,3 +44,26 @@ def test_cpp_adapter_renders_like_oracle(tmp_path):
     img = np.fromfile(out, dtype=np.float32).reshape(h, w, 4)
     ref, _, _, _ = pyoracle.OracleScene(scene).render(settings, w, h, spp)
     assert rel_rmse(img, ref) <= 1e-3
+
+
+def test_adapter_built_against_the_reference_headers_renders_like_oracle(tmp_path):
+    """oracle/_ref/adapter_ref_test = B200Render.cpp compiled against the reference's OWN render / scene / settings
+    headers with the reference's scene.cpp and camera.cpp (built where the reference tree exists, travels to the GPU
+    box): the scene goes through the real oka::Scene API, the image must be the oracle's."""
+    from util import random_scene
+
+    tool = os.path.join(ROOT, "oracle", "_ref", "adapter_ref_test")
+    if not os.path.exists(tool):
+        pytest.skip("oracle/_ref/adapter_ref_test has not been built (needs the reference tree)")
+    w, h, spp, depth = 64, 48, 6, 4
+    for scene, settings in (make_cornell(w, h, spp, depth=depth)[:2], random_scene(seed=3)):
+        settings.setAs("render/pt/sppTotal", spp)
+        settings.setAs("render/pt/depth", depth)
+        j, out = tmp_path / "journal.bin", tmp_path / "out.raw"
+        scene.write_journal(j, w, h, spp, depth)
+        r = subprocess.run([tool, "render", str(j), str(out)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        img = np.fromfile(out, dtype=np.float32).reshape(h, w, 4)
+        ref, _, _, _ = pyoracle.OracleScene(scene).render(settings, w, h, spp)
+        assert ref[..., :3].mean() > 0
+        assert rel_rmse(img, ref) <= 1e-3
