@@ -111,7 +111,8 @@ int main(int argc, char** argv)
         {
             const uint32_t isMaterialX = r.get<uint32_t>();
             float color[3] = { r.get<float>(), r.get<float>(), r.get<float>() };
-            const float roughness = r.get<float>(), metallic = r.get<float>();
+            const float roughness = r.get<float>(), metallic = r.get<float>(), ior = r.get<float>(), clearcoat = r.get<float>(),
+                        clearcoatRoughness = r.get<float>();
             Scene::MaterialDescription d;
             d.type = isMaterialX ? Scene::MaterialDescription::Type::eMaterialX : Scene::MaterialDescription::Type::eMdl;
             d.file = "default.mdl";
@@ -130,9 +131,14 @@ int main(int argc, char** argv)
                 q.value.resize(4);
                 std::memcpy(q.value.data(), &roughness, 4);
                 d.params.push_back(q);
-                q.name = "metallic";
-                std::memcpy(q.value.data(), &metallic, 4);
-                d.params.push_back(q);
+                const char* names[] = { "metallic", "ior", "clearcoat", "clearcoatRoughness" }; // UsdPreviewSurface inputs
+                const float values[] = { metallic, ior, clearcoat, clearcoatRoughness };
+                for (int k = 0; k < 4; ++k)
+                {
+                    q.name = names[k];
+                    std::memcpy(q.value.data(), &values[k], 4);
+                    d.params.push_back(q);
+                }
             }
             scene.addMaterial(d);
         }

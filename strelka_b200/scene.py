@@ -342,8 +342,9 @@ class Scene:
                 elif op[0] == "material":
                     m = op[1]
                     f.write(struct.pack("<I", 5))
-                    f.write(struct.pack("<I5f", int(m["model"] == _abi.SB_MATERIAL_USD_PREVIEW_SURFACE), *[float(x) for x in m["base_color"]],
-                                        float(m["roughness"]), float(m["metallic"])))
+                    f.write(struct.pack("<I8f", int(m["model"] == _abi.SB_MATERIAL_USD_PREVIEW_SURFACE), *[float(x) for x in m["base_color"]],
+                                        float(m["roughness"]), float(m["metallic"]), float(m["ior"]), float(m["clearcoat"]),
+                                        float(m["clearcoat_roughness"])))
             f.write(struct.pack("<I", 0))
 
     def updateLight(self, light_id: int, desc: UniformLightDesc) -> None:  # noqa: N802

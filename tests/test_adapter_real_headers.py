@@ -80,7 +80,7 @@ def _compare(real, scene):
     for f in ("points", "color", "normal", "half_angle"):
         np.testing.assert_allclose(real["lights"][f], mine["lights"][f], rtol=0, atol=3e-6, err_msg=f"lights.{f}")
     # materials as the adapter resolves them by parameter name
-    for f in ("model", "base_color", "roughness", "metallic", "ior", "opacity"):
+    for f in ("model", "base_color", "roughness", "metallic", "ior", "opacity", "clearcoat", "clearcoat_roughness"):
         np.testing.assert_allclose(real["materials"][f], mine["materials"][f], rtol=0, atol=1e-7, err_msg=f"materials.{f}")
 
 
