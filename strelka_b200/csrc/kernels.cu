@@ -194,7 +194,7 @@ constexpr int kRefill = SB_REFILL;
 // follow find them on chip instead of stalling the whole warp on a DRAM round trip (ncu: 5 % of all stall samples of the
 // closest-hit kernel sat on the first use of a freshly fetched ray).
 #ifndef SB_FETCH_CHUNK
-#define SB_FETCH_CHUNK 128
+#define SB_FETCH_CHUNK 32
 #endif
 constexpr uint32_t kFetchChunk = SB_FETCH_CHUNK;
 struct WarpFetch

@@ -23,9 +23,22 @@
 namespace sb
 {
 
+#ifndef SB_PRIM_NOALLOC
+#define SB_PRIM_NOALLOC 0 // 1: primitive records bypass L1 allocation (kept for the nodes); measured, see DESIGN.md
+#endif
 #if defined(__CUDA_ARCH__)
 #define SB_LDG4(p) __ldg(reinterpret_cast<const uint4*>(p))
+#if SB_PRIM_NOALLOC
+__device__ __forceinline__ float4 sb_ldg_noalloc(const float4* p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+#define SB_LDGF4(p) sb_ldg_noalloc(reinterpret_cast<const float4*>(p))
+#else
 #define SB_LDGF4(p) __ldg(reinterpret_cast<const float4*>(p))
+#endif
 #else
 #define SB_LDG4(p) (*reinterpret_cast<const uint4*>(p))
 #define SB_LDGF4(p) (*reinterpret_cast<const float4*>(p))
@@ -285,6 +298,9 @@ SB_HD void trav_init(Traversal& T)
 #ifndef SB_PREFETCH_CHILDREN
 #define SB_PREFETCH_CHILDREN 0
 #endif
+#ifndef SB_PRIM_PAIR
+#define SB_PRIM_PAIR 0 // 1: the closest-hit step tests up to two pending triangles per iteration (trav_tri_pair)
+#endif
 #ifndef SB_PIPE_NODE
 #define SB_PIPE_NODE 0 // 1: closest-hit kernel, 2: any-hit kernel too -- software-pipelined node fetch (trav_step_pipe)
 #endif
@@ -507,6 +523,54 @@ SB_HD bool trav_prim(Traversal& T, const void* __restrict__ prims, uint32_t rayM
     return false;
 }
 
+// Two pending triangles per call, their six loads issued together (a leaf slot holds up to three triangles; the lane
+// leaves its "primitive drain" in half the iterations and the two memory latencies overlap).  SB_PRIM_PAIR.
+template <bool ANY, bool STATS>
+SB_HD bool trav_tri_pair(Traversal& T, const void* __restrict__ prims, uint32_t rayMask, Ray& ray, HitRec& hit, TravStats* st)
+{
+    const uint32_t rel0 = bfind32(T.tgroup.y);
+    T.tgroup.y &= ~(1u << rel0);
+    const bool two = T.tgroup.y != 0u;
+    const uint32_t rel1 = two ? bfind32(T.tgroup.y) : rel0;
+    T.tgroup.y &= ~(1u << rel1);
+    const TriRec* t0 = reinterpret_cast<const TriRec*>(prims) + (T.tgroup.x + rel0);
+    const TriRec* t1 = reinterpret_cast<const TriRec*>(prims) + (T.tgroup.x + rel1);
+    const float4 a0 = SB_LDGF4(&t0->v0), b0 = SB_LDGF4(&t0->e1), c0 = SB_LDGF4(&t0->e2);
+    const float4 a1 = SB_LDGF4(&t1->v0), b1 = SB_LDGF4(&t1->e1), c1 = SB_LDGF4(&t1->e2);
+    if (STATS)
+        st->tris += two ? 2u : 1u;
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+    {
+        if (k == 1 && !two)
+            break;
+        const float4 a = k ? a1 : a0, b = k ? b1 : b0, c = k ? c1 : c0;
+        const uint32_t instMask = f2u(b.w);
+        if ((instMask >> 28) & rayMask)
+        {
+            float t, u, v;
+            if (intersect_tri(mk3(a), mk3(b), mk3(c), ray.o, ray.d, ray.tmin, ray.tmax, t, u, v))
+            {
+                if (ANY)
+                    return true;
+                const uint32_t gid = f2u(c.w);
+                if (t < ray.tmax || hit.kind != 1u || gid < hit.gid)
+                {
+                    hit.t = t;
+                    hit.u = u;
+                    hit.v = v;
+                    hit.prim = f2u(a.w);
+                    hit.inst = instMask & 0x0fffffffu;
+                    hit.kind = 1u;
+                    hit.gid = gid;
+                    ray.tmax = t;
+                }
+            }
+        }
+    }
+    return false;
+}
+
 // one full step of one lane: node half-step if idle, then one primitive if any is pending.
 // Returns false when the traversal is finished; anyHit is set when an ANY query found an occluder.
 template <int KIND, bool ANY, bool STATS, bool SSTACK = false>
@@ -520,7 +584,11 @@ SB_HD bool trav_step(Traversal& T, TravStack& K, const WideNode* __restrict__ no
     }
     if (T.tgroup.y != 0u)
     {
+#if SB_PRIM_PAIR
+        if (KIND == 1 ? trav_tri_pair<ANY, STATS>(T, prims, rayMask, ray, hit, st) : trav_prim<KIND, ANY, STATS>(T, prims, rayMask, ray, hit, st))
+#else
         if (trav_prim<KIND, ANY, STATS>(T, prims, rayMask, ray, hit, st))
+#endif
         {
             anyHit = true;
             return false;
