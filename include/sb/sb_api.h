@@ -412,6 +412,9 @@ sb_result sb_test_sampler(sb_ctx* ctx, uint32_t n, const uint32_t* x, const uint
 sb_result sb_test_light_sample(sb_ctx* ctx, uint32_t n, const sb_light* lights, const float* hit_points,
                                const float* u, uint32_t method, float* out);
 
+/* offset_ray (closest_hit.cu:218-233): out[i] = the ray origin for hit point p[i] pushed along normal[i] (3 floats each) */
+sb_result sb_test_offset_ray(sb_ctx* ctx, uint32_t n, const float* p, const float* normal, float* out);
+
 /* tex::lookup_float4 (texture_support_cuda.h:287-314) of texture `index` (0-based) of the current scene at n (u, v)
  * pairs -> n rgba quadruples: the hardware-filtered lookups the shade kernel performs for textured materials. */
 sb_result sb_test_texture(sb_ctx* ctx, uint32_t index, uint32_t n, const float* uv, float* out);

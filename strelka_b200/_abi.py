@@ -155,7 +155,7 @@ ABI_SYMBOLS = [
     "sb_buffer_host_ptr", "sb_buffer_host_size", "sb_buffer_device_ptr", "sb_buffer_width", "sb_buffer_height",
     "sb_render", "sb_render_iterations", "sb_synchronize", "sb_accum_device_ptr", "sb_resolve",
     "sb_comm_get_unique_id", "sb_comm_init", "sb_comm_destroy", "sb_comm_world", "sb_render_sharded",
-    "sb_get_counters", "sb_reset_counters", "sb_test_sampler", "sb_test_light_sample", "sb_test_trace", "sb_test_bsdf", "sb_test_texture",
+    "sb_get_counters", "sb_reset_counters", "sb_test_sampler", "sb_test_light_sample", "sb_test_trace", "sb_test_bsdf", "sb_test_texture", "sb_test_offset_ray",
 ]
 SB_COMM_ID_BYTES = 128
 SB_API_VERSION = 2
@@ -220,6 +220,7 @@ def load_library() -> C.CDLL:
         "sb_test_trace": (C.c_int, [vp, u32, vp, u32, vp]),
         "sb_test_bsdf": (C.c_int, [vp, vp, u32, vp, vp]),
         "sb_test_texture": (C.c_int, [vp, u32, u32, vp, vp]),
+        "sb_test_offset_ray": (C.c_int, [vp, u32, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

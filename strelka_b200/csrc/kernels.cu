@@ -1294,6 +1294,22 @@ void launch_test_trace_production(const LaunchCfg& cfg, const FrameParams& P, co
     SB_CUDA_CHECK(cudaGetLastError());
 }
 
+__global__ void k_test_offset_ray(uint32_t n, const float* p, const float* nrm, float* out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const float3 r = offset_ray(mk3(p[3 * i], p[3 * i + 1], p[3 * i + 2]), mk3(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]));
+        out[3 * i] = r.x;
+        out[3 * i + 1] = r.y;
+        out[3 * i + 2] = r.z;
+    }
+}
+void launch_test_offset_ray(const LaunchCfg& cfg, uint32_t n, const float* p, const float* nrm, float* out)
+{
+    k_test_offset_ray<<<grid_for(cfg, 2), 128, 0, cfg.stream>>>(n, p, nrm, out);
+    SB_CUDA_CHECK(cudaGetLastError());
+}
+
 // sb_test_texture: n lookups of texture index1 (1-based) at (u, v) -> rgba
 __global__ void k_test_texture(SceneDev S, uint32_t index1, uint32_t n, const float* uv, float* out)
 {

@@ -66,6 +66,7 @@ void launch_test_sampler(const LaunchCfg& cfg, uint32_t n, const uint32_t* x, co
                          const uint32_t* depth, const uint32_t* dim, float* out);
 void launch_test_light_sample(const LaunchCfg& cfg, uint32_t n, const sb_light* lights, const float* hp, const float* u, uint32_t method, float* out);
 void launch_test_trace(const LaunchCfg& cfg, const SceneDev& S, uint32_t n, const float* rays, uint32_t mode, sb_hit* hits);
+void launch_test_offset_ray(const LaunchCfg& cfg, uint32_t n, const float* p, const float* nrm, float* out);
 void launch_test_texture(const LaunchCfg& cfg, const SceneDev& S, uint32_t index1, uint32_t n, const float* uv, float* out);
 void launch_test_bsdf(const LaunchCfg& cfg, const sb_material& m, uint32_t n, const float* in, float* out);
 // the stages of one bounce as launch_wavefront_batch dispatches them (persistent kernels for secondary rays of non-tiny scenes)

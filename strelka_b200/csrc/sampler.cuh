@@ -1,6 +1,7 @@
 // Device sampler: Morton-indexed, Owen-scrambled 5-D Sobol, bit-exact with the reference's
 // src/render/optix/RandomSampler.h (initSampler :130-137, sobol_scramble :213-219, random<> :221-226).
-// Parity is pinned by tests/test_gpu_kats.py against tests/golden/ref_vectors.json.
+// Parity is pinned by tests/test_gpu_parity.py::test_sampler_bit_exact_on_device (and tests/test_emul_vs_oracle.py on the
+// host instantiation) against tests/golden/ref_vectors.json.
 //
 // The direction numbers are not copied from the reference table: sobol_generate() rebuilds them from
 // the Joe-Kuo primitive polynomials of dimensions 1..5 on the host and the context uploads them to

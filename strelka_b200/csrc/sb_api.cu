@@ -1234,6 +1234,24 @@ sb_result sb_test_light_sample(sb_ctx* c, uint32_t n, const sb_light* lights, co
     SB_API_END
 }
 
+sb_result sb_test_offset_ray(sb_ctx* c, uint32_t n, const float* p, const float* nrm, float* out)
+{
+    if (!c || !p || !nrm || !out)
+        return SB_FAIL;
+    SB_API_BEGIN(c)
+    cudaStream_t st = c->stream;
+    float* dp = dev_upload(p, size_t(n) * 3, st);
+    float* dn = dev_upload(nrm, size_t(n) * 3, st);
+    float* dout = dev_alloc<float>(size_t(n) * 3);
+    launch_test_offset_ray(launch_cfg(c), n, dp, dn, dout);
+    SB_CUDA_CHECK(cudaMemcpyAsync(out, dout, sizeof(float) * 3 * size_t(n), cudaMemcpyDeviceToHost, st));
+    SB_CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFree(dp);
+    cudaFree(dn);
+    cudaFree(dout);
+    SB_API_END
+}
+
 sb_result sb_test_texture(sb_ctx* c, uint32_t index, uint32_t n, const float* uv, float* out)
 {
     if (!c || !uv || !out)

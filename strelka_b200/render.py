@@ -334,6 +334,13 @@ class Render:
                "sb_test_light_sample")
         return out
 
+    def test_offset_ray(self, p, normal) -> np.ndarray:
+        p = np.ascontiguousarray(p, dtype=np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(normal, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros_like(p)
+        _check(self._lib, self._ctx, self._lib.sb_test_offset_ray(self._ctx, len(p), p.ctypes.data, nrm.ctypes.data, out.ctypes.data), "sb_test_offset_ray")
+        return out
+
     def test_texture(self, index: int, uv) -> np.ndarray:
         """Hardware-filtered lookups of texture `index` (0-based) of the current scene at (N, 2) st coordinates."""
         if not self._scene_uploaded:

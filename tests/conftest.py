@@ -41,10 +41,22 @@ def ulp_diff(a, b):
 
 
 def rel_rmse(a, b):
-    """sqrt(mean((a-b)^2) / mean(b^2)) over RGB -- the 'per-pixel relative RMSE' of the parity gate."""
+    """sqrt(mean((a-b)^2) / mean(b^2)) over RGB: the RMS of the per-pixel error relative to the RMS of the reference image
+    (one bright outlier pixel dominates it, which is the point of the gate).  The other reading of north_star's
+    "per-pixel relative RMSE" -- the RMS over pixels of |a-b| / |b| -- is per_pixel_rel_rmse below; the full-size C2 test
+    gates both."""
     a = np.asarray(a, dtype=np.float64)[..., :3]
     b = np.asarray(b, dtype=np.float64)[..., :3]
     return float(np.sqrt(np.mean((a - b) ** 2) / max(np.mean(b**2), 1e-30)))
+
+
+def per_pixel_rel_rmse(a, b, floor=1e-6):
+    """sqrt(mean_pixels((|a-b| / max(|b|, floor))^2)) over RGB vectors"""
+    a = np.asarray(a, dtype=np.float64)[..., :3]
+    b = np.asarray(b, dtype=np.float64)[..., :3]
+    num = np.linalg.norm(a - b, axis=-1)
+    den = np.maximum(np.linalg.norm(b, axis=-1), floor)
+    return float(np.sqrt(np.mean((num / den) ** 2)))
 
 
 @pytest.fixture(scope="session")

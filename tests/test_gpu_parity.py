@@ -55,7 +55,9 @@ def test_light_sampling_on_device(gpu_render, golden, key, ltype, method, tol):
     # CUDA libm vs glibc differ by <= 2 ulp in sin/cos/acos; the spherical-rectangle sampler amplifies
     # that near grazing configurations, hence the looser bound there (relative to the value scale)
     scale = np.maximum(np.abs(ref), 1.0)
-    assert np.max(np.abs(got - ref) / scale) < tol
+    err = np.abs(got - ref) / scale
+    assert np.max(err) < tol
+    assert np.percentile(err, 99) < 2e-5  # the loose bound above is for the ill-conditioned tail only
 
 
 @pytest.mark.parametrize("scene_kind", ["cornell", "random"])
@@ -273,3 +275,18 @@ def test_async_map_returns_the_frame_it_was_issued_for(gpu_render):
     assert not np.array_equal(frame0, frame1)
     for b in bufs:
         b.destroy()
+
+
+def test_offset_ray_bit_exact_on_device(gpu_render):
+    """offset_ray (closest_hit.cu:218-233, Ray Tracing Gems ch. 6): integer-ulp offsets away from the origin, float offsets
+    near it -- integer and single float operations only, so device and oracle must agree bit for bit"""
+    rng = np.random.default_rng(12)
+    n = 100000
+    p = np.concatenate([rng.uniform(-5, 5, (n // 2, 3)), rng.uniform(-1 / 16, 1 / 16, (n // 2, 3))]).astype(np.float32)
+    p[:100] = 0.0
+    p[100:200, 0] = np.float32(1.0 / 32.0)  # the switch-over magnitude itself
+    nrm = rng.normal(size=(n, 3))
+    nrm = (nrm / np.linalg.norm(nrm, axis=1, keepdims=True)).astype(np.float32)
+    got = gpu_render.test_offset_ray(p, nrm)
+    want = np.stack([pyoracle.offset_ray(p[i], nrm[i]) for i in range(0, n, 37)])
+    assert np.array_equal(got[::37].view(np.uint32), want.view(np.uint32))
