@@ -358,6 +358,11 @@ sb_result sb_comm_init(sb_ctx* ctx, const void* id, uint32_t rank, uint32_t worl
 sb_result sb_comm_destroy(sb_ctx* ctx);
 uint32_t sb_comm_world(const sb_ctx* ctx);
 sb_result sb_render_sharded(sb_ctx* ctx, sb_buffer* output, uint32_t iterations);
+/* How this context's group exchanges S: "NVLS multimem: fused all-reduce + resolve kernel" (one kernel: the NVSwitch
+ * sums the ranks' accumulation buffers in flight -- multimem.ld_reduce / multimem.st over NCCL symmetric windows --
+ * and the sums are resolved in place; needs NCCL >= 2.28 and NVLS hardware) or "ncclAllReduce + k_resolve (why)".
+ * STRELKA_B200_NVLS=0 forces the latter.  Never NULL. */
+const char* sb_comm_exchange_path(const sb_ctx* ctx);
 
 /* ------------------------------------------------------------------------------------------
  * Counters (new: the reference has no ray counters)
@@ -391,6 +396,10 @@ typedef struct sb_counters
     /* levels of the two wide BVHs; the builder refuses trees deeper than the traversal stack (sb_set_scene fails) */
     uint64_t bvh_depth_tri;
     uint64_t bvh_depth_curve;
+    /* last sb_render_sharded of a group: device time of the exchange (all-reduce + resolve), and whether it was the
+     * fused NVLS kernel (1) or ncclAllReduce + k_resolve (0) */
+    double exchange_ms;
+    uint64_t exchange_nvls;
 } sb_counters;
 
 sb_result sb_get_counters(sb_ctx* ctx, sb_counters* out); /* synchronizes */

@@ -135,6 +135,7 @@ class sb_counters(C.Structure):
         ("kernel_launches", C.c_uint64),
         ("stage_ms", C.c_double * 8), ("stage_launches", C.c_uint64 * 8),
         ("bvh_depth_tri", C.c_uint64), ("bvh_depth_curve", C.c_uint64),
+        ("exchange_ms", C.c_double), ("exchange_nvls", C.c_uint64),
     ]
 
     STAGES = ("raygen", "extend", "shade", "shadow", "accumulate", "resolve", "path_fused", "reserved")
@@ -154,7 +155,7 @@ ABI_SYMBOLS = [
     "sb_buffer_create", "sb_buffer_destroy", "sb_buffer_resize", "sb_buffer_map", "sb_buffer_unmap", "sb_buffer_map_async", "sb_buffer_map_wait",
     "sb_buffer_host_ptr", "sb_buffer_host_size", "sb_buffer_device_ptr", "sb_buffer_width", "sb_buffer_height",
     "sb_render", "sb_render_iterations", "sb_synchronize", "sb_accum_device_ptr", "sb_resolve",
-    "sb_comm_get_unique_id", "sb_comm_init", "sb_comm_destroy", "sb_comm_world", "sb_render_sharded",
+    "sb_comm_get_unique_id", "sb_comm_init", "sb_comm_destroy", "sb_comm_world", "sb_comm_exchange_path", "sb_render_sharded",
     "sb_get_counters", "sb_reset_counters", "sb_test_sampler", "sb_test_light_sample", "sb_test_trace", "sb_test_bsdf", "sb_test_texture", "sb_test_offset_ray",
 ]
 SB_COMM_ID_BYTES = 128
@@ -212,6 +213,7 @@ def load_library() -> C.CDLL:
         "sb_comm_init": (C.c_int, [vp, vp, u32, u32]),
         "sb_comm_destroy": (C.c_int, [vp]),
         "sb_comm_world": (u32, [vp]),
+        "sb_comm_exchange_path": (C.c_char_p, [vp]),
         "sb_render_sharded": (C.c_int, [vp, vp, u32]),
         "sb_get_counters": (C.c_int, [vp, P(sb_counters)]),
         "sb_reset_counters": (C.c_int, [vp]),

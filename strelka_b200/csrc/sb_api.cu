@@ -10,6 +10,7 @@
 #include "kernels.h"
 #include "scene_prep.h"
 #include "host_math.h"
+#include "sb_nvls.cuh"
 
 #include <chrono>
 #include <cstdio>
@@ -88,6 +89,17 @@ struct sb_ctx
     int commRank = 0, commWorld = 1;
     float4* Sglobal = nullptr; // all-reduced copy of S (S itself stays this rank's partial sum)
     uint64_t shardRequested = 0; // iterations asked of sb_render_sharded since the last accumulation reset
+    cudaEvent_t evXchgStart = nullptr, evXchgStop = nullptr; // brackets the exchange (all-reduce + resolve) of the last sharded render
+    // NVLS path (sb_nvls.cuh): S and Sglobal as NCCL symmetric windows, device communicator with multimem + barriers
+    bool nvlsReady = false, symBuffers = false;
+    std::string nvlsStatus = "not a multi-GPU context";
+    mutable std::string exchangeNote;
+    int nvlsGrid = 0;
+    size_t symPix = 0;
+#if SB_HAVE_NCCL_DEVICE
+    ncclDevComm devComm;
+    ncclWindow_t winS = nullptr, winG = nullptr;
+#endif
 };
 
 namespace
@@ -179,8 +191,11 @@ void free_queues(sb_ctx* c)
     c->queuePaths = 0;
 }
 
+void release_sym(sb_ctx* c, bool keepFrame); // below (needs the NCCL loader)
+
 void free_frame(sb_ctx* c)
 {
+    release_sym(c, false);
     dev_free(c->S);
     dev_free(c->direct);
     dev_free(c->aovD);
@@ -468,6 +483,15 @@ struct NcclApi
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     ncclResult_t (*GetVersion)(int*) = nullptr;
+    // NCCL >= 2.28 only (symmetric memory + device API); null with an older library
+    ncclResult_t (*MemAlloc)(void**, size_t) = nullptr;
+    ncclResult_t (*MemFree)(void*) = nullptr;
+#if SB_HAVE_NCCL_DEVICE
+    ncclResult_t (*CommWindowRegister)(ncclComm_t, void*, size_t, ncclWindow_t*, int) = nullptr;
+    ncclResult_t (*CommWindowDeregister)(ncclComm_t, ncclWindow_t) = nullptr;
+    ncclResult_t (*DevCommCreate)(ncclComm_t, ncclDevCommRequirements_t const*, ncclDevComm_t*) = nullptr;
+    ncclResult_t (*DevCommDestroy)(ncclComm_t, ncclDevComm_t const*) = nullptr;
+#endif
 };
 NcclApi& nccl_api()
 {
@@ -490,6 +514,14 @@ NcclApi& nccl_api()
     api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
     api.GetVersion = reinterpret_cast<decltype(api.GetVersion)>(sym("ncclGetVersion"));
+    api.MemAlloc = reinterpret_cast<decltype(api.MemAlloc)>(dlsym(h, "ncclMemAlloc"));
+    api.MemFree = reinterpret_cast<decltype(api.MemFree)>(dlsym(h, "ncclMemFree"));
+#if SB_HAVE_NCCL_DEVICE
+    api.CommWindowRegister = reinterpret_cast<decltype(api.CommWindowRegister)>(dlsym(h, "ncclCommWindowRegister"));
+    api.CommWindowDeregister = reinterpret_cast<decltype(api.CommWindowDeregister)>(dlsym(h, "ncclCommWindowDeregister"));
+    api.DevCommCreate = reinterpret_cast<decltype(api.DevCommCreate)>(dlsym(h, "ncclDevCommCreate"));
+    api.DevCommDestroy = reinterpret_cast<decltype(api.DevCommDestroy)>(dlsym(h, "ncclDevCommDestroy"));
+#endif
     api.handle = h;
     return api;
 }
@@ -498,6 +530,74 @@ void nccl_check(ncclResult_t r, const char* what)
     if (r != ncclSuccess)
         throw std::runtime_error(std::string(what) + ": " + nccl_api().GetErrorString(r));
 }
+
+// ---- NVLS path: S / Sglobal as NCCL symmetric windows (sb_nvls.cuh) ---------------------------------------------
+// Give the symmetric buffers back; with keepFrame the accumulated S moves into a plain allocation so that the context
+// keeps rendering (sb_comm_destroy), without it the frame is going away anyway (resize, sb_destroy).
+void release_sym(sb_ctx* c, bool keepFrame)
+{
+    if (!c->symBuffers)
+        return;
+    cudaStreamSynchronize(c->stream);
+    NcclApi& api = nccl_api();
+#if SB_HAVE_NCCL_DEVICE
+    if (c->comm && api.CommWindowDeregister)
+    {
+        if (c->winS)
+            api.CommWindowDeregister(c->comm, c->winS);
+        if (c->winG)
+            api.CommWindowDeregister(c->comm, c->winG);
+    }
+    c->winS = c->winG = nullptr;
+#endif
+    float4* plain = nullptr;
+    if (keepFrame && c->S && c->symPix)
+    {
+        plain = dev_alloc<float4>(c->symPix);
+        cudaMemcpy(plain, c->S, sizeof(float4) * c->symPix, cudaMemcpyDeviceToDevice);
+    }
+    if (c->S)
+        api.MemFree(c->S);
+    if (c->Sglobal)
+        api.MemFree(c->Sglobal);
+    c->S = plain;
+    c->Sglobal = nullptr;
+    c->symBuffers = false;
+    c->symPix = 0;
+}
+
+#if SB_HAVE_NCCL_DEVICE
+// (re)create the symmetric S / G pair for the current frame size; collective over the group
+void ensure_sym(sb_ctx* c)
+{
+    const size_t npix = size_t(c->width) * c->height;
+    if (c->symBuffers && c->symPix == npix)
+        return;
+    NcclApi& api = nccl_api();
+    SB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    release_sym(c, true);
+    void *ns = nullptr, *ng = nullptr;
+    nccl_check(api.MemAlloc(&ns, sizeof(float4) * npix), "ncclMemAlloc");
+    nccl_check(api.MemAlloc(&ng, sizeof(float4) * npix), "ncclMemAlloc");
+    if (c->S)
+    {
+        SB_CUDA_CHECK(cudaMemcpy(ns, c->S, sizeof(float4) * npix, cudaMemcpyDeviceToDevice));
+        cudaFree(c->S);
+    }
+    else
+    {
+        SB_CUDA_CHECK(cudaMemset(ns, 0, sizeof(float4) * npix));
+    }
+    if (c->Sglobal)
+        cudaFree(c->Sglobal);
+    c->S = static_cast<float4*>(ns);
+    c->Sglobal = static_cast<float4*>(ng);
+    c->symBuffers = true;
+    c->symPix = npix;
+    nccl_check(api.CommWindowRegister(c->comm, c->S, sizeof(float4) * npix, &c->winS, NCCL_WIN_COLL_SYMMETRIC), "ncclCommWindowRegister(S)");
+    nccl_check(api.CommWindowRegister(c->comm, c->Sglobal, sizeof(float4) * npix, &c->winG, NCCL_WIN_COLL_SYMMETRIC), "ncclCommWindowRegister(G)");
+}
+#endif
 
 // samples with global index < sppTotal that rank r of `world` owns (indices r, r + world, ...)
 uint32_t shard_budget(uint32_t sppTotal, uint32_t r, uint32_t world)
@@ -614,7 +714,19 @@ void sb_destroy(sb_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->comm)
+    {
+        release_sym(c, false);
+#if SB_HAVE_NCCL_DEVICE
+        if (c->nvlsReady && nccl_api().DevCommDestroy)
+            nccl_api().DevCommDestroy(c->comm, &c->devComm);
+#endif
         nccl_api().CommDestroy(c->comm);
+        c->comm = nullptr;
+    }
+    if (c->evXchgStart)
+        cudaEventDestroy(c->evXchgStart);
+    if (c->evXchgStop)
+        cudaEventDestroy(c->evXchgStop);
     c->timer.release();
     free_scene(c);
     free_frame(c);
@@ -1082,6 +1194,15 @@ sb_result sb_get_counters(sb_ctx* c, sb_counters* out)
     out->build_ms = c->buildMs;
     out->bvh_depth_tri = c->scene.triDepth;
     out->bvh_depth_curve = c->scene.segDepth;
+    out->exchange_nvls = c->nvlsReady ? 1u : 0u;
+    if (c->evXchgStart)
+    {
+        float x = 0.0f;
+        if (cudaEventElapsedTime(&x, c->evXchgStart, c->evXchgStop) == cudaSuccess)
+            out->exchange_ms = x;
+        else
+            cudaGetLastError();
+    }
     float ms = 0.0f;
     if (cudaEventElapsedTime(&ms, c->evStart, c->evStop) == cudaSuccess)
         c->renderMs = ms;
@@ -1128,6 +1249,40 @@ sb_result sb_comm_init(sb_ctx* c, const void* idBytes, uint32_t rank, uint32_t w
     nccl_check(nccl_api().CommInitRank(&c->comm, int(world), id, int(rank)), "ncclCommInitRank");
     c->commRank = int(rank);
     c->commWorld = int(world);
+    // the fused NVLS all-reduce + resolve (sb_nvls.cuh) where library, headers and hardware allow it; every rank takes the
+    // same decision (the inputs are properties of the group), else ncclAllReduce + k_resolve
+    c->nvlsReady = false;
+    if (world > 1)
+    {
+#if SB_HAVE_NCCL_DEVICE
+        NcclApi& api = nccl_api();
+        const char* env = getenv("STRELKA_B200_NVLS");
+        if (env && *env == '0')
+            c->nvlsStatus = "disabled by STRELKA_B200_NVLS=0";
+        else if (!api.DevCommCreate || !api.CommWindowRegister || !api.MemAlloc || !api.MemFree)
+            c->nvlsStatus = "libnccl older than 2.28: no device API";
+        else
+        {
+            c->nvlsGrid = c->numSms * kNvlsCtasPerSm;
+            ncclDevCommRequirements req;
+            std::memset(&req, 0, sizeof(req));
+            req.lsaMultimem = true;
+            req.lsaBarrierCount = c->nvlsGrid;
+            const ncclResult_t r = api.DevCommCreate(c->comm, &req, &c->devComm);
+            if (r != ncclSuccess)
+                c->nvlsStatus = std::string("ncclDevCommCreate: ") + api.GetErrorString(r);
+            else if (c->devComm.lsaSize != int(world))
+                c->nvlsStatus = "the ranks are not one NVLink (LSA) domain";
+            else
+            {
+                c->nvlsReady = true;
+                c->nvlsStatus = "NVLS multimem: fused all-reduce + resolve kernel";
+            }
+        }
+#else
+        c->nvlsStatus = "built without the NCCL device API headers (NCCL >= 2.28)";
+#endif
+    }
     // this rank renders the global sample indices rank, rank + world, ... (sampler indices unchanged)
     c->settings.sample_offset = rank;
     c->settings.sample_stride = world;
@@ -1143,6 +1298,13 @@ sb_result sb_comm_destroy(sb_ctx* c)
     if (c->comm)
     {
         SB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        release_sym(c, true);
+#if SB_HAVE_NCCL_DEVICE
+        if (c->nvlsReady && nccl_api().DevCommDestroy)
+            nccl_api().DevCommDestroy(c->comm, &c->devComm);
+#endif
+        c->nvlsReady = false;
+        c->nvlsStatus = "not a multi-GPU context";
         nccl_api().CommDestroy(c->comm);
         c->comm = nullptr;
         c->commRank = 0;
@@ -1159,6 +1321,13 @@ uint32_t sb_comm_world(const sb_ctx* c)
     return c ? uint32_t(c->commWorld) : 0u;
 }
 
+const char* sb_comm_exchange_path(const sb_ctx* c)
+{
+    if (!c)
+        return "";
+    return (c->commWorld > 1 && !c->nvlsReady) ? (c->exchangeNote = "ncclAllReduce + k_resolve (" + c->nvlsStatus + ")").c_str() : c->nvlsStatus.c_str();
+}
+
 sb_result sb_render_sharded(sb_ctx* c, sb_buffer* out, uint32_t iterations)
 {
     if (!c)
@@ -1170,23 +1339,51 @@ sb_result sb_render_sharded(sb_ctx* c, sb_buffer* out, uint32_t iterations)
                                  "(only then is the accumulation a plain sum over samples, SURVEY.md 8e / quirk Q1)");
     if (st.sample_offset != uint32_t(c->commRank) || st.sample_stride != uint32_t(c->commWorld))
         throw std::runtime_error("sb_render_sharded: settings.sample_offset / sample_stride must be this context's rank / world size");
+    if (!out || out->ctx != c || out->width == 0 || out->height == 0)
+        throw std::runtime_error("sb_render_sharded: bad output buffer");
+    ensure_frame(c, out->width, out->height);
+#if SB_HAVE_NCCL_DEVICE
+    if (c->commWorld > 1 && c->nvlsReady)
+        ensure_sym(c); // S and Sglobal become NCCL symmetric windows (collective; once per resolution)
+#endif
     render_impl(c, out, iterations); // this rank's share: stops at its own budget
     if (c->commWorld > 1)
     {
+        if (!c->evXchgStart)
+        {
+            SB_CUDA_CHECK(cudaEventCreate(&c->evXchgStart));
+            SB_CUDA_CHECK(cudaEventCreate(&c->evXchgStop));
+        }
+        SB_CUDA_CHECK(cudaEventRecord(c->evXchgStart, c->stream));
         // every rank is driven with the same call sequence, so the global sample count needs no exchange
         c->shardRequested += iterations;
         uint64_t total = 0;
         for (int r = 0; r < c->commWorld; ++r)
             total += std::min<uint64_t>(c->shardRequested, shard_budget(st.spp_total, uint32_t(r), uint32_t(c->commWorld)));
         const size_t npix = size_t(c->width) * c->height;
-        if (!c->Sglobal)
-            c->Sglobal = dev_alloc<float4>(npix);
-        // out of place: S stays this rank's partial sum, so further calls keep accumulating correctly
-        nccl_check(nccl_api().AllReduce(c->S, c->Sglobal, npix * 4, ncclFloat32, ncclSum, c->comm, c->stream), "ncclAllReduce");
         const LaunchCfg cfg = launch_cfg(c);
         float e[3];
         compute_exposure(st, e);
-        launch_resolve(cfg, c->Sglobal, out->dev, uint32_t(npix), uint32_t(total), e, st.tonemapper_type, st.gamma, out->format);
+        bool fused = false;
+#if SB_HAVE_NCCL_DEVICE
+        if (c->nvlsReady)
+        {
+            // ONE kernel: the NVSwitch sums the ranks' S in flight, the sums are multicast into every rank's Sglobal and
+            // resolved in place (sb_nvls.cuh).  S itself stays this rank's partial sum.
+            launch_allreduce_resolve_nvls(cfg, c->devComm, c->winS, c->winG, c->Sglobal, out->dev, uint32_t(npix), uint32_t(total), e,
+                                          st.tonemapper_type, st.gamma, out->format, c->nvlsGrid);
+            fused = true;
+        }
+#endif
+        if (!fused)
+        {
+            if (!c->Sglobal)
+                c->Sglobal = dev_alloc<float4>(npix);
+            // out of place: S stays this rank's partial sum, so further calls keep accumulating correctly
+            nccl_check(nccl_api().AllReduce(c->S, c->Sglobal, npix * 4, ncclFloat32, ncclSum, c->comm, c->stream), "ncclAllReduce");
+            launch_resolve(cfg, c->Sglobal, out->dev, uint32_t(npix), uint32_t(total), e, st.tonemapper_type, st.gamma, out->format);
+        }
+        SB_CUDA_CHECK(cudaEventRecord(c->evXchgStop, c->stream));
         SB_CUDA_CHECK(cudaEventRecord(c->evStop, c->stream));
     }
     SB_API_END

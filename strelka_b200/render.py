@@ -301,6 +301,10 @@ class Render:
     def comm_world(self) -> int:
         return int(self._lib.sb_comm_world(self._ctx)) if self._ctx else 1
 
+    def comm_exchange_path(self) -> str:
+        """how the group sums S: the fused NVLS kernel, or ncclAllReduce + resolve (and why)"""
+        return (self._lib.sb_comm_exchange_path(self._ctx) or b"").decode()
+
     def comm_destroy(self) -> None:
         _check(self._lib, self._ctx, self._lib.sb_comm_destroy(self._ctx), "sb_comm_destroy")
 

@@ -31,7 +31,7 @@ def test_struct_sizes_match_header():
     # sizes implied by the header (checked against the ctypes/numpy mirrors)
     assert C.sizeof(_abi.sb_settings) == 16 * 4 + 16
     assert C.sizeof(_abi.sb_device_cfg) == 16
-    assert C.sizeof(_abi.sb_counters) == 14 * 8 + 16 + 8 + 8 * 8 + 8 * 8 + 16
+    assert C.sizeof(_abi.sb_counters) == 14 * 8 + 16 + 8 + 8 * 8 + 8 * 8 + 16 + 16
     # ... and the sizeof() values the compiled library itself reports (load_library refuses a mismatch)
     lib = _abi.load_library()
     assert lib.sb_abi_version() == _abi.SB_API_VERSION

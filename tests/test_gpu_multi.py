@@ -46,11 +46,15 @@ def test_world_of_one_is_the_plain_render():
     r.destroy()
 
 
-def test_two_ranks_sum_to_the_single_gpu_image():
+@pytest.mark.parametrize("nvls", ["1", "0"], ids=["fused-nvls-kernel", "nccl-allreduce"])
+def test_two_ranks_sum_to_the_single_gpu_image(nvls, monkeypatch):
+    """both exchange paths of sb_render_sharded: the fused NVLS all-reduce + resolve kernel (where NCCL >= 2.28 and the
+    hardware offer it) and ncclAllReduce + k_resolve (forced by STRELKA_B200_NVLS=0)"""
     import torch
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
+    monkeypatch.setenv("STRELKA_B200_NVLS", nvls)
     w = h = 128
     total = 13  # odd on purpose: the ranks own 7 and 6 samples
     scene, st, _ = make_cornell(w, h, total)
@@ -74,7 +78,8 @@ def test_two_ranks_sum_to_the_single_gpu_image():
             r.render_sharded(buf, 4)
             mid = buf.map().copy()
             r.render_sharded(buf, 100)
-            out[i] = (mid, buf.map().copy(), r.getSharedContext().mSubframeIndex)
+            c = r.counters()
+            out[i] = (mid, buf.map().copy(), r.getSharedContext().mSubframeIndex, r.comm_exchange_path(), c["exchange_nvls"], c["exchange_ms"])
             r.comm_destroy()
             buf.destroy()
             r.destroy()
@@ -85,6 +90,10 @@ def test_two_ranks_sum_to_the_single_gpu_image():
     [t.start() for t in th]
     [t.join(120) for t in th]
     assert not errs, errs
+    print("exchange path:", out[0][3], "| exchange_ms", out[0][5])
+    assert out[0][3] == out[1][3] and out[0][4] == out[1][4]
+    if nvls == "0":
+        assert out[0][4] == 0 and "ncclAllReduce" in out[0][3]
     assert out[0][2] == 7 and out[1][2] == 6
     for i in range(2):
         np.testing.assert_allclose(out[i][1][..., :3], want[..., :3], rtol=2e-5, atol=1e-7)
