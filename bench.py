@@ -301,6 +301,10 @@ def bench_scene(hx: Harness, key: str, steps: int, warmup: int, with_cpu: bool, 
     cnt = render.counters()
     rays_step = (cnt["radiance_rays"] + cnt["shadow_rays"]) / steps
     launches = cnt["kernel_launches"]
+    exchange = None
+    if world > 1:
+        exchange = {"path": render.comm_exchange_path(), "ms_last_step": cnt["exchange_ms"], "bytes": W * H * 16,
+                    "note": "device time of the exchange inside the step (rank 0): sum of the ranks' float4 S buffers + resolve"}
 
     # ---- e2e: host buffers in, host image out, through the public API (wall clock) ----------------
     view = scene.view(pinned=True)
@@ -343,7 +347,7 @@ def bench_scene(hx: Harness, key: str, steps: int, warmup: int, with_cpu: bool, 
             "e2e": {"value": rays_total / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s, "includes": "scene upload from pinned host memory, on-device BVH build, render of the slice"
                     + (", NCCL all-reduce + resolve" if world > 1 else "") + ", D2H of the float4 image"},
-            "gpu_launches": launches_total, "clocks": clk,
+            "gpu_launches": launches_total, "clocks": clk, "exchange": exchange,
         }
     # ---- roofline of the traversal kernels: separately instrumented single-rank passes on rank 0 ---------------
     if rank == 0:
@@ -433,11 +437,13 @@ def run_b200(args) -> None:
             "data": "synthetic",
             "config": {"workload": c["desc"] + f"; step = {head['slice']}", "width": c["w"], "height": c["h"], "spp_total": c["spp_total"],
                        "depth": c["depth"],
-                       "parallelism": (f"sample-stride x{world}: scene/BVH replicas, ncclAllReduce of the 132.7 MB float4 S buffer + resolve "
-                                       "inside the timed region (sb_render_sharded)") if world > 1 else "single GPU",
+                       "parallelism": (f"sample-stride x{world}: scene/BVH replicas; the 132.7 MB float4 S buffers are summed and resolved "
+                                       "inside the timed region by sb_render_sharded (fused NVLS multimem kernel, or ncclAllReduce + "
+                                       "resolve: see `exchange`)") if world > 1 else "single GPU",
                        "l2": "explicit 256 MiB flush between timed steps; the per-batch path state (4 spp x 8.3 Mpix x 180 B = 6 GB) also exceeds L2"},
             "spp_mpix_per_s": head["spp_mpix_per_s"], "rays_per_step": head["rays_per_step"], "wall_ms_per_step": head["wall_ms_per_step"],
             "bvh_build_ms": head["bvh_build_ms"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
+            "exchange": head.get("exchange"),
             "roofline": head.get("roofline"), "roofline_other": head.get("roofline_other"), "traversal": head.get("traversal"),
             "stage_ms_share": head.get("stage_ms_share"), "cpu_baseline": head.get("cpu_baseline"), "scenes": scenes,
         }
