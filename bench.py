@@ -13,10 +13,11 @@ Metric: Mrays/s = (radiance + shadow rays actually traced, device counters) / ti
   e2e   : the same through the C ABI with HOST buffers: scene upload from pinned host memory, on-device BVH build,
           render, device->host read of the float4 image; wall clock, max over ranks
 N > 1 (torchrun): STRONG scaling -- the same 64-sample slice is split by sample index (rank r renders r, r+N, ...;
-64/N samples per rank) on scene/BVH replicas; the float4 accumulation buffers S (132.7 MB) are summed with ONE
-ncclAllReduce issued by the library itself on the render stream (sb_render_sharded) and resolved on every rank, all
-inside the timed region.  torch.distributed (gloo) is used only as the control plane: the NCCL id hand-off, barriers
-and the max-over-ranks of the timings.
+64/N samples per rank) on scene/BVH replicas; the float4 accumulation buffers S (132.7 MB) are summed and resolved
+on every rank by the library itself on the render stream (sb_render_sharded: ONE fused NVLS kernel -- multimem.ld_reduce
+/ multimem.st over NCCL symmetric windows -- where NCCL >= 2.28 and the hardware offer it, else ncclAllReduce + resolve;
+`exchange` in the output says which and how long), all inside the timed region.  torch.distributed (gloo) is used only
+as the control plane: the NCCL id hand-off, barriers and the max-over-ranks of the timings.
 
 Sub-records for the other configs (C2 Cornell, C3 kitchen-scale, C4 hair) are reported under "scenes" with the same
 fields (value, e2e, roofline, cpu_baseline at N = 1).
