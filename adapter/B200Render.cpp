@@ -83,7 +83,7 @@ void B200Render::fail(const char* what)
 void B200Render::init()
 {
     sb_device_cfg cfg = {};
-    cfg.device = 0; // the reference uses the current device (cudaFree(0), OptixRender.cpp:166)
+    cfg.device = mDevice; // the reference uses the current device (cudaFree(0), OptixRender.cpp:166)
     if (sb_create(&cfg, &mCtx) != SB_OK)
     {
         fail("sb_create");
@@ -279,30 +279,71 @@ sb_settings B200Render::readSettings()
     return s;
 }
 
-void B200Render::render(Buffer* output)
+// frame-0 uploads, camera and settings of OptiXRender::render (OptixRender.cpp:874-1004); false = skip the frame
+bool B200Render::prepareFrame(Buffer* output, sb_settings& s)
 {
     if (!mCtx || !mScene || !output)
-        return;
+        return false;
     // frame 0: uploads + acceleration structure (OptixRender.cpp:876-888)
     if (getSharedContext().mFrameNumber == 0 || !mSceneUploaded)
     {
         uploadScene();
         if (!mSceneUploaded)
-            return;
+            return false;
     }
     Camera& camera = mScene->getCamera(0);
     camera.updateAspectRatio(output->width() / float(output->height()));
     camera.updateViewMatrix();
     if (sb_set_camera(mCtx, glm::value_ptr(camera.matrices.view), camera.fov) != SB_OK)
-        return fail("sb_set_camera");
-    const sb_settings s = readSettings();
+    {
+        fail("sb_set_camera");
+        return false;
+    }
+    s = readSettings();
+    s.sample_offset = mRank; // sample sharding: this rank's stride of the global sample indices
+    s.sample_stride = mWorld;
     if (sb_set_settings(mCtx, &s) != SB_OK)
-        return fail("sb_set_settings");
+    {
+        fail("sb_set_settings");
+        return false;
+    }
+    return true;
+}
+
+void B200Render::render(Buffer* output)
+{
+    sb_settings s;
+    if (!prepareFrame(output, s))
+        return;
     if (sb_render(mCtx, static_cast<B200Buffer*>(output)->handle()) != SB_OK)
         return fail("sb_render");
     getSharedContext().mSubframeIndex = sb_subframe_index(mCtx);
     output->unmap();
     getSharedContext().mFrameNumber++;
+}
+
+bool B200Render::joinGroup(const void* id, uint32_t rank, uint32_t world)
+{
+    if (!mCtx || sb_comm_init(mCtx, id, rank, world) != SB_OK)
+    {
+        fail("sb_comm_init");
+        return false;
+    }
+    mRank = rank;
+    mWorld = world;
+    return true;
+}
+
+void B200Render::renderSharded(Buffer* output, uint32_t iterationsPerRank)
+{
+    sb_settings s;
+    if (!prepareFrame(output, s))
+        return;
+    if (sb_render_sharded(mCtx, static_cast<B200Buffer*>(output)->handle(), iterationsPerRank) != SB_OK)
+        return fail("sb_render_sharded");
+    getSharedContext().mSubframeIndex = sb_subframe_index(mCtx); // this rank's samples
+    output->unmap();
+    getSharedContext().mFrameNumber += iterationsPerRank;
 }
 
 } // namespace oka

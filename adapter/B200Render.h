@@ -63,6 +63,17 @@ public:
     // 120-136); OptiXRender decodes them with stb_image (OptixRender.cpp:1191-1200).  This adapter has no image
     // library of its own: the host hands it a decoder (path -> RGBA8, width, height).  Without one, or when decoding
     // fails, the material keeps its constant colour (the reference logs an error and binds an empty texture).
+    // ---- multi-GPU (new: OptiXRender is single-GPU, OptixRender.cpp:163-189) ---------------------------------
+    // One B200Render per GPU = one rank.  setDevice() before init(); rank 0 calls groupId() and hands the bytes to the
+    // other ranks (MPI, socket ...); every rank then calls joinGroup() (collective) and renderSharded() instead of
+    // render(): the rank renders sample indices rank, rank + world, ... of every pixel, the library sums the
+    // accumulation buffers over NVLink (fused NVLS kernel or ncclAllReduce) and every rank's buffer receives the image.
+    void setDevice(int device) { mDevice = device; }
+    static bool groupId(char id[SB_COMM_ID_BYTES]) { return sb_comm_get_unique_id(id) == SB_OK; }
+    bool joinGroup(const void* id, uint32_t rank, uint32_t world);
+    void renderSharded(Buffer* output, uint32_t iterationsPerRank);
+    const char* exchangePath() const { return sb_comm_exchange_path(mCtx); }
+
     using TextureLoader = std::function<bool(const std::string& path, std::vector<uint8_t>& rgba, uint32_t& width, uint32_t& height)>;
     void setTextureLoader(TextureLoader loader) { mTextureLoader = std::move(loader); }
 
@@ -72,7 +83,10 @@ private:
     sb_settings readSettings();
     void fail(const char* what);
 
+    bool prepareFrame(Buffer* output, sb_settings& s);
     sb_ctx* mCtx = nullptr;
+    int mDevice = 0;
+    uint32_t mRank = 0, mWorld = 1;
     bool mSceneUploaded = false;
     std::string mError;
 };

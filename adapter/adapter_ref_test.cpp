@@ -5,7 +5,7 @@
 // addMaterial), replaying the call journal a strelka_b200.Scene recorded, so that
 //   dump   : what oka::Scene + B200Render::buildSceneView flatten it to can be compared with the Python mirror
 //   render : the image through RenderFactory-style use of B200Render can be compared with the oracle (needs a GPU)
-// Usage: adapter_ref_test dump|render <journal.bin> <out.bin>
+// Usage: adapter_ref_test dump|render|sharded <journal.bin> <out.bin>
 #include "B200Render.h"
 
 #include <cstdio>
@@ -50,7 +50,8 @@ int main(int argc, char** argv)
 {
     if (argc < 4)
         return 2;
-    const bool doRender = std::strcmp(argv[1], "render") == 0;
+    const bool sharded = std::strcmp(argv[1], "sharded") == 0; // render through joinGroup / renderSharded (a group of one)
+    const bool doRender = std::strcmp(argv[1], "render") == 0 || sharded;
     Reader r{ std::fopen(argv[2], "rb") };
     if (!r.f)
         return 2;
@@ -207,8 +208,19 @@ int main(int argc, char** argv)
     render.setSharedContext(&ctx);
     render.init();
     Buffer* out = render.createBuffer(BufferDesc{ width, height, BufferFormat::FLOAT4 });
+    if (sharded)
+    {
+        char id[SB_COMM_ID_BYTES];
+        if (!B200Render::groupId(id) || !render.joinGroup(id, 0, 1))
+            return 4;
+    }
     for (uint32_t i = 0; i < sppTotal + 2; ++i) // two extra frames: nothing left to render, the image stays
-        render.render(out);
+    {
+        if (sharded)
+            render.renderSharded(out, 1);
+        else
+            render.render(out);
+    }
     out->map();
     std::fwrite(out->getHostPointer(), 1, out->getHostDataSize(), o);
     std::fclose(o);

@@ -301,6 +301,9 @@ SB_HD void trav_init(Traversal& T)
 #ifndef SB_PREFETCH_NEXT_NODE
 #define SB_PREFETCH_NEXT_NODE 0
 #endif
+#ifndef SB_SIMPLE_PREFETCH
+#define SB_SIMPLE_PREFETCH 0 // next-triangle prefetch in the one-ray-per-thread closest-hit traversal (camera rays)
+#endif
 #ifndef SB_PRIM_PAIR
 #define SB_PRIM_PAIR 0 // 1: the closest-hit step tests up to two pending triangles per iteration (trav_tri_pair)
 #endif
@@ -740,7 +743,7 @@ SB_HD bool traverse_bvh(const WideNode* __restrict__ nodes, const void* __restri
             break;
         while (T.tgroup.y != 0u)
         {
-            if (trav_prim<KIND, ANY, STATS>(T, prims, rayMask, ray, hit, st))
+            if (trav_prim<KIND, ANY, STATS, (SB_SIMPLE_PREFETCH != 0 && !ANY && KIND == 1)>(T, prims, rayMask, ray, hit, st))
             {
                 anyHit = true;
                 break;

@@ -61,9 +61,10 @@ def test_adapter_built_against_the_reference_headers_renders_like_oracle(tmp_pat
         settings.setAs("render/pt/depth", depth)
         j, out = tmp_path / "journal.bin", tmp_path / "out.raw"
         scene.write_journal(j, w, h, spp, depth)
-        r = subprocess.run([tool, "render", str(j), str(out)], capture_output=True, text=True)
-        assert r.returncode == 0, r.stdout + r.stderr
-        img = np.fromfile(out, dtype=np.float32).reshape(h, w, 4)
         ref, _, _, _ = pyoracle.OracleScene(scene).render(settings, w, h, spp)
         assert ref[..., :3].mean() > 0
-        assert rel_rmse(img, ref) <= 1e-3
+        for mode in ("render", "sharded"):  # B200Render::render, and joinGroup + renderSharded with a group of one
+            r = subprocess.run([tool, mode, str(j), str(out)], capture_output=True, text=True)
+            assert r.returncode == 0, mode + ": " + r.stdout + r.stderr
+            img = np.fromfile(out, dtype=np.float32).reshape(h, w, 4)
+            assert rel_rmse(img, ref) <= 1e-3, mode
