@@ -48,8 +48,8 @@ CONFIGS = {
                cpu_spp=2),
     "c3": dict(desc="C3 kitchen-scale 2.05M triangles, 50 UsdPreviewSurface materials, 1920x1080, sppTotal 2048, depth4 (configs[2])", w=1920,
                h=1080, spp_total=2048, depth=4, slice=32, cpu_stride=2, cpu_spp=1),
-    "c4": dict(desc="C4 hair 1.0M cubic B-spline segments, 1024x1024, sppTotal 1024, depth6 (configs[3])", w=1024, h=1024, spp_total=1024,
-               depth=6, slice=32, cpu_stride=2, cpu_spp=1),
+    "c4": dict(desc="C4 hair 1.0M cubic B-spline segments with the hair fibre BSDF (hairmat-style), 1024x1024, sppTotal 1024, depth6 (configs[3])",
+               w=1024, h=1024, spp_total=1024, depth=6, slice=32, cpu_stride=2, cpu_spp=1, kwargs=dict(material="hair")),
     "c5": dict(desc="C5 10.24M instanced triangles, 3840x2160, sppTotal 4096, depth4 (BASELINE.json configs[4])", w=3840, h=2160, spp_total=4096,
                depth=4, slice=64, cpu_stride=4, cpu_spp=1),
 }
@@ -60,7 +60,7 @@ def make_scene(key):
 
     c = CONFIGS[key]
     mk = {"c2": make_cornell, "c3": make_kitchen, "c4": make_hair, "c5": make_instanced}[key]
-    return mk(c["w"], c["h"], c["spp_total"], depth=c["depth"])
+    return mk(c["w"], c["h"], c["spp_total"], depth=c["depth"], **c.get("kwargs", {}))
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -215,6 +215,20 @@ class Render:
         h = C.c_void_p(-1) if cuda_stream is None else C.c_void_p(cuda_stream)
         _check(self._lib, self._ctx, self._lib.sb_set_stream(self._ctx, h), "sb_set_stream")
 
+    def set_camera_matrices(self, clip_to_view, view_to_world) -> None:
+        """Raw Params.clipToView / viewToWorld (row-major float[16] each, OptixRender.cpp:953-954) instead of the camera of
+        the scene; accumulation restarts only when the matrices differ from the previous call's (OptixRender.cpp:903-908).
+        Use with sb_render through render_raw()."""
+        a = np.ascontiguousarray(clip_to_view, dtype=np.float32).reshape(16)
+        b = np.ascontiguousarray(view_to_world, dtype=np.float32).reshape(16)
+        _check(self._lib, self._ctx, self._lib.sb_set_camera_matrices(self._ctx, a.ctypes.data_as(C.POINTER(C.c_float)),
+                                                                      b.ctypes.data_as(C.POINTER(C.c_float))), "sb_set_camera_matrices")
+
+    def render_raw(self, output: Buffer) -> None:
+        """sb_render without re-sending the scene camera (for hosts that drive the raw matrices)"""
+        _check(self._lib, self._ctx, self._lib.sb_render(self._ctx, output._h), "sb_render")
+        self.mSharedCtx.mSubframeIndex = self._lib.sb_subframe_index(self._ctx)
+
     def synchronize(self) -> None:
         _check(self._lib, self._ctx, self._lib.sb_synchronize(self._ctx), "sb_synchronize")
 

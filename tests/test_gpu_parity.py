@@ -290,3 +290,34 @@ def test_offset_ray_bit_exact_on_device(gpu_render):
     got = gpu_render.test_offset_ray(p, nrm)
     want = np.stack([pyoracle.offset_ray(p[i], nrm[i]) for i in range(0, n, 37)])
     assert np.array_equal(got[::37].view(np.uint32), want.view(np.uint32))
+
+
+def test_raw_camera_matrices_reset_only_on_change(gpu_render):
+    """a host that sets Params.clipToView / viewToWorld every frame keeps accumulating while they stand still
+    (OptixRender.cpp:903-908 resets only when the matrices differ from the previous frame's)"""
+    from strelka_b200.scenes import make_cornell
+
+    w = h = 48
+    s, st, _ = make_cornell(w, h, 16)
+    r = gpu_render
+    r.setScene(s)
+    r.setSharedContext(SharedContext(mSettingsManager=st))
+    r._last_settings = None
+    buf = r.createBuffer(BufferDesc(w, h, BufferFormat.FLOAT4))
+    r.render(buf)  # uploads scene, settings and the scene camera
+    c2v, v2w = pyoracle.OracleScene(s).camera_matrices(w, h)
+    r.set_camera_matrices(c2v, v2w)  # switching from the fov path: restart
+    assert r._lib.sb_subframe_index(r._ctx) == 0
+    for i in range(3):
+        r.set_camera_matrices(c2v, v2w)  # unchanged: no restart
+        r.render_raw(buf)
+        assert r.getSharedContext().mSubframeIndex == i + 1
+    a = buf.map().copy()
+    ref, _, _, _ = pyoracle.OracleScene(s).render(st, w, h, 3)
+    assert rel_rmse(a, ref) <= 1e-3  # the raw matrices are the ones the scene camera produces
+    v2w2 = v2w.copy()
+    v2w2[3] += 0.01  # move the eye
+    r.set_camera_matrices(c2v, v2w2)
+    assert r._lib.sb_subframe_index(r._ctx) == 0
+    r._last_view = None  # hand the camera back to the scene for the tests that follow
+    buf.destroy()
