@@ -236,23 +236,35 @@ SB_HD float3 hair_to_local(const HairFrame& f, const float3& w)
     return mk3(dot(w, f.t), dot(w, f.n), dot(w, f.b));
 }
 
-// evaluate: fcos = f * |cos| for world directions k1 (towards the viewer) and k2 (towards the light)
-SB_HD void hair_evaluate(const sb_material& m, const float3& normal, const float3& tangent, const float3& k1, const float3& k2, float3& fcos,
-                         float& pdf)
+// Everything that depends on the material, the fibre frame and the outgoing direction k1 only: computed once per hit and
+// shared by the BSDF sample and the NEE evaluation of the same bounce (closest_hit.cu:521 and :571 see the same state).
+struct HairCtx
 {
-    const HairLobes L = hair_init(m);
-    const HairFrame F = hair_frame(tangent, normal);
-    const HairOut o = hair_outgoing(L, hair_to_local(F, k1));
-    hair_eval_local(L, o, hair_to_local(F, k2), fcos, pdf);
+    HairLobes L;
+    HairFrame F;
+    HairOut o;
+};
+SB_HD HairCtx hair_prepare(const sb_material& m, const float3& normal, const float3& tangent, const float3& k1)
+{
+    HairCtx c;
+    c.L = hair_init(m);
+    c.F = hair_frame(tangent, normal);
+    c.o = hair_outgoing(c.L, hair_to_local(c.F, k1));
+    return c;
+}
+
+// evaluate: fcos = f * |cos| for the world direction k2 (towards the light)
+SB_HD void hair_evaluate(const HairCtx& c, const float3& k2, float3& fcos, float& pdf)
+{
+    hair_eval_local(c.L, c.o, hair_to_local(c.F, k2), fcos, pdf);
 }
 
 // sample: xi.z picks the lobe, (xi.x, xi.y) the longitudinal angle, xi.w the azimuth.  Returns false for an absorbed sample.
-SB_HD bool hair_sample(const sb_material& m, const float3& normal, const float3& tangent, const float3& k1, const float4& xi, float3& k2,
-                       float3& weight, float& pdf)
+SB_HD bool hair_sample(const HairCtx& c, const float4& xi, float3& k2, float3& weight, float& pdf)
 {
-    const HairLobes L = hair_init(m);
-    const HairFrame F = hair_frame(tangent, normal);
-    const HairOut o = hair_outgoing(L, hair_to_local(F, k1));
+    const HairLobes& L = c.L;
+    const HairFrame& F = c.F;
+    const HairOut& o = c.o;
     int p = 0;
     float u = xi.z;
     for (; p < kHairLobes; ++p)
@@ -286,6 +298,20 @@ SB_HD bool hair_sample(const sb_material& m, const float3& normal, const float3&
     k2 = normalize(wi.x * F.t + wi.y * F.n + wi.z * F.b);
     weight = fcos / pdf;
     return true;
+}
+
+// one-shot forms (test hook, host emulation)
+SB_HD void hair_evaluate(const sb_material& m, const float3& normal, const float3& tangent, const float3& k1, const float3& k2, float3& fcos,
+                         float& pdf)
+{
+    const HairCtx c = hair_prepare(m, normal, tangent, k1);
+    hair_evaluate(c, k2, fcos, pdf);
+}
+SB_HD bool hair_sample(const sb_material& m, const float3& normal, const float3& tangent, const float3& k1, const float4& xi, float3& k2,
+                       float3& weight, float& pdf)
+{
+    const HairCtx c = hair_prepare(m, normal, tangent, k1);
+    return hair_sample(c, xi, k2, weight, pdf);
 }
 
 } // namespace sb

@@ -525,8 +525,11 @@ struct StagedSink
 #ifndef SB_SHADE_MIN_BLOCKS
 #define SB_SHADE_MIN_BLOCKS 8 // measured: 64 registers + a few L1 spills beat 111 registers at 25 % occupancy (latency-bound kernel)
 #endif
+#ifndef SB_SHADE_HAIR_MIN_BLOCKS
+#define SB_SHADE_HAIR_MIN_BLOCKS 4 // the fibre BSDF wants ~112 registers (no spills); measured +1.4 % on the C4 step
+#endif
 template <bool CURVES, bool PREVIEW, bool RECT_UNIFORM, bool HAIR = false, bool TEX = false>
-__global__ void __launch_bounds__(kBlock, SB_SHADE_MIN_BLOCKS) k_shade(FrameParams P, SceneDev S, Queues Q, uint32_t depth)
+__global__ void __launch_bounds__(kBlock, (HAIR ? SB_SHADE_HAIR_MIN_BLOCKS : SB_SHADE_MIN_BLOCKS)) k_shade(FrameParams P, SceneDev S, Queues Q, uint32_t depth)
 {
     // 12 KB of byte-sliced Sobol tables per CTA (L2-resident source; 6 x 128-bit loads per thread)
     __shared__ __align__(16) uint32_t s_tab[kSobolTabWords];

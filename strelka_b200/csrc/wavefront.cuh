@@ -406,7 +406,23 @@ SB_HD bool shade_bounce(const FrameParams& P, const SceneDev& S, PathState& ps, 
     // lightPoint = (v[3], v[4]), russian roulette = v[4]
     const Sample5 rn = sampler_sample5(sidx, depth, sobolTab);
     const float3 k1 = -rayD;
-    const BsdfSample bs = bsdf_sample<PREVIEW, HAIR>(mat, baseColor, shadingNormal, sf.geomNormal, sf.tangent, k1, mk4(rn.v[0], rn.v[1], rn.v[2], rn.v[3]));
+    // hair: material constants, fibre frame and everything that depends on k1 only are shared by the sample and the NEE
+    // evaluation of this bounce (hair.cuh; same arithmetic as the one-shot forms)
+    const bool isHair = HAIR && mat.model == SB_MATERIAL_HAIR;
+    HairCtx hc;
+    BsdfSample bs;
+    if (isHair)
+    {
+        hc = hair_prepare(mat, shadingNormal, sf.tangent, k1);
+        bs.k2 = mk3(0.0f);
+        bs.bsdf_over_pdf = mk3(0.0f);
+        bs.pdf = 0.0f;
+        bs.event = EV_ABSORB;
+        if (hair_sample(hc, mk4(rn.v[0], rn.v[1], rn.v[2], rn.v[3]), bs.k2, bs.bsdf_over_pdf, bs.pdf))
+            bs.event = EV_GLOSSY | (dot(sf.geomNormal, bs.k2) >= 0.0f ? EV_REFLECTION : EV_TRANSMISSION);
+    }
+    else
+        bs = bsdf_sample<PREVIEW, false>(mat, baseColor, shadingNormal, sf.geomNormal, sf.tangent, k1, mk4(rn.v[0], rn.v[1], rn.v[2], rn.v[3]));
     if (bs.event == EV_ABSORB)
     {
         return false; // throughput = 0 (firstEventType = eAbsorb: counted by neither AOV)
@@ -453,7 +469,14 @@ SB_HD bool shade_bounce(const FrameParams& P, const SceneDev& S, PathState& ps, 
                 const bool nextEventValid = ((dot(ls.L, shadingNormal) > 0.0f) != isInside) && lightPdf != 0.0f;
                 if (nextEventValid)
                 {
-                    const BsdfEval ev = bsdf_evaluate<PREVIEW, HAIR>(mat, baseColor, shadingNormal, sf.geomNormal, sf.tangent, k1, ls.L);
+                    BsdfEval ev;
+                    if (isHair)
+                    {
+                        ev.diffuse = mk3(0.0f);
+                        hair_evaluate(hc, ls.L, ev.glossy, ev.pdf);
+                    }
+                    else
+                        ev = bsdf_evaluate<PREVIEW, false>(mat, baseColor, shadingNormal, sf.geomNormal, sf.tangent, k1, ls.L);
                     if (isnan3(ev.diffuse) || isnan3(ev.glossy))
                     {
                         ps.L = mk4(10000.0f, 0.0f, 0.0f, 0.0f);
