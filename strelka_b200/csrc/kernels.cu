@@ -281,6 +281,18 @@ __device__ __forceinline__ void stage_top_nodes(uint4* dst, const WideNode* node
 #ifndef SB_CURVE_PREFETCH
 #define SB_CURVE_PREFETCH 0
 #endif
+#ifndef SB_EXTEND_HIT_SMEM
+#define SB_EXTEND_HIT_SMEM 0
+#endif
+// share of the child-box byte conversions done on the XU pipe (wide_node_hits: 16 * pair mask + children per half);
+// measured per kernel (profiles/r02_ab_experiments.txt, r2t..r2v): near-xy + z pairs of two children per half for the
+// closest-hit loop, the z pair of every child for the any-hit loop and the one-ray-per-thread kernels (SB_SIMPLE_XU)
+#ifndef SB_EXTEND_XU
+#define SB_EXTEND_XU (16 * 5 + 2)
+#endif
+#ifndef SB_SHADOW_XU
+#define SB_SHADOW_XU (16 * 4 + 4)
+#endif
 #ifndef SB_EXTEND_PREFETCH
 #define SB_EXTEND_PREFETCH 1 // closest-hit rays prefetch the next pending triangle of a leaf group (trav_prim PF)
 #endif
@@ -297,7 +309,14 @@ __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FramePa
     int phase = 0;
     Ray ray;
     RayPrep rp;
+#if SB_EXTEND_HIT_SMEM
+    // the hit record is cold state (written when a closer hit is accepted, read once at the end of the ray): it lives in
+    // shared memory (7-word stride: conflict-free) and its registers go to the traversal loop
+    __shared__ HitRec s_hit[kBlock];
+    HitRec& hit = s_hit[threadIdx.x];
+#else
     HitRec hit;
+#endif
     Traversal T;
     TravStack K;
     NodeRegs pn; // node in flight (SB_PIPE_NODE)
@@ -356,9 +375,9 @@ __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FramePa
                     more = trav_step_pipe<2, false, STATS, (SB_SMEM_STACK > 0)>(T, K, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st, pn, pnValid);
 #else
                 if (phase == 0)
-                    more = trav_step<1, false, STATS, (SB_SMEM_STACK > 0), (SB_EXTEND_PREFETCH != 0)>(T, K, S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, anyHit, &st, topTri);
+                    more = trav_step<1, false, STATS, (SB_SMEM_STACK > 0), (SB_EXTEND_PREFETCH != 0), SB_EXTEND_XU>(T, K, S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, anyHit, &st, topTri);
                 else if (CURVES && phase == 1)
-                    more = trav_step<2, false, STATS, (SB_SMEM_STACK > 0), (SB_CURVE_PREFETCH != 0)>(T, K, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st, topSeg);
+                    more = trav_step<2, false, STATS, (SB_SMEM_STACK > 0), (SB_CURVE_PREFETCH != 0), SB_EXTEND_XU>(T, K, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st, topSeg);
 #endif
                 if (!more)
                 {
@@ -467,9 +486,9 @@ __global__ void __launch_bounds__(kBlock, SB_SHADOW_MIN_BLOCKS) k_shadow(SceneDe
                     more = trav_step_unit_pipe<2, true, STATS, (SB_SMEM_STACK > 0)>(T, K, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st, pn, pnValid);
 #else
                 if (phase == 0)
-                    more = trav_step_unit<1, true, STATS, (SB_SMEM_STACK > 0), PF>(T, K, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st, topTri);
+                    more = trav_step_unit<1, true, STATS, (SB_SMEM_STACK > 0), PF, SB_SHADOW_XU>(T, K, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st, topTri);
                 else if (CURVES && phase == 1)
-                    more = trav_step_unit<2, true, STATS, (SB_SMEM_STACK > 0), (SB_CURVE_PREFETCH != 0)>(T, K, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st, topSeg);
+                    more = trav_step_unit<2, true, STATS, (SB_SMEM_STACK > 0), (SB_CURVE_PREFETCH != 0), SB_SHADOW_XU>(T, K, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st, topSeg);
 #endif
                 if (!more)
                 {

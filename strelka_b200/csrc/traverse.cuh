@@ -115,6 +115,12 @@ SB_HD float byte_to_float(uint32_t w, int j)
 #endif
 }
 
+#ifndef SB_MAGIC_CONST
+#define SB_MAGIC_CONST 1
+#endif
+#if SB_MAGIC_CONST && defined(__CUDACC__)
+static __constant__ uint32_t c_byteMagic = 0x4B000000u;
+#endif
 #if defined(__CUDA_ARCH__)
 // Packed fp32 arithmetic of sm_100 (FADD2 / FFMA2: two IEEE fp32 operations per issued instruction, each
 // component rounded exactly like the scalar instruction).  The traversal kernels are bound by instruction issue,
@@ -141,15 +147,23 @@ __device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsig
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
 }
-// bit pattern of 2^23 + byte j of w (see byte_to_float)
+// bit pattern of 2^23 + byte j of w (see byte_to_float).  PRMT takes ONE immediate: with the 2^23 pattern as a literal,
+// ptxas spends it on that and re-materialises the four byte selectors in registers -- 65 moves per node visit in the
+// SASS of the persistent kernels.  Read from constant memory the pattern is a c[3][..] operand and the selector is the
+// immediate (SB_MAGIC_CONST=1).
 __device__ __forceinline__ float byte_magic(uint32_t w, int j)
 {
+#if SB_MAGIC_CONST
+    return __uint_as_float(__byte_perm(w, c_byteMagic, 0x7540u + uint32_t(j)));
+#else
     return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + uint32_t(j)));
+#endif
 }
 #endif
 
 // Ray/child-box tests of one wide node -> 32-bit hit mask: bits 24..31 inner children in traversal
 // priority (highest first), bits 0..23 leaf primitives relative to primBase.
+template <int XU = 0>
 SB_HD uint32_t wide_node_hits(const uint4& n0, const uint4& n1, const uint4& n2, const uint4& n3, const uint4& n4, const float3& o,
                               const float3& idir, uint32_t octinv4, bool negx, bool negy, bool negz, float tmin, float tmax)
 {
@@ -184,9 +198,18 @@ SB_HD uint32_t wide_node_hits(const uint4& n0, const uint4& n1, const uint4& n2,
         {
 #if defined(__CUDA_ARCH__) && SB_F32X2
             float t0x, t0y, t0z, t1x, t1y, t1z;
-            f2_unpack(f2_fma(f2_add(f2_pack(byte_magic(nearx, j), byte_magic(neary, j)), kMagic), Axy, Bxy), t0x, t0y);
-            f2_unpack(f2_fma(f2_add(f2_pack(byte_magic(farx, j), byte_magic(fary, j)), kMagic), Axy, Bxy), t1x, t1y);
-            f2_unpack(f2_fma(f2_add(f2_pack(byte_magic(nearz, j), byte_magic(farz, j)), kMagic), Azz, Bzz), t0z, t1z);
+            // XU = 16 * pairs + n: the pairs selected by `pairs` (1: near xy, 2: far xy, 4: z) of the first n children of
+            // each half convert on the otherwise idle XU pipe -- I2F.U8 with a byte selector, one instruction instead of
+            // PRMT + half an FADD2 (the ALU pipe is the busiest one in this loop).  Both conversions are exact.
+#define SB_SLAB_PAIR(bit, wa, wb, A, B, ra, rb)                                                                           \
+    if (((XU >> 4) & bit) != 0 && j < (XU & 15))                                                                           \
+        f2_unpack(f2_fma(f2_pack(float(byte_of(wa, j)), float(byte_of(wb, j))), A, B), ra, rb);                            \
+    else                                                                                                                   \
+        f2_unpack(f2_fma(f2_add(f2_pack(byte_magic(wa, j), byte_magic(wb, j)), kMagic), A, B), ra, rb);
+            SB_SLAB_PAIR(1, nearx, neary, Axy, Bxy, t0x, t0y)
+            SB_SLAB_PAIR(2, farx, fary, Axy, Bxy, t1x, t1y)
+            SB_SLAB_PAIR(4, nearz, farz, Azz, Bzz, t0z, t1z)
+#undef SB_SLAB_PAIR
 #else
             const float t0x = fmaf(byte_to_float(nearx, j), ax, bx);
             const float t0y = fmaf(byte_to_float(neary, j), ay, by);
@@ -301,6 +324,9 @@ SB_HD void trav_init(Traversal& T)
 #ifndef SB_PREFETCH_NEXT_NODE
 #define SB_PREFETCH_NEXT_NODE 0
 #endif
+#ifndef SB_SIMPLE_XU
+#define SB_SIMPLE_XU (16 * 4 + 4) // XU share of the byte conversions (wide_node_hits) in the one-ray-per-thread traversals
+#endif
 #ifndef SB_SIMPLE_PREFETCH
 #define SB_SIMPLE_PREFETCH 0 // next-triangle prefetch in the one-ray-per-thread closest-hit traversal (camera rays)
 #endif
@@ -313,7 +339,7 @@ SB_HD void trav_init(Traversal& T)
 #ifndef SB_TOP_SMEM
 #define SB_TOP_SMEM 0 // number of top-level nodes (the first K of the level-ordered array) staged in shared memory
 #endif
-template <bool STATS, bool SSTACK = false>
+template <bool STATS, bool SSTACK = false, int XU = 0>
 SB_HD bool trav_node(Traversal& T, TravStack& K, const WideNode* __restrict__ nodes, const Ray& ray, const RayPrep& rp, TravStats* st,
                      const uint4* __restrict__ topNodes = nullptr)
 {
@@ -379,7 +405,7 @@ SB_HD bool trav_node(Traversal& T, TravStack& K, const WideNode* __restrict__ no
     }
     if (STATS)
         st->nodes++;
-    const uint32_t hm = wide_node_hits(n0, n1, n2, n3, n4, ray.o, rp.idir, rp.octinv4, rp.negx, rp.negy, rp.negz, ray.tmin, ray.tmax);
+    const uint32_t hm = wide_node_hits<XU>(n0, n1, n2, n3, n4, ray.o, rp.idir, rp.octinv4, rp.negx, rp.negy, rp.negz, ray.tmin, ray.tmax);
 #if defined(__CUDA_ARCH__) && SB_PREFETCH_CHILDREN
     // the hit children that will wait on the stack: pull their nodes towards the SM now (children are contiguous)
     if (SSTACK && (hm & 0xff000000u) != 0u)
@@ -598,13 +624,13 @@ SB_HD bool trav_tri_pair(Traversal& T, const void* __restrict__ prims, uint32_t 
 
 // one full step of one lane: node half-step if idle, then one primitive if any is pending.
 // Returns false when the traversal is finished; anyHit is set when an ANY query found an occluder.
-template <int KIND, bool ANY, bool STATS, bool SSTACK = false, bool PF = false>
+template <int KIND, bool ANY, bool STATS, bool SSTACK = false, bool PF = false, int XU = 0>
 SB_HD bool trav_step(Traversal& T, TravStack& K, const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask, Ray& ray,
                      const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st, const uint4* __restrict__ topNodes = nullptr)
 {
     if (T.tgroup.y == 0u)
     {
-        if (!trav_node<STATS, SSTACK>(T, K, nodes, ray, rp, st, topNodes))
+        if (!trav_node<STATS, SSTACK, XU>(T, K, nodes, ray, rp, st, topNodes))
             return false;
     }
     if (T.tgroup.y != 0u)
@@ -687,7 +713,7 @@ SB_HD bool trav_step_unit_pipe(Traversal& T, TravStack& K, const WideNode* __res
 // Single-unit variant of trav_step: ONE primitive test if any is pending, else ONE node visit.  Measured on the
 // 2 M-triangle scene the any-hit (shadow) kernel runs 1.5x faster with this shape, the closest-hit kernel
 // slightly faster with the node+primitive shape above (profiles/r01_b_*).
-template <int KIND, bool ANY, bool STATS, bool SSTACK = false, bool PF = false>
+template <int KIND, bool ANY, bool STATS, bool SSTACK = false, bool PF = false, int XU = 0>
 SB_HD bool trav_step_unit(Traversal& T, TravStack& K, const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask, Ray& ray,
                           const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st, const uint4* __restrict__ topNodes = nullptr)
 {
@@ -700,7 +726,7 @@ SB_HD bool trav_step_unit(Traversal& T, TravStack& K, const WideNode* __restrict
         }
         return true;
     }
-    return trav_node<STATS, SSTACK>(T, K, nodes, ray, rp, st, topNodes);
+    return trav_node<STATS, SSTACK, XU>(T, K, nodes, ray, rp, st, topNodes);
 }
 
 // "While-while" step: ONE node visit, then ALL the primitives it queued.  The lanes of a warp meet again at every
@@ -739,7 +765,7 @@ SB_HD bool traverse_bvh(const WideNode* __restrict__ nodes, const void* __restri
     // lanes of a warp meet again at every node test (the expensive half) instead of drifting apart
     for (;;)
     {
-        if (T.tgroup.y == 0u && !trav_node<STATS>(T, K, nodes, ray, rp, st))
+        if (T.tgroup.y == 0u && !trav_node<STATS, false, SB_SIMPLE_XU>(T, K, nodes, ray, rp, st))
             break;
         while (T.tgroup.y != 0u)
         {
@@ -753,7 +779,7 @@ SB_HD bool traverse_bvh(const WideNode* __restrict__ nodes, const void* __restri
             break;
     }
 #else
-    while (trav_step<KIND, ANY, STATS>(T, K, nodes, prims, rayMask, ray, rp, hit, anyHit, st))
+    while (trav_step<KIND, ANY, STATS, false, false, SB_SIMPLE_XU>(T, K, nodes, prims, rayMask, ray, rp, hit, anyHit, st))
     {
     }
 #endif
