@@ -10,15 +10,22 @@
 //
 // Node (80 B = 5 x 16 B, fetched with 128-bit loads):
 //   n0 = { p.x, p.y, p.z, ex | ey<<8 | ez<<16 | imask<<24 }      quantisation frame + inner-node mask
-//   n1 = { childBase, primBase, meta[0..3], meta[4..7] }
+//   n1 = { childBase, primBase, valid, 0 }      (SB_FIXED_BITS = 0: { childBase, primBase, meta[0..3], meta[4..7] })
 //   n2 = { qlo.x[0..3], qlo.x[4..7], qlo.y[0..3], qlo.y[4..7] }
 //   n3 = { qlo.z[0..3], qlo.z[4..7], qhi.x[0..3], qhi.x[4..7] }
 //   n4 = { qhi.y[0..3], qhi.y[4..7], qhi.z[0..3], qhi.z[4..7] }
-// child box = p + q * 2^(e-127); meta: 0 empty | inner: 0x20 | (24 + slot) | leaf: unary(count)<<5 | first
-// primitive offset (relative to primBase, < 24).  Slot s prefers children lying towards
+// child box = p + q * 2^(e-127).  valid = the bits of a 32-bit hit mask the node's slots own: slot s owns bits
+// 3s..3s+2 if it is a leaf (one bit per primitive, unary; its first primitive is primBase + popc(valid below bit 3s))
+// and bit 24+s if it is an inner node (its node is childBase + popc(imask below s)); an empty slot owns nothing.
+// (meta, the encoding of Ylitie et al.: 0 empty | inner: 0x20 | (24 + slot) | leaf: unary(count)<<5 | first primitive
+// offset relative to primBase, < 24.)  Slot s prefers children lying towards
 // ((s&1?+:-), (s&2?+:-), (s&4?+:-)) of the node centre, which makes (slot ^ octant) a front-to-back order.
 #pragma once
 #include "hd.cuh"
+
+#ifndef SB_FIXED_BITS
+#define SB_FIXED_BITS 1 // hit-mask assembly of a node visit: see traverse.cuh
+#endif
 
 namespace sb
 {
@@ -371,7 +378,7 @@ SB_HD void collapse_emit(const Bvh2Node* nodes, const uint32_t* count, uint32_t 
     const float sx = u2f(ex << 23), sy = u2f(ey << 23), sz = u2f(ez << 23); // cell sizes (powers of two)
     const float isx = 1.0f / sx, isy = 1.0f / sy, isz = 1.0f / sz;
     uint8_t meta[8], qlo[3][8], qhi[3][8];
-    uint32_t imask = 0, innerRank = 0, primOff = 0;
+    uint32_t imask = 0, innerRank = 0, primOff = 0, leafBits = 0;
     for (int s = 0; s < 8; ++s)
     {
         const uint32_t c = slots[s];
@@ -422,6 +429,7 @@ SB_HD void collapse_emit(const Bvh2Node* nodes, const uint32_t* count, uint32_t 
                 primOrder[primBase + primOff + k] = leaves[k];
             const uint32_t unary = (nl >= 3) ? 7u : ((nl == 2) ? 3u : 1u);
             meta[s] = uint8_t((unary << 5) | primOff);
+            leafBits |= unary << (3 * s);
             primOff += nl;
         }
     }
@@ -432,8 +440,14 @@ SB_HD void collapse_emit(const Bvh2Node* nodes, const uint32_t* count, uint32_t 
     out.n0.w = ex | (ey << 8) | (ez << 16) | (imask << 24);
     out.n1.x = childBase;
     out.n1.y = primBase;
+#if SB_FIXED_BITS
+    out.n1.z = leafBits | (imask << 24); // the bits of a hit mask this node's slots own (traverse.cuh)
+    out.n1.w = 0u;
+    (void)meta;
+#else
     out.n1.z = pack4(meta);
     out.n1.w = pack4(meta + 4);
+#endif
     out.n2.x = pack4(qlo[0]);
     out.n2.y = pack4(qlo[0] + 4);
     out.n2.z = pack4(qlo[1]);

@@ -319,8 +319,6 @@ __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FramePa
 #endif
     Traversal T;
     TravStack K;
-    NodeRegs pn; // node in flight (SB_PIPE_NODE)
-    bool pnValid = false;
 #if SB_SMEM_STACK
     static_assert(kTravBlock == kBlock, "shared-memory traversal stack stride");
     __shared__ uint2 s_stack[SB_SMEM_STACK * kBlock];
@@ -354,7 +352,6 @@ __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FramePa
             hit.prim = hit.inst = hit.kind = 0u;
             hit.gid = 0xffffffffu;
             trav_init(T);
-            pnValid = false;
             phase = haveTris ? 0 : (haveSegs ? 1 : 2);
             active = true;
         }
@@ -368,24 +365,16 @@ __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FramePa
                 // step shape: node visit + one primitive test per iteration.  Measured on the 2 M / 10 M-triangle and hair
                 // scenes against one unit per iteration (best for the any-hit kernel) and node + all its primitives
                 // (+7 % here; best for the one-ray-per-thread kernels, which have no refill ballots).
-#if SB_PIPE_NODE >= 1
-                if (phase == 0)
-                    more = trav_step_pipe<1, false, STATS, (SB_SMEM_STACK > 0)>(T, K, S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, anyHit, &st, pn, pnValid);
-                else if (CURVES && phase == 1)
-                    more = trav_step_pipe<2, false, STATS, (SB_SMEM_STACK > 0)>(T, K, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st, pn, pnValid);
-#else
                 if (phase == 0)
                     more = trav_step<1, false, STATS, (SB_SMEM_STACK > 0), (SB_EXTEND_PREFETCH != 0), SB_EXTEND_XU>(T, K, S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, anyHit, &st, topTri);
                 else if (CURVES && phase == 1)
                     more = trav_step<2, false, STATS, (SB_SMEM_STACK > 0), (SB_CURVE_PREFETCH != 0), SB_EXTEND_XU>(T, K, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st, topSeg);
-#endif
                 if (!more)
                 {
                     if (phase == 0 && haveSegs)
                     {
                         phase = 1;
                         trav_init(T);
-                        pnValid = false;
                     }
                     else
                     {
@@ -432,8 +421,6 @@ __global__ void __launch_bounds__(kBlock, SB_SHADOW_MIN_BLOCKS) k_shadow(SceneDe
     HitRec hit;
     Traversal T;
     TravStack K;
-    NodeRegs pn; // node in flight (SB_PIPE_NODE)
-    bool pnValid = false;
 #if SB_SMEM_STACK
     static_assert(kTravBlock == kBlock, "shared-memory traversal stack stride");
     __shared__ uint2 s_stack[SB_SMEM_STACK * kBlock];
@@ -466,7 +453,6 @@ __global__ void __launch_bounds__(kBlock, SB_SHADOW_MIN_BLOCKS) k_shadow(SceneDe
             hit.kind = 0u;
             hit.gid = 0xffffffffu;
             trav_init(T);
-            pnValid = false;
             phase = haveTris ? 0 : (haveSegs ? 1 : 2);
             active = true;
         }
@@ -479,24 +465,16 @@ __global__ void __launch_bounds__(kBlock, SB_SHADOW_MIN_BLOCKS) k_shadow(SceneDe
                 bool more = false, occluded = false;
                 // step shape: ONE unit (a primitive test if one is pending, else a node visit) per iteration: measured
                 // 1.5x faster for any-hit rays than node + primitive (profiles/r01_b_*)
-#if SB_PIPE_NODE >= 2
-                if (phase == 0)
-                    more = trav_step_unit_pipe<1, true, STATS, (SB_SMEM_STACK > 0)>(T, K, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st, pn, pnValid);
-                else if (CURVES && phase == 1)
-                    more = trav_step_unit_pipe<2, true, STATS, (SB_SMEM_STACK > 0)>(T, K, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st, pn, pnValid);
-#else
                 if (phase == 0)
                     more = trav_step_unit<1, true, STATS, (SB_SMEM_STACK > 0), PF, SB_SHADOW_XU>(T, K, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st, topTri);
                 else if (CURVES && phase == 1)
                     more = trav_step_unit<2, true, STATS, (SB_SMEM_STACK > 0), (SB_CURVE_PREFETCH != 0), SB_SHADOW_XU>(T, K, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st, topSeg);
-#endif
                 if (!more)
                 {
                     if (!occluded && phase == 0 && haveSegs)
                     {
                         phase = 1;
                         trav_init(T);
-                        pnValid = false;
                     }
                     else
                     {

@@ -161,6 +161,52 @@ __device__ __forceinline__ float byte_magic(uint32_t w, int j)
 }
 #endif
 
+// SB_FIXED_BITS: how the hit mask of a node visit is assembled.
+//   0: Ylitie et al. 2017 -- per child, (unary triangle count) << (meta index ^ octant): five ALU instructions each.
+//   1: every child slot s owns FIXED bits of the mask -- 3s..3s+2 if it is a leaf (its triangles, unary), 24+s if it is
+//      an inner node -- so a hit costs one predicated OR with an immediate; the node carries the valid-bit word
+//      (n1.z) that strips the bits a slot does not own.  The octant permutation of the inner byte (traversal order:
+//      bit 24 + (s ^ octinv)) is one lookup in a 2 KB table, and a pending triangle's index is recovered from the
+//      valid word with one population count: primBase + popc(valid below the bit).
+#ifndef SB_FIXED_BITS
+#define SB_FIXED_BITS 1
+#endif
+#if SB_FIXED_BITS
+struct OctantPermLut
+{
+    uint8_t v[8 * 256]; // v[o * 256 + x]: bit s of x moved to bit s ^ o
+    constexpr OctantPermLut() : v{}
+    {
+        for (int o = 0; o < 8; ++o)
+            for (int x = 0; x < 256; ++x)
+            {
+                int y = 0;
+                for (int b = 0; b < 8; ++b)
+                    if (x & (1 << b))
+                        y |= 1 << (b ^ o);
+                v[o * 256 + x] = uint8_t(y);
+            }
+    }
+};
+#if defined(__CUDACC__)
+static __device__ const OctantPermLut g_octantPerm = OctantPermLut();
+#endif
+// inner: hit inner children by slot (8 bits); octinv8 = octinv << 8
+SB_HD uint32_t permute_inner_hits(uint32_t inner, uint32_t octinv8)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg(&g_octantPerm.v[octinv8 | inner]);
+#else
+    const uint32_t o = octinv8 >> 8;
+    uint32_t y = 0;
+    for (uint32_t b = 0; b < 8u; ++b)
+        if (inner & (1u << b))
+            y |= 1u << (b ^ o);
+    return y;
+#endif
+}
+#endif
+
 // Ray/child-box tests of one wide node -> 32-bit hit mask: bits 24..31 inner children in traversal
 // priority (highest first), bits 0..23 leaf primitives relative to primBase.
 template <int XU = 0>
@@ -183,11 +229,13 @@ SB_HD uint32_t wide_node_hits(const uint4& n0, const uint4& n1, const uint4& n2,
 #pragma unroll
     for (int half = 0; half < 2; ++half)
     {
+#if !SB_FIXED_BITS
         const uint32_t meta4 = half ? n1.w : n1.z;
         const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
         const uint32_t innerMask4 = (isInner4 >> 4) * 0xffu;
         const uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1f1f1f1fu;
         const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+#endif
         const uint32_t qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z, qloz = half ? n3.y : n3.x;
         const uint32_t qhix = half ? n3.w : n3.z, qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
         const uint32_t nearx = negx ? qhix : qlox, farx = negx ? qlox : qhix;
@@ -222,11 +270,20 @@ SB_HD uint32_t wide_node_hits(const uint4& n0, const uint4& n1, const uint4& n2,
             // conservative far plane: the 1 + 2*gamma(3) factor of Ize 2013 (the CPU oracle's slab test uses it
             // too).  It must scale the RESULT: pre-scaled plane coefficients lose it to cancellation.
             const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tmax)) * 1.0000004f;
+#if SB_FIXED_BITS
+            if (cmin <= cmax)
+                hitmask |= (7u << (3 * (4 * half + j))) | (1u << (24 + 4 * half + j));
+#else
             if (cmin <= cmax)
                 hitmask |= byte_of(childBits4, j) << byte_of(bitIndex4, j);
+#endif
         }
     }
+#if SB_FIXED_BITS
+    return hitmask & n1.z; // inner bits by SLOT (not yet in traversal order)
+#else
     return hitmask;
+#endif
 }
 
 // Moller-Trumbore on (v0, e1, e2); expression tree identical to the oracle's (fma dot/cross).
@@ -265,7 +322,11 @@ SB_HD RayPrep prepare_ray(const float3& d)
     r.negz = d.z < 0.0f;
     const uint32_t oct = (r.negx ? 1u : 0u) | (r.negy ? 2u : 0u) | (r.negz ? 4u : 0u);
     r.octinv = 7u - oct;
+#if SB_FIXED_BITS
+    r.octinv4 = r.octinv << 8; // row of the permutation table
+#else
     r.octinv4 = r.octinv * 0x01010101u;
+#endif
     const float eps = 1e-20f;
     r.idir.x = 1.0f / (fabsf(d.x) > eps ? d.x : copysignf(eps, d.x));
     r.idir.y = 1.0f / (fabsf(d.y) > eps ? d.y : copysignf(eps, d.y));
@@ -291,6 +352,7 @@ struct TravStack
 struct Traversal
 {
     uint2 ngroup, tgroup;
+    uint32_t tvalid; // SB_FIXED_BITS: valid-bit word of the node the pending primitives belong to
     int sp;
 #if defined(__CUDACC__)
     uint2* sstack; // this thread's column of the block's shared-memory stack (SSTACK traversals only)
@@ -318,9 +380,6 @@ SB_HD void trav_init(Traversal& T)
 //   trav_node : if the lane has no primitives pending, visit the next node (returns false when nothing is left)
 //   trav_prim : if the lane has primitives pending, test exactly one
 // KIND 1: triangles (prims = TriRec), KIND 2: curve segments (prims = SegRec).  ANY: shadow rays.
-#ifndef SB_PREFETCH_CHILDREN
-#define SB_PREFETCH_CHILDREN 0
-#endif
 #ifndef SB_PREFETCH_NEXT_NODE
 #define SB_PREFETCH_NEXT_NODE 0
 #endif
@@ -329,12 +388,6 @@ SB_HD void trav_init(Traversal& T)
 #endif
 #ifndef SB_SIMPLE_PREFETCH
 #define SB_SIMPLE_PREFETCH 0 // next-triangle prefetch in the one-ray-per-thread closest-hit traversal (camera rays)
-#endif
-#ifndef SB_PRIM_PAIR
-#define SB_PRIM_PAIR 0 // 1: the closest-hit step tests up to two pending triangles per iteration (trav_tri_pair)
-#endif
-#ifndef SB_PIPE_NODE
-#define SB_PIPE_NODE 0 // 1: closest-hit kernel, 2: any-hit kernel too -- software-pipelined node fetch (trav_step_pipe)
 #endif
 #ifndef SB_TOP_SMEM
 #define SB_TOP_SMEM 0 // number of top-level nodes (the first K of the level-ordered array) staged in shared memory
@@ -406,90 +459,26 @@ SB_HD bool trav_node(Traversal& T, TravStack& K, const WideNode* __restrict__ no
     if (STATS)
         st->nodes++;
     const uint32_t hm = wide_node_hits<XU>(n0, n1, n2, n3, n4, ray.o, rp.idir, rp.octinv4, rp.negx, rp.negy, rp.negz, ray.tmin, ray.tmax);
-#if defined(__CUDA_ARCH__) && SB_PREFETCH_CHILDREN
-    // the hit children that will wait on the stack: pull their nodes towards the SM now (children are contiguous)
-    if (SSTACK && (hm & 0xff000000u) != 0u)
-    {
-        const uint32_t imask = n0.w >> 24;
-        uint32_t rest = hm >> 24;
-        while (rest)
-        {
-            const uint32_t b = 31u - __clz(rest);
-            rest &= ~(1u << b);
-            const uint32_t sl = b ^ (rp.octinv & 7u);
-            const uint32_t r2 = popc32(imask & ~(0xffffffffu << sl));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nodes + (n1.x + r2)));
-        }
-    }
-#endif
     T.ngroup.x = n1.x;
+#if SB_FIXED_BITS
+    T.ngroup.y = (permute_inner_hits(hm >> 24, rp.octinv4) << 24) | (n0.w >> 24);
+    T.tvalid = n1.z;
+#else
     T.ngroup.y = (hm & 0xff000000u) | (n0.w >> 24);
+#endif
     T.tgroup.x = n1.y;
     T.tgroup.y = hm & 0x00ffffffu;
     return true;
 }
 
-// ---- the two halves of trav_node, for the software-pipelined step (SB_PIPE_NODE) --------------------------------
-struct NodeRegs
+// offset, from the node's first primitive, of the pending primitive at bit `rel` of tgroup.y
+SB_HD uint32_t prim_offset(const Traversal& T, uint32_t rel)
 {
-    uint4 n0, n1, n2, n3, n4;
-};
-// pick the next node to visit (popping the stack when the current group is used up) and ISSUE its five loads;
-// the current group is consumed: its remaining hits are postponed on the stack.  False when nothing is left.
-template <bool SSTACK>
-SB_HD bool trav_select_load(Traversal& T, TravStack& K, const WideNode* __restrict__ nodes, const RayPrep& rp, NodeRegs& N)
-{
-    if (T.ngroup.y <= 0x00ffffffu)
-    {
-        if (T.sp == 0)
-            return false;
-        --T.sp;
-#if defined(__CUDA_ARCH__) && SB_SMEM_STACK
-        if (SSTACK)
-            T.ngroup = (T.sp < SB_SMEM_STACK) ? T.sstack[T.sp * kTravBlock] : SB_TSTACK(T, K)[T.sp - SB_SMEM_STACK];
-        else
+#if SB_FIXED_BITS
+    return popc32(T.tvalid & ~(0xffffffffu << rel));
+#else
+    return rel;
 #endif
-            T.ngroup = SB_TSTACK(T, K)[T.sp];
-    }
-    const uint32_t hits = T.ngroup.y;
-    const uint32_t bit = bfind32(hits);
-    T.ngroup.y &= ~(1u << bit);
-    if (T.ngroup.y > 0x00ffffffu && T.sp < kStackSize)
-    {
-#if defined(__CUDA_ARCH__) && SB_SMEM_STACK
-        if (SSTACK)
-        {
-            if (T.sp < SB_SMEM_STACK)
-                T.sstack[T.sp * kTravBlock] = T.ngroup;
-            else
-                SB_TSTACK(T, K)[T.sp - SB_SMEM_STACK] = T.ngroup;
-        }
-        else
-#endif
-            SB_TSTACK(T, K)[T.sp] = T.ngroup;
-        ++T.sp;
-    }
-    T.ngroup.y = 0u; // consumed
-    const uint32_t slot = (bit - 24u) ^ (rp.octinv & 7u);
-    const uint32_t rel = popc32(hits & ~(0xffffffffu << slot) & 0xffu);
-    const WideNode* np = nodes + (T.ngroup.x + rel);
-    N.n0 = SB_LDG4(&np->n0);
-    N.n1 = SB_LDG4(&np->n1);
-    N.n2 = SB_LDG4(&np->n2);
-    N.n3 = SB_LDG4(&np->n3);
-    N.n4 = SB_LDG4(&np->n4);
-    return true;
-}
-template <bool STATS>
-SB_HD void trav_test_node(Traversal& T, const NodeRegs& N, const Ray& ray, const RayPrep& rp, TravStats* st)
-{
-    if (STATS)
-        st->nodes++;
-    const uint32_t hm = wide_node_hits(N.n0, N.n1, N.n2, N.n3, N.n4, ray.o, rp.idir, rp.octinv4, rp.negx, rp.negy, rp.negz, ray.tmin, ray.tmax);
-    T.ngroup.x = N.n1.x;
-    T.ngroup.y = (hm & 0xff000000u) | (N.n0.w >> 24);
-    T.tgroup.x = N.n1.y;
-    T.tgroup.y = hm & 0x00ffffffu;
 }
 
 // tests one pending primitive; returns true if an any-hit query is satisfied (ANY only)
@@ -501,7 +490,7 @@ SB_HD bool trav_prim(Traversal& T, const void* __restrict__ prims, uint32_t rayM
 {
     const uint32_t rel = bfind32(T.tgroup.y);
     T.tgroup.y &= ~(1u << rel);
-    const uint32_t pi = T.tgroup.x + rel;
+    const uint32_t pi = T.tgroup.x + prim_offset(T, rel);
     if (KIND == 1)
     {
         const TriRec* tr = reinterpret_cast<const TriRec*>(prims) + pi;
@@ -509,7 +498,7 @@ SB_HD bool trav_prim(Traversal& T, const void* __restrict__ prims, uint32_t rayM
 #if defined(__CUDA_ARCH__)
         if (PF && T.tgroup.y != 0u)
         {
-            const TriRec* nx = reinterpret_cast<const TriRec*>(prims) + (T.tgroup.x + bfind32(T.tgroup.y));
+            const TriRec* nx = reinterpret_cast<const TriRec*>(prims) + (T.tgroup.x + prim_offset(T, bfind32(T.tgroup.y)));
             asm volatile("prefetch.global.L1 [%0];" ::"l"(&nx->v0));
             asm volatile("prefetch.global.L1 [%0];" ::"l"(&nx->e2));
         }
@@ -545,7 +534,7 @@ SB_HD bool trav_prim(Traversal& T, const void* __restrict__ prims, uint32_t rayM
 #if defined(__CUDA_ARCH__)
         if (PF && T.tgroup.y != 0u)
         {
-            const SegRec* nx = reinterpret_cast<const SegRec*>(prims) + (T.tgroup.x + bfind32(T.tgroup.y));
+            const SegRec* nx = reinterpret_cast<const SegRec*>(prims) + (T.tgroup.x + prim_offset(T, bfind32(T.tgroup.y)));
             asm volatile("prefetch.global.L1 [%0];" ::"l"(&nx->q[0]));
             asm volatile("prefetch.global.L1 [%0];" ::"l"(&nx->q[2]));
         }
@@ -569,54 +558,6 @@ SB_HD bool trav_prim(Traversal& T, const void* __restrict__ prims, uint32_t rayM
             hit.kind = 2u;
             hit.gid = pi;
             ray.tmax = t;
-        }
-    }
-    return false;
-}
-
-// Two pending triangles per call, their six loads issued together (a leaf slot holds up to three triangles; the lane
-// leaves its "primitive drain" in half the iterations and the two memory latencies overlap).  SB_PRIM_PAIR.
-template <bool ANY, bool STATS>
-SB_HD bool trav_tri_pair(Traversal& T, const void* __restrict__ prims, uint32_t rayMask, Ray& ray, HitRec& hit, TravStats* st)
-{
-    const uint32_t rel0 = bfind32(T.tgroup.y);
-    T.tgroup.y &= ~(1u << rel0);
-    const bool two = T.tgroup.y != 0u;
-    const uint32_t rel1 = two ? bfind32(T.tgroup.y) : rel0;
-    T.tgroup.y &= ~(1u << rel1);
-    const TriRec* t0 = reinterpret_cast<const TriRec*>(prims) + (T.tgroup.x + rel0);
-    const TriRec* t1 = reinterpret_cast<const TriRec*>(prims) + (T.tgroup.x + rel1);
-    const float4 a0 = SB_LDGF4(&t0->v0), b0 = SB_LDGF4(&t0->e1), c0 = SB_LDGF4(&t0->e2);
-    const float4 a1 = SB_LDGF4(&t1->v0), b1 = SB_LDGF4(&t1->e1), c1 = SB_LDGF4(&t1->e2);
-    if (STATS)
-        st->tris += two ? 2u : 1u;
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-    {
-        if (k == 1 && !two)
-            break;
-        const float4 a = k ? a1 : a0, b = k ? b1 : b0, c = k ? c1 : c0;
-        const uint32_t instMask = f2u(b.w);
-        if ((instMask >> 28) & rayMask)
-        {
-            float t, u, v;
-            if (intersect_tri(mk3(a), mk3(b), mk3(c), ray.o, ray.d, ray.tmin, ray.tmax, t, u, v))
-            {
-                if (ANY)
-                    return true;
-                const uint32_t gid = f2u(c.w);
-                if (t < ray.tmax || hit.kind != 1u || gid < hit.gid)
-                {
-                    hit.t = t;
-                    hit.u = u;
-                    hit.v = v;
-                    hit.prim = f2u(a.w);
-                    hit.inst = instMask & 0x0fffffffu;
-                    hit.kind = 1u;
-                    hit.gid = gid;
-                    ray.tmax = t;
-                }
-            }
         }
     }
     return false;
@@ -647,66 +588,12 @@ SB_HD bool trav_step(Traversal& T, TravStack& K, const WideNode* __restrict__ no
             asm volatile("prefetch.global.L1 [%0];" ::"l"(&nx->n4));
         }
 #endif
-#if SB_PRIM_PAIR
-        if (KIND == 1 ? trav_tri_pair<ANY, STATS>(T, prims, rayMask, ray, hit, st) : trav_prim<KIND, ANY, STATS>(T, prims, rayMask, ray, hit, st))
-#else
         if (trav_prim<KIND, ANY, STATS, PF>(T, prims, rayMask, ray, hit, st))
-#endif
         {
             anyHit = true;
             return false;
         }
     }
-    return true;
-}
-
-// Software-pipelined form of trav_step: the loads of the NEXT node are issued before the primitive test of the current
-// one, so that the two memory latencies of an iteration overlap (the choice of the next node does not depend on the
-// outcome of the primitive test; a closer hit only makes its box test stricter when it is finally run).
-// `pn` holds the node in flight, `pnValid` says whether there is one.
-template <int KIND, bool ANY, bool STATS, bool SSTACK = false>
-SB_HD bool trav_step_pipe(Traversal& T, TravStack& K, const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask,
-                          Ray& ray, const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st, NodeRegs& pn, bool& pnValid)
-{
-    if (T.tgroup.y == 0u)
-    {
-        if (!pnValid && !trav_select_load<SSTACK>(T, K, nodes, rp, pn))
-            return false;
-        trav_test_node<STATS>(T, pn, ray, rp, st);
-        pnValid = false;
-    }
-    if (!pnValid)
-        pnValid = trav_select_load<SSTACK>(T, K, nodes, rp, pn);
-    if (T.tgroup.y != 0u)
-    {
-        if (trav_prim<KIND, ANY, STATS>(T, prims, rayMask, ray, hit, st))
-        {
-            anyHit = true;
-            return false;
-        }
-    }
-    return pnValid || T.tgroup.y != 0u;
-}
-// ... and of trav_step_unit (any-hit rays)
-template <int KIND, bool ANY, bool STATS, bool SSTACK = false>
-SB_HD bool trav_step_unit_pipe(Traversal& T, TravStack& K, const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask,
-                               Ray& ray, const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st, NodeRegs& pn, bool& pnValid)
-{
-    if (T.tgroup.y != 0u)
-    {
-        if (!pnValid)
-            pnValid = trav_select_load<SSTACK>(T, K, nodes, rp, pn);
-        if (trav_prim<KIND, ANY, STATS>(T, prims, rayMask, ray, hit, st))
-        {
-            anyHit = true;
-            return false;
-        }
-        return pnValid || T.tgroup.y != 0u;
-    }
-    if (!pnValid && !trav_select_load<SSTACK>(T, K, nodes, rp, pn))
-        return false;
-    trav_test_node<STATS>(T, pn, ray, rp, st);
-    pnValid = false;
     return true;
 }
 

@@ -163,6 +163,20 @@ void emul_bvh_stats(const emul_scene* e, uint64_t* out)
         uint32_t innerSeen = 0;
         for (int j = 0; j < 8; ++j)
         {
+#if SB_FIXED_BITS
+            // valid word: slot j owns bits 3j..3j+2 (leaf, unary primitive count) or bit 24+j (inner node)
+            const uint32_t valid = n.n1.z;
+            const bool inner = ((valid >> (24 + j)) & 1u) != 0u;
+            const uint32_t childBits = (valid >> (3 * j)) & 7u;
+            const uint32_t bitIndex = inner ? 24u : uint32_t(__builtin_popcount(valid & ((1u << (3 * j)) - 1u)));
+            if (!inner && childBits == 0u)
+            {
+                out[6]++;
+                continue;
+            }
+            if (inner && childBits != 0u)
+                out[4] += 1u << 21; // a slot cannot be both
+#else
             const uint32_t meta = ((j < 4 ? n.n1.z : n.n1.w) >> (8 * (j & 3))) & 0xffu;
             if (meta == 0u)
             {
@@ -170,6 +184,7 @@ void emul_bvh_stats(const emul_scene* e, uint64_t* out)
                 continue;
             }
             const uint32_t bitIndex = meta & 31u, childBits = meta >> 5;
+#endif
             if (bitIndex >= 24u)
             {
                 out[1]++;
