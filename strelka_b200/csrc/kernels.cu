@@ -284,11 +284,12 @@ __device__ __forceinline__ void stage_top_nodes(uint4* dst, const WideNode* node
 #ifndef SB_EXTEND_HIT_SMEM
 #define SB_EXTEND_HIT_SMEM 0
 #endif
-// share of the child-box byte conversions done on the XU pipe (wide_node_hits: 16 * pair mask + children per half);
-// measured per kernel (profiles/r02_ab_experiments.txt, r2t..r2v): near-xy + z pairs of two children per half for the
-// closest-hit loop, the z pair of every child for the any-hit loop and the one-ray-per-thread kernels (SB_SIMPLE_XU)
+// how the child-box bytes become floats (wide_node_hits<XU>), measured per kernel (profiles/r02_ab_experiments.txt,
+// r2t..r2x): fp16-pair unpack with the z planes of two children per half on the XU pipe for the closest-hit loop and the
+// one-ray-per-thread kernels (SB_SIMPLE_XU); byte permutes with the z pair of every child on the XU pipe for the any-hit
+// loop (the fp16 form costs it 3-7 % on the 2 M-triangle scene)
 #ifndef SB_EXTEND_XU
-#define SB_EXTEND_XU (16 * 5 + 2)
+#define SB_EXTEND_XU (kXuHalfUnpack | 0x24)
 #endif
 #ifndef SB_SHADOW_XU
 #define SB_SHADOW_XU (16 * 4 + 4)

@@ -118,8 +118,21 @@ SB_HD float byte_to_float(uint32_t w, int j)
 #ifndef SB_MAGIC_CONST
 #define SB_MAGIC_CONST 1
 #endif
+#ifndef SB_HALF_UNPACK
+#define SB_HALF_UNPACK 1 // two bytes per byte-permute through an fp16 pair (byte_pair_to_float); needs SB_FIXED_BITS
+#endif
+// XU template argument of wide_node_hits: how the quantised child planes become floats, chosen per kernel.
+//   without kXuHalfUnpack: 16 * pairs + n -- PRMT + FADD2 per byte, except the pairs `pairs` (1: near xy, 2: far xy,
+//     4: z) of the first n children of each half, which go through I2F.U8 on the XU pipe
+//   with kXuHalfUnpack: fp16-pair unpack (byte_pair_to_float), except plane word i (0..2 near x y z, 3..5 far x y z) of
+//     children 0,1 (bit i) / children 2,3 (bit 8 + i) of each half, which go through I2F.U8
+constexpr int kXuHalfUnpack = 0x10000;
 #if SB_MAGIC_CONST && defined(__CUDACC__)
 static __constant__ uint32_t c_byteMagic = 0x4B000000u;
+static __constant__ uint32_t c_halfMagic = 0x64646464u; // SB_HALF_UNPACK
+// FHADD reads its fp32 addend from a vector register only; as a literal or a constant-bank value ptxas re-materialises
+// it per use (40 moves per node visit).  Loaded from (mutable) global memory once per ray it stays in one register.
+static __device__ float g_halfBias = -1024.0f;
 #endif
 #if defined(__CUDA_ARCH__)
 // Packed fp32 arithmetic of sm_100 (FADD2 / FFMA2: two IEEE fp32 operations per issued instruction, each
@@ -207,11 +220,25 @@ SB_HD uint32_t permute_inner_hits(uint32_t inner, uint32_t octinv8)
 }
 #endif
 
+#if defined(__CUDA_ARCH__)
+// SB_HALF_UNPACK: bytes j and j+1 of w -> two floats through ONE byte-permute: the permute builds the fp16 pair
+// (1024 + b_j, 1024 + b_j+1) (0x64 in the high bytes: 1024 has an ulp of 1), and the mixed-precision add of sm_100
+// (add.f32.f16 -> FHADD, fma pipe, reads either half of a register) removes the 1024 in fp32.  Exact like byte_magic,
+// with half the ALU-pipe instructions.
+__device__ __forceinline__ void byte_pair_to_float(uint32_t w, int j, float bias, float& q0, float& q1)
+{
+    const uint32_t h = __byte_perm(w, c_halfMagic, j == 0 ? 0x4140u : 0x4342u);
+    asm("{ .reg .f16 l, h; mov.b32 {l, h}, %2; add.rn.f32.f16 %0, l, %3; add.rn.f32.f16 %1, h, %3; }"
+        : "=f"(q0), "=f"(q1)
+        : "r"(h), "f"(bias));
+}
+#endif
+
 // Ray/child-box tests of one wide node -> 32-bit hit mask: bits 24..31 inner children in traversal
 // priority (highest first), bits 0..23 leaf primitives relative to primBase.
 template <int XU = 0>
 SB_HD uint32_t wide_node_hits(const uint4& n0, const uint4& n1, const uint4& n2, const uint4& n3, const uint4& n4, const float3& o,
-                              const float3& idir, uint32_t octinv4, bool negx, bool negy, bool negz, float tmin, float tmax)
+                              const float3& idir, uint32_t octinv4, bool negx, bool negy, bool negz, float tmin, float tmax, float halfBias = -1024.0f)
 {
     const float3 p = mk3(u2f(n0.x), u2f(n0.y), u2f(n0.z));
     // child plane distance t = q * (2^e * idir) + (p - o) * idir
@@ -241,6 +268,46 @@ SB_HD uint32_t wide_node_hits(const uint4& n0, const uint4& n1, const uint4& n2,
         const uint32_t nearx = negx ? qhix : qlox, farx = negx ? qlox : qhix;
         const uint32_t neary = negy ? qhiy : qloy, fary = negy ? qloy : qhiy;
         const uint32_t nearz = negz ? qhiz : qloz, farz = negz ? qloz : qhiz;
+#if defined(__CUDA_ARCH__) && SB_F32X2 && SB_HALF_UNPACK && SB_FIXED_BITS
+        if (XU & kXuHalfUnpack)
+        {
+            // two children per step.  XU: bit i (children 0,1) / bit 8 + i (children 2,3) of each half sends plane word i
+            // (0..2 near x y z, 3..5 far x y z) through I2F.U8 on the XU pipe instead
+#pragma unroll
+            for (int jp = 0; jp < 4; jp += 2)
+            {
+                float t0x[2], t0y[2], t0z[2], t1x[2], t1y[2], t1z[2];
+#define SB_SLAB2(idx, w, a, b, r)                                                                                          \
+        {                                                                                                                  \
+            float q0, q1;                                                                                                  \
+            if ((XU >> (idx + 4 * jp)) & 1)                                                                                \
+            {                                                                                                              \
+                q0 = float(byte_of(w, jp));                                                                                \
+                q1 = float(byte_of(w, jp + 1));                                                                            \
+            }                                                                                                              \
+            else                                                                                                           \
+                byte_pair_to_float(w, jp, halfBias, q0, q1);                                                               \
+            f2_unpack(f2_fma(f2_pack(q0, q1), f2_pack(a, a), f2_pack(b, b)), r[0], r[1]);                                  \
+        }
+                SB_SLAB2(0, nearx, ax, bx, t0x)
+                SB_SLAB2(1, neary, ay, by, t0y)
+                SB_SLAB2(2, nearz, az, bz, t0z)
+                SB_SLAB2(3, farx, ax, bx, t1x)
+                SB_SLAB2(4, fary, ay, by, t1y)
+                SB_SLAB2(5, farz, az, bz, t1z)
+#undef SB_SLAB2
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                {
+                    const float cmin = fmaxf(fmaxf(t0x[k], t0y[k]), fmaxf(t0z[k], tmin));
+                    const float cmax = fminf(fminf(t1x[k], t1y[k]), fminf(t1z[k], tmax)) * 1.0000004f;
+                    if (cmin <= cmax)
+                        hitmask |= (7u << (3 * (4 * half + jp + k))) | (1u << (24 + 4 * half + jp + k));
+                }
+            }
+            continue;
+        }
+#endif
 #pragma unroll
         for (int j = 0; j < 4; ++j)
         {
@@ -313,6 +380,7 @@ struct RayPrep
     uint32_t octinv4;
     uint32_t octinv;
     bool negx, negy, negz;
+    float halfBias; // -1024 in a register the compiler cannot re-materialise (byte_pair_to_float)
 };
 SB_HD RayPrep prepare_ray(const float3& d)
 {
@@ -322,6 +390,11 @@ SB_HD RayPrep prepare_ray(const float3& d)
     r.negz = d.z < 0.0f;
     const uint32_t oct = (r.negx ? 1u : 0u) | (r.negy ? 2u : 0u) | (r.negz ? 4u : 0u);
     r.octinv = 7u - oct;
+#if defined(__CUDA_ARCH__)
+    r.halfBias = g_halfBias;
+#else
+    r.halfBias = -1024.0f;
+#endif
 #if SB_FIXED_BITS
     r.octinv4 = r.octinv << 8; // row of the permutation table
 #else
@@ -384,7 +457,7 @@ SB_HD void trav_init(Traversal& T)
 #define SB_PREFETCH_NEXT_NODE 0
 #endif
 #ifndef SB_SIMPLE_XU
-#define SB_SIMPLE_XU (16 * 4 + 4) // XU share of the byte conversions (wide_node_hits) in the one-ray-per-thread traversals
+#define SB_SIMPLE_XU (kXuHalfUnpack | 0x24) // conversion mix of the byte conversions (wide_node_hits) in the one-ray-per-thread traversals
 #endif
 #ifndef SB_SIMPLE_PREFETCH
 #define SB_SIMPLE_PREFETCH 0 // next-triangle prefetch in the one-ray-per-thread closest-hit traversal (camera rays)
@@ -458,7 +531,7 @@ SB_HD bool trav_node(Traversal& T, TravStack& K, const WideNode* __restrict__ no
     }
     if (STATS)
         st->nodes++;
-    const uint32_t hm = wide_node_hits<XU>(n0, n1, n2, n3, n4, ray.o, rp.idir, rp.octinv4, rp.negx, rp.negy, rp.negz, ray.tmin, ray.tmax);
+    const uint32_t hm = wide_node_hits<XU>(n0, n1, n2, n3, n4, ray.o, rp.idir, rp.octinv4, rp.negx, rp.negy, rp.negz, ray.tmin, ray.tmax, rp.halfBias);
     T.ngroup.x = n1.x;
 #if SB_FIXED_BITS
     T.ngroup.y = (permute_inner_hits(hm >> 24, rp.octinv4) << 24) | (n0.w >> 24);
