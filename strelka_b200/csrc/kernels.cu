@@ -275,6 +275,107 @@ __device__ __forceinline__ void stage_top_nodes(uint4* dst, const WideNode* node
 #endif
 }
 
+
+// ---- deferred primitive tests ---------------------------------------------------------------------------------
+// In the plain loop a lane tests a primitive as soon as a node visit queues one, so primitive tests run with whatever
+// few lanes happen to hold one (ncu: 4.7 of 32 lanes in the curve test of the hair scene, ~8 in the triangle test) while
+// the rest of the warp waits.  Here a lane may park up to D leaf groups in shared memory and keep visiting nodes;
+// the warp runs ONE primitive test per lane with pending work when at least THRESH lanes have some, or when a
+// lane cannot go on otherwise (its queue is full, or it has no nodes left).  Results do not depend on the order of the
+// tests (closest hit: ties break on the primitive id; any hit: a boolean).
+// Depth of the parking queue and vote threshold per kernel family, measured (profiles/r02_ab_experiments.txt, r2y/r2z):
+// curve scenes gain 5 % (closest hit) and 15 % (any hit); triangle-only scenes 1-2 % for closest-hit rays and nothing
+// for any-hit rays.  0 = the plain loop.  (Prefetching the first parked primitive at the node visit: no gain on the
+// hair scene, +35 % closest-hit time on the 2 M-triangle scene.)
+#ifndef SB_DEFER_CURVES
+#define SB_DEFER_CURVES 3
+#endif
+#ifndef SB_DEFER_CURVES_THRESH
+#define SB_DEFER_CURVES_THRESH 16
+#endif
+#ifndef SB_DEFER_TRIS
+#define SB_DEFER_TRIS 2
+#endif
+#ifndef SB_DEFER_TRIS_SHADOW
+#define SB_DEFER_TRIS_SHADOW 0
+#endif
+#ifndef SB_DEFER_TRIS_THRESH
+#define SB_DEFER_TRIS_THRESH 12
+#endif
+#ifndef SB_DEFER_PREFETCH
+#define SB_DEFER_PREFETCH 0
+#endif
+// all 32 lanes call this (it votes); returns whether the lane's traversal of the current BVH goes on
+template <bool ANY, bool STATS, bool CURVES, bool PF, int XU, int D, int THRESH>
+__device__ __forceinline__ bool trav_iter_defer(bool active, int phase, const SceneDev& S, Traversal& T, TravStack& K, uint32_t* dq, int& dc,
+                                                uint32_t rayMask, Ray& ray, const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st)
+{
+    const bool curvePhase = CURVES && phase == 1;
+    bool pend = false, stuck = false, haveNodes = false;
+    if (active)
+    {
+        haveNodes = T.ngroup.y > 0x00ffffffu || T.sp > 0;
+        if (haveNodes && (T.tgroup.y == 0u || dc < D))
+        {
+            if (T.tgroup.y != 0u)
+            {
+                uint32_t* e = dq + dc * 3 * kBlock;
+                e[0] = T.tgroup.x;
+                e[kBlock] = T.tgroup.y;
+                e[2 * kBlock] = T.tvalid;
+                ++dc;
+                T.tgroup.y = 0u;
+            }
+            trav_node<STATS, (SB_SMEM_STACK > 0), XU>(T, K, curvePhase ? S.segNodes : S.triNodes, ray, rp, st);
+            haveNodes = T.ngroup.y > 0x00ffffffu || T.sp > 0;
+#if SB_DEFER_PREFETCH
+            if (T.tgroup.y != 0u)
+            {
+                const uint32_t pi = T.tgroup.x + prim_offset(T, bfind32(T.tgroup.y));
+                if (curvePhase)
+                {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(&S.segs[pi].q[0]));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(&S.segs[pi].q[2]));
+                }
+                else
+                {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(&S.tris[pi].v0));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(&S.tris[pi].e2));
+                }
+            }
+#endif
+        }
+        pend = T.tgroup.y != 0u || dc > 0;
+        stuck = pend && (!haveNodes || (T.tgroup.y != 0u && dc == D));
+    }
+    const unsigned waiting = __ballot_sync(0xffffffffu, pend);
+    const bool force = __any_sync(0xffffffffu, stuck);
+    if (force || __popc(waiting) >= THRESH)
+    {
+        if (pend)
+        {
+            if (T.tgroup.y == 0u)
+            {
+                --dc;
+                const uint32_t* e = dq + dc * 3 * kBlock;
+                T.tgroup.x = e[0];
+                T.tgroup.y = e[kBlock];
+                T.tvalid = e[2 * kBlock];
+            }
+            const bool found = curvePhase ? trav_prim<2, ANY, STATS, false>(T, S.segs, rayMask, ray, hit, st)
+                                          : trav_prim<1, ANY, STATS, PF>(T, S.tris, rayMask, ray, hit, st);
+            if (found)
+            {
+                anyHit = true;
+                dc = 0;
+                T.tgroup.y = 0u;
+                return false;
+            }
+        }
+    }
+    return active && (haveNodes || T.tgroup.y != 0u || dc > 0);
+}
+
 #ifndef SB_EXTEND_MIN_BLOCKS
 #define SB_EXTEND_MIN_BLOCKS 8
 #endif
@@ -320,6 +421,10 @@ __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FramePa
 #endif
     Traversal T;
     TravStack K;
+    constexpr int kDeferDepth = CURVES ? SB_DEFER_CURVES : SB_DEFER_TRIS, kDeferThresh = CURVES ? SB_DEFER_CURVES_THRESH : SB_DEFER_TRIS_THRESH;
+    __shared__ uint32_t s_defer[kDeferDepth > 0 ? kDeferDepth * 3 * kBlock : 1];
+    uint32_t* dq = s_defer + threadIdx.x;
+    int dc = 0;
 #if SB_SMEM_STACK
     static_assert(kTravBlock == kBlock, "shared-memory traversal stack stride");
     __shared__ uint2 s_stack[SB_SMEM_STACK * kBlock];
@@ -360,13 +465,18 @@ __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FramePa
             break;
         for (;;)
         {
+            bool more = false, anyHit = false;
+            if (kDeferDepth > 0)
+                more = trav_iter_defer<false, STATS, CURVES, (SB_EXTEND_PREFETCH != 0), SB_EXTEND_XU, kDeferDepth, kDeferThresh>(active, phase, S, T, K, dq, dc, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
             if (active)
             {
-                bool more = false, anyHit = false;
                 // step shape: node visit + one primitive test per iteration.  Measured on the 2 M / 10 M-triangle and hair
                 // scenes against one unit per iteration (best for the any-hit kernel) and node + all its primitives
                 // (+7 % here; best for the one-ray-per-thread kernels, which have no refill ballots).
-                if (phase == 0)
+                if (kDeferDepth > 0)
+                {
+                }
+                else if (phase == 0)
                     more = trav_step<1, false, STATS, (SB_SMEM_STACK > 0), (SB_EXTEND_PREFETCH != 0), SB_EXTEND_XU>(T, K, S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, anyHit, &st, topTri);
                 else if (CURVES && phase == 1)
                     more = trav_step<2, false, STATS, (SB_SMEM_STACK > 0), (SB_CURVE_PREFETCH != 0), SB_EXTEND_XU>(T, K, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st, topSeg);
@@ -422,6 +532,10 @@ __global__ void __launch_bounds__(kBlock, SB_SHADOW_MIN_BLOCKS) k_shadow(SceneDe
     HitRec hit;
     Traversal T;
     TravStack K;
+    constexpr int kDeferDepth = CURVES ? SB_DEFER_CURVES : SB_DEFER_TRIS_SHADOW, kDeferThresh = CURVES ? SB_DEFER_CURVES_THRESH : SB_DEFER_TRIS_THRESH;
+    __shared__ uint32_t s_defer[kDeferDepth > 0 ? kDeferDepth * 3 * kBlock : 1];
+    uint32_t* dq = s_defer + threadIdx.x;
+    int dc = 0;
 #if SB_SMEM_STACK
     static_assert(kTravBlock == kBlock, "shared-memory traversal stack stride");
     __shared__ uint2 s_stack[SB_SMEM_STACK * kBlock];
@@ -461,12 +575,17 @@ __global__ void __launch_bounds__(kBlock, SB_SHADOW_MIN_BLOCKS) k_shadow(SceneDe
             break;
         for (;;)
         {
+            bool more = false, occluded = false;
+            if (kDeferDepth > 0)
+                more = trav_iter_defer<true, STATS, CURVES, PF, SB_SHADOW_XU, kDeferDepth, kDeferThresh>(active, phase, S, T, K, dq, dc, kRayMaskShadow, ray, rp, hit, occluded, &st);
             if (active)
             {
-                bool more = false, occluded = false;
                 // step shape: ONE unit (a primitive test if one is pending, else a node visit) per iteration: measured
                 // 1.5x faster for any-hit rays than node + primitive (profiles/r01_b_*)
-                if (phase == 0)
+                if (kDeferDepth > 0)
+                {
+                }
+                else if (phase == 0)
                     more = trav_step_unit<1, true, STATS, (SB_SMEM_STACK > 0), PF, SB_SHADOW_XU>(T, K, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st, topTri);
                 else if (CURVES && phase == 1)
                     more = trav_step_unit<2, true, STATS, (SB_SMEM_STACK > 0), (SB_CURVE_PREFETCH != 0), SB_SHADOW_XU>(T, K, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st, topSeg);
