@@ -8,7 +8,8 @@
 // RenderPass.cpp:252-257) and ONE wide BVH per primitive kind is built over all of it, so traversal
 // never transforms rays and never chases an instance indirection.
 //
-// Node (80 B = 5 x 16 B, fetched with 128-bit loads):
+// Node (80 B of content = 5 x 16 B; stored at a 96-byte stride, 32-byte aligned, and fetched with three 256-bit loads
+// when SB_NODE96, else packed and fetched with five 128-bit loads):
 //   n0 = { p.x, p.y, p.z, ex | ey<<8 | ez<<16 | imask<<24 }      quantisation frame + inner-node mask
 //   n1 = { childBase, primBase, valid, 0 }      (SB_FIXED_BITS = 0: { childBase, primBase, meta[0..3], meta[4..7] })
 //   n2 = { qlo.x[0..3], qlo.x[4..7], qlo.y[0..3], qlo.y[4..7] }
@@ -85,11 +86,25 @@ SB_HD void node_set_box(Bvh2Node& n, const Aabb& b)
     n.hi[2] = b.hi.z;
 }
 
+// SB_NODE96: the 80-byte node padded to 96 bytes and 32-byte aligned, so that a visit fetches it with three 256-bit
+// loads (LDG.E.ENL2.256, sm_100) instead of five 128-bit ones: with 32 divergent lanes every load instruction is 32 L1 tag
+// look-ups, and the L1 data path is the busiest unit of the traversal kernels.
+#ifndef SB_NODE96
+#define SB_NODE96 1
+#endif
+#if SB_NODE96
+struct alignas(32) WideNode
+{
+    uint4 n0, n1, n2, n3, n4, pad;
+};
+static_assert(sizeof(WideNode) == 96, "padded CWBVH node must be 96 bytes");
+#else
 struct WideNode
 {
     uint4 n0, n1, n2, n3, n4;
 };
 static_assert(sizeof(WideNode) == 80, "CWBVH node must be 80 bytes");
+#endif
 
 // ---- 63-bit Morton code of a point in the unit cube ------------------------------------------------
 SB_HD uint64_t spread21(uint64_t x)

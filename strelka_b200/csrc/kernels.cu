@@ -430,6 +430,15 @@ __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FramePa
     __shared__ uint2 s_stack[SB_SMEM_STACK * kBlock];
     T.sstack = s_stack + threadIdx.x;
 #endif
+#if SB_PERM_SMEM && SB_FIXED_BITS
+    __shared__ uint32_t s_perm[512];
+    for (uint32_t i = threadIdx.x; i < 512u; i += kBlock)
+        s_perm[i] = reinterpret_cast<const uint32_t*>(g_octantPerm.v)[i];
+    __syncthreads();
+    const uint32_t permBase = uint32_t(__cvta_generic_to_shared(s_perm));
+#else
+    const uint32_t permBase = 0u;
+#endif
 #if SB_TOP_SMEM
     __shared__ uint4 s_top[(CURVES ? 2 : 1) * SB_TOP_SMEM * 5];
     stage_top_nodes(s_top, S.triNodes, S.numTriNodes);
@@ -453,7 +462,7 @@ __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FramePa
             ray.d = mk3(rd);
             ray.tmin = P.materialTmin;
             ray.tmax = 1e16f;
-            rp = prepare_ray(ray.d);
+            rp = prepare_ray(ray.d, permBase);
             hit.t = hit.u = hit.v = 0.0f;
             hit.prim = hit.inst = hit.kind = 0u;
             hit.gid = 0xffffffffu;
@@ -541,6 +550,15 @@ __global__ void __launch_bounds__(kBlock, SB_SHADOW_MIN_BLOCKS) k_shadow(SceneDe
     __shared__ uint2 s_stack[SB_SMEM_STACK * kBlock];
     T.sstack = s_stack + threadIdx.x;
 #endif
+#if SB_PERM_SMEM && SB_FIXED_BITS
+    __shared__ uint32_t s_perm[512];
+    for (uint32_t i = threadIdx.x; i < 512u; i += kBlock)
+        s_perm[i] = reinterpret_cast<const uint32_t*>(g_octantPerm.v)[i];
+    __syncthreads();
+    const uint32_t permBase = uint32_t(__cvta_generic_to_shared(s_perm));
+#else
+    const uint32_t permBase = 0u;
+#endif
 #if SB_TOP_SMEM
     __shared__ uint4 s_top[(CURVES ? 2 : 1) * SB_TOP_SMEM * 5];
     stage_top_nodes(s_top, S.triNodes, S.numTriNodes);
@@ -564,7 +582,7 @@ __global__ void __launch_bounds__(kBlock, SB_SHADOW_MIN_BLOCKS) k_shadow(SceneDe
             ray.tmin = so.w;
             ray.d = mk3(sd);
             ray.tmax = sd.w;
-            rp = prepare_ray(ray.d);
+            rp = prepare_ray(ray.d, permBase);
             hit.kind = 0u;
             hit.gid = 0xffffffffu;
             trav_init(T);

@@ -204,10 +204,21 @@ struct OctantPermLut
 #if defined(__CUDACC__)
 static __device__ const OctantPermLut g_octantPerm = OctantPermLut();
 #endif
-// inner: hit inner children by slot (8 bits); octinv8 = octinv << 8
+// inner: hit inner children by slot (8 bits); octinv8 = octinv << 8 (+ the shared-memory address of a copy of the
+// table when SMEM: the persistent kernels stage one per CTA, SB_PERM_SMEM)
+#ifndef SB_PERM_SMEM
+#define SB_PERM_SMEM 1
+#endif
+template <bool SMEM = false>
 SB_HD uint32_t permute_inner_hits(uint32_t inner, uint32_t octinv8)
 {
 #if defined(__CUDA_ARCH__)
+    if (SMEM)
+    {
+        uint32_t v;
+        asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(octinv8 + inner));
+        return v;
+    }
     return __ldg(&g_octantPerm.v[octinv8 | inner]);
 #else
     const uint32_t o = octinv8 >> 8;
@@ -382,7 +393,7 @@ struct RayPrep
     bool negx, negy, negz;
     float halfBias; // -1024 in a register the compiler cannot re-materialise (byte_pair_to_float)
 };
-SB_HD RayPrep prepare_ray(const float3& d)
+SB_HD RayPrep prepare_ray(const float3& d, uint32_t permLutBase = 0u)
 {
     RayPrep r;
     r.negx = d.x < 0.0f;
@@ -396,7 +407,7 @@ SB_HD RayPrep prepare_ray(const float3& d)
     r.halfBias = -1024.0f;
 #endif
 #if SB_FIXED_BITS
-    r.octinv4 = r.octinv << 8; // row of the permutation table
+    r.octinv4 = permLutBase + (r.octinv << 8); // row of the permutation table
 #else
     r.octinv4 = r.octinv * 0x01010101u;
 #endif
@@ -523,18 +534,31 @@ SB_HD bool trav_node(Traversal& T, TravStack& K, const WideNode* __restrict__ no
     else
 #endif
     {
+#if defined(__CUDA_ARCH__) && SB_NODE96
+        uint4 unused;
+        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(n0.x), "=r"(n0.y), "=r"(n0.z), "=r"(n0.w), "=r"(n1.x), "=r"(n1.y), "=r"(n1.z), "=r"(n1.w)
+                     : "l"(&np->n0));
+        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(n2.x), "=r"(n2.y), "=r"(n2.z), "=r"(n2.w), "=r"(n3.x), "=r"(n3.y), "=r"(n3.z), "=r"(n3.w)
+                     : "l"(&np->n2));
+        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(n4.x), "=r"(n4.y), "=r"(n4.z), "=r"(n4.w), "=r"(unused.x), "=r"(unused.y), "=r"(unused.z), "=r"(unused.w)
+                     : "l"(&np->n4));
+#else
         n0 = SB_LDG4(&np->n0);
         n1 = SB_LDG4(&np->n1);
         n2 = SB_LDG4(&np->n2);
         n3 = SB_LDG4(&np->n3);
         n4 = SB_LDG4(&np->n4);
+#endif
     }
     if (STATS)
         st->nodes++;
     const uint32_t hm = wide_node_hits<XU>(n0, n1, n2, n3, n4, ray.o, rp.idir, rp.octinv4, rp.negx, rp.negy, rp.negz, ray.tmin, ray.tmax, rp.halfBias);
     T.ngroup.x = n1.x;
 #if SB_FIXED_BITS
-    T.ngroup.y = (permute_inner_hits(hm >> 24, rp.octinv4) << 24) | (n0.w >> 24);
+    T.ngroup.y = (permute_inner_hits<(SSTACK && SB_PERM_SMEM != 0)>(hm >> 24, rp.octinv4) << 24) | (n0.w >> 24);
     T.tvalid = n1.z;
 #else
     T.ngroup.y = (hm & 0xff000000u) | (n0.w >> 24);

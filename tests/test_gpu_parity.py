@@ -321,3 +321,37 @@ def test_raw_camera_matrices_reset_only_on_change(gpu_render):
     assert r._lib.sb_subframe_index(r._ctx) == 0
     r._last_view = None  # hand the camera back to the scene for the tests that follow
     buf.destroy()
+
+
+def test_buffer_resize_restarts_accumulation_like_reference(gpu_render):
+    """the viewer resizes the output buffer in place (OptixBuffer.cpp:20-35); the next render() sees a new resolution,
+    reallocates the accumulation buffers and restarts at subframe 0 (OptixRender.cpp:827-872, 910-934).  The resized
+    frame must equal a fresh render at that size, bit for bit, and going back to the first size must do the same."""
+    s, st, _ = make_cornell(96, 64, 8)
+    fresh_small = _render(gpu_render, s, st, 64, 48, 3, batched=False)
+    fresh_large = _render(gpu_render, s, st, 96, 64, 2, batched=False)
+    r = gpu_render
+    r.setScene(s)
+    r.setSharedContext(SharedContext(mSettingsManager=st))
+    r._last_settings = None
+    r.reset_accumulation()
+    buf = r.createBuffer(BufferDesc(64, 48, BufferFormat.FLOAT4))
+    for _ in range(3):
+        r.render(buf)
+    assert r.getSharedContext().mSubframeIndex == 3
+    assert np.array_equal(buf.map().copy(), fresh_small)
+    buf.unmap()
+    buf.resize(96, 64)
+    assert buf.map().shape[:2] == (64, 96) and not buf.map().any()  # a resized buffer starts cleared
+    buf.unmap()
+    for i in range(2):
+        r.render(buf)
+        assert r.getSharedContext().mSubframeIndex == i + 1  # restarted
+    assert np.array_equal(buf.map().copy(), fresh_large)
+    buf.unmap()
+    buf.resize(64, 48)
+    for _ in range(3):
+        r.render(buf)
+    assert np.array_equal(buf.map().copy(), fresh_small)
+    buf.unmap()
+    buf.destroy()
