@@ -265,17 +265,6 @@ __device__ __forceinline__ uint32_t fetch_slots(WarpFetch& wf, uint32_t* head, u
     return slot;
 }
 
-// stage the first SB_TOP_SMEM nodes of a level-ordered BVH in shared memory (the top of the tree every ray walks)
-__device__ __forceinline__ void stage_top_nodes(uint4* dst, const WideNode* nodes, uint32_t numNodes)
-{
-#if SB_TOP_SMEM
-    const uint32_t words = min(uint32_t(SB_TOP_SMEM), numNodes) * 5u;
-    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x)
-        dst[i] = __ldg(reinterpret_cast<const uint4*>(nodes) + i);
-#endif
-}
-
-
 // ---- deferred primitive tests ---------------------------------------------------------------------------------
 // In the plain loop a lane tests a primitive as soon as a node visit queues one, so primitive tests run with whatever
 // few lanes happen to hold one (ncu: 4.7 of 32 lanes in the curve test of the hair scene, ~8 in the triangle test) while
@@ -302,9 +291,6 @@ __device__ __forceinline__ void stage_top_nodes(uint4* dst, const WideNode* node
 #ifndef SB_DEFER_TRIS_THRESH
 #define SB_DEFER_TRIS_THRESH 12
 #endif
-#ifndef SB_DEFER_PREFETCH
-#define SB_DEFER_PREFETCH 0
-#endif
 // all 32 lanes call this (it votes); returns whether the lane's traversal of the current BVH goes on
 template <bool ANY, bool STATS, bool CURVES, bool PF, int XU, int D, int THRESH>
 __device__ __forceinline__ bool trav_iter_defer(bool active, int phase, const SceneDev& S, Traversal& T, TravStack& K, uint32_t* dq, int& dc,
@@ -328,22 +314,6 @@ __device__ __forceinline__ bool trav_iter_defer(bool active, int phase, const Sc
             }
             trav_node<STATS, (SB_SMEM_STACK > 0), XU>(T, K, curvePhase ? S.segNodes : S.triNodes, ray, rp, st);
             haveNodes = T.ngroup.y > 0x00ffffffu || T.sp > 0;
-#if SB_DEFER_PREFETCH
-            if (T.tgroup.y != 0u)
-            {
-                const uint32_t pi = T.tgroup.x + prim_offset(T, bfind32(T.tgroup.y));
-                if (curvePhase)
-                {
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(&S.segs[pi].q[0]));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(&S.segs[pi].q[2]));
-                }
-                else
-                {
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(&S.tris[pi].v0));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(&S.tris[pi].e2));
-                }
-            }
-#endif
         }
         pend = T.tgroup.y != 0u || dc > 0;
         stuck = pend && (!haveNodes || (T.tgroup.y != 0u && dc == D));
@@ -379,12 +349,6 @@ __device__ __forceinline__ bool trav_iter_defer(bool active, int phase, const Sc
 #ifndef SB_EXTEND_MIN_BLOCKS
 #define SB_EXTEND_MIN_BLOCKS 8
 #endif
-#ifndef SB_CURVE_PREFETCH
-#define SB_CURVE_PREFETCH 0
-#endif
-#ifndef SB_EXTEND_HIT_SMEM
-#define SB_EXTEND_HIT_SMEM 0
-#endif
 // how the child-box bytes become floats (wide_node_hits<XU>), measured per kernel (profiles/r02_ab_experiments.txt,
 // r2t..r2x): fp16-pair unpack with the z planes of two children per half on the XU pipe for the closest-hit loop and the
 // one-ray-per-thread kernels (SB_SIMPLE_XU); byte permutes with the z pair of every child on the XU pipe for the any-hit
@@ -411,14 +375,7 @@ __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FramePa
     int phase = 0;
     Ray ray;
     RayPrep rp;
-#if SB_EXTEND_HIT_SMEM
-    // the hit record is cold state (written when a closer hit is accepted, read once at the end of the ray): it lives in
-    // shared memory (7-word stride: conflict-free) and its registers go to the traversal loop
-    __shared__ HitRec s_hit[kBlock];
-    HitRec& hit = s_hit[threadIdx.x];
-#else
     HitRec hit;
-#endif
     Traversal T;
     TravStack K;
     constexpr int kDeferDepth = CURVES ? SB_DEFER_CURVES : SB_DEFER_TRIS, kDeferThresh = CURVES ? SB_DEFER_CURVES_THRESH : SB_DEFER_TRIS_THRESH;
@@ -438,18 +395,6 @@ __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FramePa
     const uint32_t permBase = uint32_t(__cvta_generic_to_shared(s_perm));
 #else
     const uint32_t permBase = 0u;
-#endif
-#if SB_TOP_SMEM
-    __shared__ uint4 s_top[(CURVES ? 2 : 1) * SB_TOP_SMEM * 5];
-    stage_top_nodes(s_top, S.triNodes, S.numTriNodes);
-    if (CURVES)
-        stage_top_nodes(s_top + SB_TOP_SMEM * 5, S.segNodes, S.numSegNodes);
-    __syncthreads();
-    const uint4* topTri = s_top;
-    const uint4* topSeg = s_top + (CURVES ? SB_TOP_SMEM * 5 : 0);
-#else
-    const uint4* topTri = nullptr;
-    const uint4* topSeg = nullptr;
 #endif
     for (;;)
     {
@@ -486,9 +431,9 @@ __global__ void __launch_bounds__(kBlock, SB_EXTEND_MIN_BLOCKS) k_extend(FramePa
                 {
                 }
                 else if (phase == 0)
-                    more = trav_step<1, false, STATS, (SB_SMEM_STACK > 0), (SB_EXTEND_PREFETCH != 0), SB_EXTEND_XU>(T, K, S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, anyHit, &st, topTri);
+                    more = trav_step<1, false, STATS, (SB_SMEM_STACK > 0), (SB_EXTEND_PREFETCH != 0), SB_EXTEND_XU>(T, K, S.triNodes, S.tris, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
                 else if (CURVES && phase == 1)
-                    more = trav_step<2, false, STATS, (SB_SMEM_STACK > 0), (SB_CURVE_PREFETCH != 0), SB_EXTEND_XU>(T, K, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st, topSeg);
+                    more = trav_step<2, false, STATS, (SB_SMEM_STACK > 0), false, SB_EXTEND_XU>(T, K, S.segNodes, S.segs, kRayMaskPrimary, ray, rp, hit, anyHit, &st);
                 if (!more)
                 {
                     if (phase == 0 && haveSegs)
@@ -559,18 +504,6 @@ __global__ void __launch_bounds__(kBlock, SB_SHADOW_MIN_BLOCKS) k_shadow(SceneDe
 #else
     const uint32_t permBase = 0u;
 #endif
-#if SB_TOP_SMEM
-    __shared__ uint4 s_top[(CURVES ? 2 : 1) * SB_TOP_SMEM * 5];
-    stage_top_nodes(s_top, S.triNodes, S.numTriNodes);
-    if (CURVES)
-        stage_top_nodes(s_top + SB_TOP_SMEM * 5, S.segNodes, S.numSegNodes);
-    __syncthreads();
-    const uint4* topTri = s_top;
-    const uint4* topSeg = s_top + (CURVES ? SB_TOP_SMEM * 5 : 0);
-#else
-    const uint4* topTri = nullptr;
-    const uint4* topSeg = nullptr;
-#endif
     for (;;)
     {
         const uint32_t got = fetch_slots(wf, head, n, !active, Q.shO, Q.shD, Q.shC);
@@ -604,9 +537,9 @@ __global__ void __launch_bounds__(kBlock, SB_SHADOW_MIN_BLOCKS) k_shadow(SceneDe
                 {
                 }
                 else if (phase == 0)
-                    more = trav_step_unit<1, true, STATS, (SB_SMEM_STACK > 0), PF, SB_SHADOW_XU>(T, K, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st, topTri);
+                    more = trav_step_unit<1, true, STATS, (SB_SMEM_STACK > 0), PF, SB_SHADOW_XU>(T, K, S.triNodes, S.tris, kRayMaskShadow, ray, rp, hit, occluded, &st);
                 else if (CURVES && phase == 1)
-                    more = trav_step_unit<2, true, STATS, (SB_SMEM_STACK > 0), (SB_CURVE_PREFETCH != 0), SB_SHADOW_XU>(T, K, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st, topSeg);
+                    more = trav_step_unit<2, true, STATS, (SB_SMEM_STACK > 0), false, SB_SHADOW_XU>(T, K, S.segNodes, S.segs, kRayMaskShadow, ray, rp, hit, occluded, &st);
                 if (!more)
                 {
                     if (!occluded && phase == 0 && haveSegs)

@@ -23,22 +23,9 @@
 namespace sb
 {
 
-#ifndef SB_PRIM_NOALLOC
-#define SB_PRIM_NOALLOC 0 // 1: primitive records bypass L1 allocation (kept for the nodes); measured, see DESIGN.md
-#endif
 #if defined(__CUDA_ARCH__)
 #define SB_LDG4(p) __ldg(reinterpret_cast<const uint4*>(p))
-#if SB_PRIM_NOALLOC
-__device__ __forceinline__ float4 sb_ldg_noalloc(const float4* p)
-{
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-#define SB_LDGF4(p) sb_ldg_noalloc(reinterpret_cast<const float4*>(p))
-#else
 #define SB_LDGF4(p) __ldg(reinterpret_cast<const float4*>(p))
-#endif
 #else
 #define SB_LDG4(p) (*reinterpret_cast<const uint4*>(p))
 #define SB_LDGF4(p) (*reinterpret_cast<const float4*>(p))
@@ -423,9 +410,6 @@ SB_HD RayPrep prepare_ray(const float3& d, uint32_t permLutBase = 0u)
 // SB_SMEM_STACK > 0: the first SB_SMEM_STACK stack levels of the persistent kernels live in shared memory
 // (strided by the block size, bank-conflict free), deeper ones in local memory.
 constexpr int kTravBlock = 128; // threads per block of the kernels that use the shared-memory stack
-#ifndef SB_STACK_SEPARATE
-#define SB_STACK_SEPARATE 1
-#endif
 // The postponed node groups live in their own array (TravStack), NOT inside Traversal: with a dynamically indexed array
 // member nvcc keeps the whole object addressable and writes ngroup / tgroup / sp back to local memory after every
 // update (4 STL per node visit in the SASS of the persistent kernels, 31 M local stores per 7 M-ray launch in ncu).
@@ -441,15 +425,8 @@ struct Traversal
 #if defined(__CUDACC__)
     uint2* sstack; // this thread's column of the block's shared-memory stack (SSTACK traversals only)
 #endif
-#if !SB_STACK_SEPARATE
-    uint2 stack[kStackSize];
-#endif
 };
-#if SB_STACK_SEPARATE
 #define SB_TSTACK(T, K) (K).e
-#else
-#define SB_TSTACK(T, K) (T).stack
-#endif
 SB_HD void trav_init(Traversal& T)
 {
     T.ngroup.x = 0u;
@@ -464,21 +441,14 @@ SB_HD void trav_init(Traversal& T)
 //   trav_node : if the lane has no primitives pending, visit the next node (returns false when nothing is left)
 //   trav_prim : if the lane has primitives pending, test exactly one
 // KIND 1: triangles (prims = TriRec), KIND 2: curve segments (prims = SegRec).  ANY: shadow rays.
-#ifndef SB_PREFETCH_NEXT_NODE
-#define SB_PREFETCH_NEXT_NODE 0
-#endif
 #ifndef SB_SIMPLE_XU
 #define SB_SIMPLE_XU (kXuHalfUnpack | 0x24) // conversion mix of the byte conversions (wide_node_hits) in the one-ray-per-thread traversals
 #endif
 #ifndef SB_SIMPLE_PREFETCH
 #define SB_SIMPLE_PREFETCH 0 // next-triangle prefetch in the one-ray-per-thread closest-hit traversal (camera rays)
 #endif
-#ifndef SB_TOP_SMEM
-#define SB_TOP_SMEM 0 // number of top-level nodes (the first K of the level-ordered array) staged in shared memory
-#endif
 template <bool STATS, bool SSTACK = false, int XU = 0>
-SB_HD bool trav_node(Traversal& T, TravStack& K, const WideNode* __restrict__ nodes, const Ray& ray, const RayPrep& rp, TravStats* st,
-                     const uint4* __restrict__ topNodes = nullptr)
+SB_HD bool trav_node(Traversal& T, TravStack& K, const WideNode* __restrict__ nodes, const Ray& ray, const RayPrep& rp, TravStats* st)
 {
     if (T.ngroup.y <= 0x00ffffffu)
     {
@@ -520,39 +490,24 @@ SB_HD bool trav_node(Traversal& T, TravStack& K, const WideNode* __restrict__ no
     const uint32_t ni = T.ngroup.x + rel;
     const WideNode* np = nodes + ni;
     uint4 n0, n1, n2, n3, n4;
-#if defined(__CUDA_ARCH__) && SB_TOP_SMEM
-    if (SSTACK && ni < uint32_t(SB_TOP_SMEM))
-    {
-        // the hot top of the tree: a copy in shared memory (the persistent kernels stage it once per CTA)
-        const uint4* sp_ = topNodes + 5u * ni;
-        n0 = sp_[0];
-        n1 = sp_[1];
-        n2 = sp_[2];
-        n3 = sp_[3];
-        n4 = sp_[4];
-    }
-    else
-#endif
-    {
 #if defined(__CUDA_ARCH__) && SB_NODE96
-        uint4 unused;
-        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(n0.x), "=r"(n0.y), "=r"(n0.z), "=r"(n0.w), "=r"(n1.x), "=r"(n1.y), "=r"(n1.z), "=r"(n1.w)
-                     : "l"(&np->n0));
-        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(n2.x), "=r"(n2.y), "=r"(n2.z), "=r"(n2.w), "=r"(n3.x), "=r"(n3.y), "=r"(n3.z), "=r"(n3.w)
-                     : "l"(&np->n2));
-        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(n4.x), "=r"(n4.y), "=r"(n4.z), "=r"(n4.w), "=r"(unused.x), "=r"(unused.y), "=r"(unused.z), "=r"(unused.w)
-                     : "l"(&np->n4));
+    uint4 unused;
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(n0.x), "=r"(n0.y), "=r"(n0.z), "=r"(n0.w), "=r"(n1.x), "=r"(n1.y), "=r"(n1.z), "=r"(n1.w)
+                 : "l"(&np->n0));
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(n2.x), "=r"(n2.y), "=r"(n2.z), "=r"(n2.w), "=r"(n3.x), "=r"(n3.y), "=r"(n3.z), "=r"(n3.w)
+                 : "l"(&np->n2));
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(n4.x), "=r"(n4.y), "=r"(n4.z), "=r"(n4.w), "=r"(unused.x), "=r"(unused.y), "=r"(unused.z), "=r"(unused.w)
+                 : "l"(&np->n4));
 #else
-        n0 = SB_LDG4(&np->n0);
-        n1 = SB_LDG4(&np->n1);
-        n2 = SB_LDG4(&np->n2);
-        n3 = SB_LDG4(&np->n3);
-        n4 = SB_LDG4(&np->n4);
+    n0 = SB_LDG4(&np->n0);
+    n1 = SB_LDG4(&np->n1);
+    n2 = SB_LDG4(&np->n2);
+    n3 = SB_LDG4(&np->n3);
+    n4 = SB_LDG4(&np->n4);
 #endif
-    }
     if (STATS)
         st->nodes++;
     const uint32_t hm = wide_node_hits<XU>(n0, n1, n2, n3, n4, ray.o, rp.idir, rp.octinv4, rp.negx, rp.negy, rp.negz, ray.tmin, ray.tmax, rp.halfBias);
@@ -664,27 +619,15 @@ SB_HD bool trav_prim(Traversal& T, const void* __restrict__ prims, uint32_t rayM
 // Returns false when the traversal is finished; anyHit is set when an ANY query found an occluder.
 template <int KIND, bool ANY, bool STATS, bool SSTACK = false, bool PF = false, int XU = 0>
 SB_HD bool trav_step(Traversal& T, TravStack& K, const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask, Ray& ray,
-                     const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st, const uint4* __restrict__ topNodes = nullptr)
+                     const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st)
 {
     if (T.tgroup.y == 0u)
     {
-        if (!trav_node<STATS, SSTACK, XU>(T, K, nodes, ray, rp, st, topNodes))
+        if (!trav_node<STATS, SSTACK, XU>(T, K, nodes, ray, rp, st))
             return false;
     }
     if (T.tgroup.y != 0u)
     {
-#if defined(__CUDA_ARCH__) && SB_PREFETCH_NEXT_NODE
-        // the node this lane visits in its next iteration is already decided (the nearest remaining child of the current
-        // group): start its fetch before the primitive test, not after
-        if (PF && T.ngroup.y > 0x00ffffffu)
-        {
-            const uint32_t hits = T.ngroup.y;
-            const uint32_t slot = (bfind32(hits) - 24u) ^ (rp.octinv & 7u);
-            const WideNode* nx = nodes + (T.ngroup.x + popc32(hits & ~(0xffffffffu << slot) & 0xffu));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(&nx->n0));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(&nx->n4));
-        }
-#endif
         if (trav_prim<KIND, ANY, STATS, PF>(T, prims, rayMask, ray, hit, st))
         {
             anyHit = true;
@@ -699,7 +642,7 @@ SB_HD bool trav_step(Traversal& T, TravStack& K, const WideNode* __restrict__ no
 // slightly faster with the node+primitive shape above (profiles/r01_b_*).
 template <int KIND, bool ANY, bool STATS, bool SSTACK = false, bool PF = false, int XU = 0>
 SB_HD bool trav_step_unit(Traversal& T, TravStack& K, const WideNode* __restrict__ nodes, const void* __restrict__ prims, uint32_t rayMask, Ray& ray,
-                          const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st, const uint4* __restrict__ topNodes = nullptr)
+                          const RayPrep& rp, HitRec& hit, bool& anyHit, TravStats* st)
 {
     if (T.tgroup.y != 0u)
     {
@@ -710,7 +653,7 @@ SB_HD bool trav_step_unit(Traversal& T, TravStack& K, const WideNode* __restrict
         }
         return true;
     }
-    return trav_node<STATS, SSTACK, XU>(T, K, nodes, ray, rp, st, topNodes);
+    return trav_node<STATS, SSTACK, XU>(T, K, nodes, ray, rp, st);
 }
 
 // "While-while" step: ONE node visit, then ALL the primitives it queued.  The lanes of a warp meet again at every
