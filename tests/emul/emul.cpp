@@ -482,6 +482,25 @@ void emul_bsdf_batch(const sb_material* m, uint32_t n, const float* in, float* o
     }
 }
 
+// The octant permutation of the inner hit byte (traverse.cuh): the device reads the constexpr table, the host path of
+// permute_inner_hits computes it bit by bit.  Returns the number of (octant, byte) pairs on which they differ, plus
+// the table itself (2048 bytes) for the caller to check against its own definition.
+int emul_octant_perm_table(unsigned char* table)
+{
+    int bad = 0;
+#if SB_FIXED_BITS
+    const OctantPermLut lut;
+    for (uint32_t o = 0; o < 8u; ++o)
+        for (uint32_t x = 0; x < 256u; ++x)
+        {
+            table[o * 256u + x] = lut.v[o * 256u + x];
+            if (uint32_t(lut.v[o * 256u + x]) != permute_inner_hits(x, o << 8))
+                ++bad;
+        }
+#endif
+    return bad;
+}
+
 void emul_camera(const float* view, float fovY, float aspect, float* clipToView, float* viewToWorld)
 {
     clip_to_view_from_fov(fovY, aspect, clipToView);

@@ -32,6 +32,8 @@ def lib():
         _lib.emul_light_sample.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         _lib.emul_curve_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.emul_camera.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+        _lib.emul_octant_perm_table.argtypes = [C.c_void_p]
+        _lib.emul_octant_perm_table.restype = C.c_int
     return _lib
 
 
@@ -117,3 +119,10 @@ def camera(view, fov, aspect):
     v2w = np.zeros(16, dtype=np.float32)
     lib().emul_camera(view.ctypes.data, C.c_float(fov), C.c_float(aspect), c2v.ctypes.data, v2w.ctypes.data)
     return c2v, v2w
+
+
+def octant_perm_table():
+    """(mismatches between the device's constexpr table and the host's bit-by-bit permutation, the 8 x 256 table)"""
+    t = np.zeros(2048, np.uint8)
+    bad = lib().emul_octant_perm_table(t.ctypes.data)
+    return bad, t.reshape(8, 256)

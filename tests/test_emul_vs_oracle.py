@@ -224,3 +224,20 @@ def test_sample_stride_shards_sum_to_whole():
         _, S_g, _ = e.render(st, 32, 32, 4, chunk_max=4)
         S_sum += S_g
     np.testing.assert_allclose(S_sum, S_full, rtol=2e-6, atol=1e-9)
+
+
+def test_octant_permutation_table_of_the_fixed_bit_hit_mask():
+    """traverse.cuh: inner-child hit bits are gathered by SLOT and moved to traversal order (bit s -> bit s ^ octinv) by a
+    256-entry table per octant.  The device reads the table, the host emulation computes the permutation: both must
+    agree, and both must be the XOR permutation (an involution that keeps the population count)."""
+    from emul import pyemul
+
+    bad, t = pyemul.octant_perm_table()
+    assert bad == 0
+    x = np.arange(256)
+    for o in range(8):
+        want = np.zeros(256, np.int64)
+        for b in range(8):
+            want |= ((x >> b) & 1) << (b ^ o)
+        assert np.array_equal(t[o], want)
+        assert np.array_equal(t[o][t[o]], x)  # applying it twice is the identity
