@@ -392,7 +392,7 @@ def bench_scene(hx: Harness, key: str, steps: int, warmup: int, with_cpu: bool, 
                    "alg_bytes_per_ray": per_ray[trav], "avg_launch_ms": stage_ms[trav] / nl, "launches": stage_n[trav],
                    "share_of_step": stage_ms[trav] / total_ms}
             # what the memory system and the SMs actually did (north_star: achieved L2/HBM GB/s, SM issue utilisation)
-            for k in ("dram_gbs", "dram_frac_of_peak", "l2_gbs", "issue_active_pct", "warp_lanes_active", "source", "launch"):
+            for k in ("dram_gbs", "dram_frac_of_peak", "l2_gbs", "issue_active_pct", "warp_lanes_active", "l1_data_pipe_pct", "alu_pipe_pct", "source", "launch"):
                 if k in ncu:
                     out["ncu_" + k] = ncu[k]
             return out

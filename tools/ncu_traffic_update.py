@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 from ncu_summary import KEYS  # noqa: E402
 
-EXTRA = ["lts__t_sectors.sum", "lts__t_sectors.sum.per_second", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+EXTRA = ["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors.sum", "lts__t_sectors.sum.per_second", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
          "l1tex__throughput.avg.pct_of_peak_sustained_active", "sass__inst_executed_shared_loads", "sass__inst_executed_shared_stores",
          "dram__bytes.sum.per_second", "sm__cycles_elapsed.avg.per_second"]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
@@ -65,6 +65,8 @@ def main():
                    "l2_gbs": l2 / dur / 1e9, "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                    "warp_lanes_active": num("smsp__thread_inst_executed_per_inst_executed.ratio"),
                    "l1_hit_pct": num("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": num("lts__t_sector_hit_rate.pct"),
+                   "l1_data_pipe_pct": num("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+                   "alu_pipe_pct": num("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
                    "launch": f"{name.split('(')[0].replace('void ', '')}, bounce 1 of a 4-sample batch", "source": f"profiles/{tag}_{cfg}_{k}_full.txt"}
             traffic.setdefault(cfg, {})[k] = rec
             src = os.path.join(ROOT, "gpurun_out", f"{tag}_{cfg}_{k}_source.csv")
